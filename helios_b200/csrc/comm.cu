@@ -1,0 +1,166 @@
+// One-shot peer-memory all-reduce for wavelength sharding.
+//
+// The only exchange of a wavelength-sharded RT iteration is the sum over ranks of the per-interface
+// flux totals: 2*ninterface doubles (~1.6 kB), pure latency.  Instead of a ring/tree collective each
+// rank STOREs its partial vector straight into a slot of every peer's mailbox over NVLink (the
+// mailboxes are cudaIpc-mapped into every process), raises a sequence flag, waits for the peers'
+// flags and adds the world's slots in rank order.  One kernel, one NVLink round trip, and every rank
+// ends up with bitwise-identical totals (fixed summation order), so the replicated temperature update
+// cannot drift between ranks.  The reference has no counterpart (single GPU).
+#include "common.cuh"
+
+#define COMM_MAX_WORLD 16
+
+struct helios_comm_state {
+    int rank = 0, world = 1, slot = 0;
+    unsigned long long seq = 0;
+    // own mailbox: [2 banks][world][slot] doubles, then [world] flags (u64), flags padded to 128 B
+    void* own = nullptr;
+    void* peers[COMM_MAX_WORLD] = {nullptr};
+    bool opened[COMM_MAX_WORLD] = {false};
+    void** peers_dev = nullptr;
+    size_t data_bytes = 0;
+};
+
+struct CommPeers {
+    void* p[COMM_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_peer_allreduce(CommPeers peers, double* __restrict__ vec, int n, int rank, int world, int slot,
+                 size_t data_bytes, unsigned long long seq) {
+    const int bank = (int)(seq & 1ull);
+    // 1. scatter my partials into slot `rank` of every mailbox (my own included)
+    for (int k = threadIdx.x; k < n * world; k += blockDim.x) {
+        const int r = k / n, t = k - r * n;
+        double* data = reinterpret_cast<double*>(peers.p[r]);
+        data[((size_t)bank * world + rank) * slot + t] = vec[t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish: flag[rank] of every mailbox <- seq
+    if ((int)threadIdx.x < world) {
+        unsigned long long* flags =
+            reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peers.p[threadIdx.x]) + data_bytes);
+        st_flag(flags + 16 * rank, seq);
+    }
+    // 3. wait until every rank has published this round into MY mailbox
+    if ((int)threadIdx.x < world) {
+        const unsigned long long* flags =
+            reinterpret_cast<const unsigned long long*>(reinterpret_cast<char*>(peers.p[rank]) + data_bytes);
+        while (ld_flag(flags + 16 * threadIdx.x) < seq) {
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    // 4. add the world's slots in rank order
+    const volatile double* mine = reinterpret_cast<const volatile double*>(peers.p[rank]);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < world; r++) acc += mine[((size_t)bank * world + r) * slot + t];
+        vec[t] = acc;
+    }
+}
+
+extern "C" {
+
+int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles, unsigned char* handle_out) {
+    HCTX(ctx);
+    HARG(handle_out != nullptr && world >= 1 && world <= COMM_MAX_WORLD && rank >= 0 && rank < world &&
+         slot_doubles > 0);
+    static_assert(sizeof(cudaIpcMemHandle_t) == HELIOS_IPC_HANDLE_BYTES, "IPC handle size");
+    if (ctx->comm) {
+        helios_set_error("helios_comm_create: communicator already exists");
+        return HELIOS_ERR_STATE;
+    }
+    helios_comm_state* c = new helios_comm_state();
+    c->rank = rank;
+    c->world = world;
+    c->slot = slot_doubles;
+    c->data_bytes = (size_t)2 * world * slot_doubles * sizeof(double);
+    c->data_bytes = (c->data_bytes + 127) / 128 * 128;
+    const size_t total = c->data_bytes + (size_t)world * 128;
+    cudaError_t e = cudaMalloc(&c->own, total);
+    if (e != cudaSuccess) {
+        delete c;
+        return helios_fail_cuda(e, "cudaMalloc(mailbox)", __FILE__, __LINE__);
+    }
+    e = cudaMemset(c->own, 0, total);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->own);
+    if (e != cudaSuccess) {
+        cudaFree(c->own);
+        delete c;
+        return helios_fail_cuda(e, "mailbox setup", __FILE__, __LINE__);
+    }
+    memcpy(handle_out, &h, sizeof(h));
+    c->peers[rank] = c->own;
+    ctx->comm = c;
+    return HELIOS_OK;
+}
+
+int helios_comm_connect(helios_ctx* ctx, const unsigned char* handles) {
+    HCTX(ctx);
+    HARG(handles != nullptr);
+    helios_comm_state* c = ctx->comm;
+    if (!c) {
+        helios_set_error("helios_comm_connect: call helios_comm_create first");
+        return HELIOS_ERR_STATE;
+    }
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * HELIOS_IPC_HANDLE_BYTES, sizeof(h));
+        HCUDA(cudaIpcOpenMemHandle(&c->peers[r], h, cudaIpcMemLazyEnablePeerAccess));
+        c->opened[r] = true;
+    }
+    return HELIOS_OK;
+}
+
+int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n) {
+    HCTX(ctx);
+    helios_comm_state* c = ctx->comm;
+    if (!c) {
+        helios_set_error("helios_comm_allreduce_sum: no communicator");
+        return HELIOS_ERR_STATE;
+    }
+    HARG(vec != nullptr && n > 0 && n <= c->slot);
+    for (int r = 0; r < c->world; r++) {
+        if (c->peers[r] == nullptr) {
+            helios_set_error("helios_comm_allreduce_sum: peer %d not connected", r);
+            return HELIOS_ERR_STATE;
+        }
+    }
+    CommPeers p;
+    for (int r = 0; r < COMM_MAX_WORLD; r++) p.p[r] = c->peers[r];
+    c->seq++;
+    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(p, vec, n, c->rank, c->world, c->slot, c->data_bytes, c->seq);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_comm_destroy(helios_ctx* ctx) {
+    if (ctx == nullptr || ctx->comm == nullptr) return HELIOS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    helios_comm_state* c = ctx->comm;
+    for (int r = 0; r < c->world; r++)
+        if (c->opened[r] && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
+    if (c->own) cudaFree(c->own);
+    delete c;
+    ctx->comm = nullptr;
+    return HELIOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Shared definitions for libhelios_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include "../../include/helios_b200.h"
+
+// physical constants: the literals of the reference device code (K:36-41), so that both sides
+// evaluate with identical scalars.
+namespace hc {
+constexpr double PI = 3.141592653589793;
+constexpr double HCONST = 6.62607004e-27;
+constexpr double CSPEED = 29979245800.0;
+constexpr double KBOLTZMANN = 1.38064852e-16;
+constexpr double STEFANBOLTZMANN = 5.6703669999999995e-5;
+constexpr double AMU = 1.6605390666e-24;
+}  // namespace hc
+
+struct helios_comm_state;
+
+struct helios_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int num_sms = 0;
+    size_t l2_bytes = 0;
+    size_t total_mem = 0;
+    unsigned long long launches = 0;
+    size_t bytes_allocated = 0;
+    std::unordered_map<void*, size_t> allocs;
+    // small per-context scratch (reductions, flags)
+    double* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    helios_comm_state* comm = nullptr;
+    std::mutex mu;
+};
+
+struct helios_event {
+    cudaEvent_t ev = nullptr;
+    int device = 0;
+};
+
+void helios_set_error(const char* fmt, ...);
+int helios_fail_cuda(cudaError_t e, const char* what, const char* file, int line);
+// grows ctx->scratch to at least nbytes (stream-ordered with respect to ctx->stream users)
+int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out);
+
+#define HCUDA(call)                                                            \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return helios_fail_cuda(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define HARG(cond)                                                             \
+    do {                                                                       \
+        if (!(cond)) {                                                         \
+            helios_set_error("%s: invalid argument: %s", __func__, #cond);     \
+            return HELIOS_ERR_ARG;                                             \
+        }                                                                      \
+    } while (0)
+
+#define HCTX(ctx)                                                              \
+    do {                                                                       \
+        if ((ctx) == nullptr) {                                                \
+            helios_set_error("%s: null context", __func__);                    \
+            return HELIOS_ERR_ARG;                                             \
+        }                                                                      \
+        HCUDA(cudaSetDevice((ctx)->device));                                   \
+    } while (0)
+
+// after a <<<>>> launch
+#define HLAUNCHED(ctx)                                                         \
+    do {                                                                       \
+        (ctx)->launches++;                                                     \
+        HCUDA(cudaGetLastError());                                             \
+    } while (0)
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- device helpers ------------
+
+// fitting function for the E parameter (K:109-124)
+__device__ __forceinline__ double E_parameter(double w0, double g0, double i2s_transition) {
+    if (w0 > i2s_transition && g0 >= 0.0) {
+        return fmax(1.0, 1.225 - 0.1582 * g0 - 0.1777 * w0 - 0.07465 * (g0 * g0) + 0.2351 * w0 * g0 -
+                             0.05582 * (w0 * w0));
+    }
+    return 1.0;
+}

@@ -1,0 +1,514 @@
+// Band / Gauss-point flux integration, temperature stepping and the post-processing diagnostics.
+// From-scratch sm_100a kernels for K:2428-3139 of the reference.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// integrate_flux (K:2428-2513).  The reference runs ONE 1024-thread block that funnels every cell
+// through fp64 CAS-loop atomics.  Here:
+//   stage 1  grid (x-tiles, interfaces): a block stages XB*ny contiguous doubles of each of the three
+//            wg arrays through shared memory (coalesced), then one thread per bin adds its ny Gauss
+//            points in y order  -> F_*_band[i][x]
+//   stage 2  one block per interface: fixed-shape tree over x -> F_up_tot, F_down_tot, F_net
+// The summation order is fixed, so results are bitwise reproducible run to run.
+// ------------------------------------------------------------------------------------------------
+#define IF_THREADS 256
+
+__global__ void __launch_bounds__(IF_THREADS)
+k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict__ F_up_wg,
+                 const double* __restrict__ F_dir_wg, double* __restrict__ F_down_band,
+                 double* __restrict__ F_up_band, double* __restrict__ F_dir_band,
+                 const double* __restrict__ gauss_weight, int nbin, int ny, int xb) {
+    extern __shared__ double sm[];
+    const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
+    double* s_dn = sm;
+    double* s_up = sm + (size_t)xb * pitch;
+    double* s_dr = sm + (size_t)2 * xb * pitch;
+    const int i = blockIdx.y;
+    const int x0 = blockIdx.x * xb;
+    const int nx = min(xb, nbin - x0);
+    const size_t base = ((size_t)i * nbin + x0) * ny;
+    const int n = nx * ny;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int xl = k / ny, y = k - xl * ny;
+        const int d = xl * pitch + y;
+        s_dn[d] = F_down_wg[base + k];
+        s_up[d] = F_up_wg[base + k];
+        s_dr[d] = F_dir_wg[base + k];
+    }
+    __syncthreads();
+    for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
+        double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
+        for (int y = 0; y < ny; y++) {
+            const double hw = 0.5 * gauss_weight[y];
+            a_dr += hw * s_dr[xl * pitch + y];
+            a_up += hw * s_up[xl * pitch + y];
+            a_dn += hw * s_dn[xl * pitch + y];
+        }
+        const size_t o = (size_t)i * nbin + x0 + xl;
+        F_dir_band[o] = a_dr;
+        F_up_band[o] = a_up;
+        F_down_band[o] = a_dn;
+    }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(IF_THREADS)
+k_total_integrate(const double* __restrict__ deltalambda, const double* __restrict__ F_down_band,
+                  const double* __restrict__ F_up_band, const double* __restrict__ F_dir_band,
+                  double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net,
+                  int nbin) {
+    __shared__ double red[IF_THREADS];
+    const int i = blockIdx.x;
+    double up = 0.0, dn = 0.0;
+    for (int x = threadIdx.x; x < nbin; x += blockDim.x) {
+        const size_t o = (size_t)i * nbin + x;
+        up += F_up_band[o] * deltalambda[x];
+        dn += (F_dir_band[o] + F_down_band[o]) * deltalambda[x];
+    }
+    up = block_sum(up, red);
+    dn = block_sum(dn, red);
+    if (threadIdx.x == 0) {
+        F_up_tot[i] = up;
+        F_down_tot[i] = dn;
+        F_net[i] = up - dn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Temperature stepping (K:2606-2884).  One block; the reads of neighbouring temperatures, the
+// smoothing prefix sums and the temperature update are separated by block barriers (the reference
+// races across its 16-thread blocks when smoothing is on, K:2665-2669).
+// ------------------------------------------------------------------------------------------------
+struct TempScalars {
+    int itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, conv;
+    double f_factor, g, physical_tstep, local_limit, F_intern;
+};
+
+__global__ void __launch_bounds__(256)
+k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_net,
+            double* __restrict__ F_net_diff, double* __restrict__ tlay, const double* __restrict__ play,
+            const double* __restrict__ pint, int* __restrict__ abrt, double* __restrict__ T_store,
+            double* __restrict__ prefactor, const int* __restrict__ marked_red,
+            const double* __restrict__ F_add_heat_lay, const double* __restrict__ F_add_heat_sum,
+            double* __restrict__ F_smooth, double* __restrict__ F_smooth_sum,
+            const double* __restrict__ c_p_lay, const double* __restrict__ mmm_lay, TempScalars s) {
+    const int nl = s.numlayers;
+    // phase 1: flux divergence and smoothing force, from the OLD temperatures
+    for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+        F_net_diff[i] = F_net[i] - F_net[i + 1] + F_add_heat_lay[i];
+        if (s.smooth == 1) {
+            double t_mid = tlay[i];
+            if (play[i] < 1e6 && i < nl - 1 && i > 0) t_mid = (tlay[i - 1] + tlay[i + 1]) / 2.0;
+            F_smooth[i] = pow(t_mid - tlay[i], 7.0);
+        }
+    }
+    __syncthreads();
+    if (s.smooth == 1) {
+        // running sum in layer order (K:2668-2669), one thread: nl is ~100
+        if (threadIdx.x == 0) {
+            double acc = 0.0;
+            for (int j = 0; j < nl; j++) {
+                acc += F_smooth[j];
+                F_smooth_sum[j] = acc;
+            }
+        }
+        __syncthreads();
+    }
+    // phase 2: step every layer and the surface "ghost layer" i = nl
+    for (int i = threadIdx.x; i < nl + 1; i += blockDim.x) {
+        double combined;
+        if (i < nl) {
+            combined = F_net_diff[i] + F_smooth[i];
+        } else {
+            combined = s.F_intern - F_net[0];
+            if (s.conv == 0) {
+                if (fabs(s.F_intern - F_net[1]) / (F_down_tot[nl] + s.F_intern) > 0.5 * s.local_limit)
+                    combined = s.F_intern - F_net[1];
+            } else {
+                for (int j = 0; j < nl; j++) {
+                    if (marked_red[j] == 1) {
+                        combined = s.F_intern - F_net[j + 1];
+                        break;
+                    }
+                }
+            }
+        }
+        double delta_T = 0.0;
+        const double T_old = tlay[i];
+        if (s.conv == 0) {
+            if (s.physical_tstep == 0) {
+                if (s.itervalue == s.foreplay) prefactor[i] = 1e0;
+                if (s.itervalue == 10000) prefactor[i] = 1e-1;
+                double delta_t = 0.0;  // the reference leaves it uninitialised when combined == 0
+                if (combined != 0) delta_t = prefactor[i] * play[0] / pow(fabs(combined), 0.9);
+                delta_T = combined / (pint[0] - pint[1]) * delta_t;
+                if (fabs(delta_T) > 500.0) delta_T = 500.0 * combined / fabs(combined);
+                if (s.itervalue % s.adapt_interval == 0) T_store[i] = T_old;
+                if (s.itervalue % s.adapt_interval == s.adapt_interval - 1) {
+                    if (fabs(T_old - T_store[i]) < s.adapt_interval / 2.0 * fabs(delta_T)) prefactor[i] /= 1.5;
+                    else prefactor[i] *= 1.1;
+                }
+            } else {
+                const double delta_t = s.physical_tstep;
+                const int k = i < nl ? i : 0;
+                delta_T = s.g / (c_p_lay[k] / (mmm_lay[k] / hc::AMU)) * combined / (pint[k] - pint[k + 1]) * delta_t;
+            }
+            double T_new = T_old + delta_T;
+            if (s.no_atmo == 1 && i != nl) T_new = 1.001;
+            const double max_limit = s.dim * s.step - 1.001;
+            T_new = fmin(fmax(T_new, 1.001), max_limit);
+            tlay[i] = T_new;
+            bool ok;
+            if (i < nl)
+                ok = fabs(s.F_intern + F_add_heat_sum[i] + F_smooth_sum[i] - F_net[i + 1]) /
+                         (F_down_tot[nl] + s.F_intern) < s.local_limit;
+            else
+                ok = fabs(s.F_intern - F_net[0]) / (F_down_tot[nl] + s.F_intern) < s.local_limit;
+            abrt[i] = ok ? 1 : 0;
+        } else {
+            if (s.itervalue == 0) prefactor[i] = 1e-2;
+            if (s.itervalue == 6000) prefactor[i] = 1e-3;
+            double delta_t = 0.0;
+            if (combined != 0) delta_t = prefactor[i] * play[0] / pow(fabs(combined), 0.5);
+            delta_T = combined / (pint[0] - pint[1]) * delta_t;
+            if (fabs(delta_T) > 20.0) delta_T = 20.0 * combined / fabs(combined);
+            if (s.itervalue % s.adapt_interval == 0) T_store[i] = T_old;
+            if (s.itervalue % s.adapt_interval == s.adapt_interval - 1) {
+                if (fabs(T_old - T_store[i]) < s.adapt_interval / 2.0 * fabs(delta_T)) prefactor[i] /= 1.5;
+                else prefactor[i] *= 1.1;
+            }
+            tlay[i] = fmax(T_old + delta_T, 1.001);
+        }
+    }
+}
+
+// conv_temp_iter's smoothing branch differs slightly (no i > 0 guard in the reference, K:2808, which
+// reads tlay[-1]); the guarded form is used for both.
+
+__global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict__ out) {
+    __shared__ int red[256];
+    int a = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a += abrt[i];
+    red[threadIdx.x] = a;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------------
+// post-processing diagnostics (K:2888-3139)
+// ------------------------------------------------------------------------------------------------
+template <bool NONISO>
+__global__ void k_optdepth_trans(const double* __restrict__ tr_a, const double* __restrict__ tr_b,
+                                 double* __restrict__ trans_band, const double* __restrict__ dt_a,
+                                 const double* __restrict__ dt_b, double* __restrict__ dtau_band,
+                                 const double* __restrict__ gw, double* __restrict__ dtc,
+                                 const double* __restrict__ dtc_u, const double* __restrict__ dtc_l, int nbin,
+                                 int nlayer, int ny) {
+    const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (o >= (long long)nbin * nlayer) return;
+    double dsum = 0.0, tsum = 0.0;
+    const size_t base = (size_t)o * ny;
+    for (int y = 0; y < ny; y++) {
+        if (NONISO) {
+            dsum += 0.5 * gw[y] * (dt_a[base + y] + dt_b[base + y]);
+            tsum += 0.5 * gw[y] * (tr_a[base + y] * tr_b[base + y]);
+        } else {
+            dsum += 0.5 * gw[y] * dt_a[base + y];
+            tsum += 0.5 * gw[y] * tr_a[base + y];
+        }
+    }
+    dtau_band[o] = dsum;
+    trans_band[o] = tsum;
+    if (NONISO) dtc[o] = dtc_l[o] + dtc_u[o];
+}
+
+// contribution function: one thread per bin walks every Gauss column from the top, carrying the
+// transmission to TOA as a running product (the reference rebuilds that product for every layer,
+// O(nlayer^2 ny) per thread, K:2970-2979).
+template <bool NONISO>
+__global__ void k_contr_func(const double* __restrict__ tr_a, const double* __restrict__ tr_b,
+                             double* __restrict__ tw_band, double* __restrict__ cf_band,
+                             const double* __restrict__ gw, const double* __restrict__ planck_lay,
+                             double epsi, int nbin, int nlayer, int ny) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nbin) return;
+    for (int y = 0; y < ny; y++) {
+        double to_top = 1.0;
+        for (int i = nlayer - 1; i >= 0; i--) {
+            const size_t e = (size_t)y + (size_t)ny * x + (size_t)ny * nbin * i;
+            const double t = NONISO ? tr_a[e] * tr_b[e] : tr_a[e];
+            tw_band[x + (size_t)nbin * i] += 0.5 * gw[y] * (1.0 - t) * to_top;
+            to_top *= t;
+        }
+    }
+    for (int i = 0; i < nlayer; i++)
+        cf_band[x + (size_t)nbin * i] =
+            2.0 * hc::PI * epsi * planck_lay[i + (size_t)x * (nlayer + 2)] * tw_band[x + (size_t)nbin * i];
+}
+
+// K:294-329
+__device__ __forceinline__ double dB_dT(double lambda, double T) {
+    const double c3 = hc::CSPEED * hc::CSPEED * hc::CSPEED;
+    const double l2 = lambda * lambda;
+    const double l6 = l2 * l2 * l2;
+    const double D = 2.0 * hc::HCONST * c3 * hc::HCONST / (l6 * hc::KBOLTZMANN * (T * T));
+    const double ex = exp(hc::HCONST * hc::CSPEED / (lambda * hc::KBOLTZMANN * T));
+    return D * ex / ((ex - 1.0) * (ex - 1.0));
+}
+
+__device__ __forceinline__ double integrated_dB_dT(const double* __restrict__ kw, const double* __restrict__ ky,
+                                                   int ny, double lbot, double ltop, double T) {
+    double r = 0.0;
+    for (int y = 0; y < ny; y++) {
+        const double xx = (ky[y] - 0.5) * 2.0;
+        const double arg = (ltop - lbot) / 2.0 * xx + (ltop + lbot) / 2.0;
+        r += (ltop - lbot) / 2.0 * kw[y] * dB_dT(arg, T);
+    }
+    return r;
+}
+
+// one block per layer; the eight spectral sums are reduced in a fixed tree over the bins
+__global__ void __launch_bounds__(IF_THREADS)
+k_mean_opacities(double* __restrict__ planck_pl, double* __restrict__ ross_pl, double* __restrict__ planck_st,
+                 double* __restrict__ ross_st, const double* __restrict__ opac_wg_lay,
+                 const double* __restrict__ abs_cl, const double* __restrict__ mmm,
+                 const double* __restrict__ planck_lay, const double* __restrict__ interwave,
+                 const double* __restrict__ deltawave, const double* __restrict__ T_lay,
+                 const double* __restrict__ gw, const double* __restrict__ gy, double* __restrict__ opac_band,
+                 int nlayer, int nbin, int ny, double T_star) {
+    __shared__ double red[IF_THREADS];
+    const int i = blockIdx.x;
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const double Ti = T_lay[i];
+    for (int x = threadIdx.x; x < nbin; x += blockDim.x) {
+        double band = 0.0;
+        const size_t base = ((size_t)i * nbin + x) * ny;
+        for (int y = 0; y < ny; y++) band += 0.5 * gw[y] * opac_wg_lay[base + y];
+        opac_band[x + (size_t)nbin * i] = band;
+        const double k = band + abs_cl[x + (size_t)nbin * i] / mmm[i];
+        const double Bp = planck_lay[i + (size_t)x * (nlayer + 2)] * deltawave[x];
+        const double Bs = planck_lay[nlayer + (size_t)x * (nlayer + 2)] * deltawave[x];
+        const double dpl = integrated_dB_dT(gw, gy, ny, interwave[x], interwave[x + 1], Ti);
+        const double dst = integrated_dB_dT(gw, gy, ny, interwave[x], interwave[x + 1], T_star);
+        a[0] += k * Bp;  // planckband * deltawave grouped; agrees with K:3071 to rounding
+        a[1] += Bp;
+        a[2] += dpl;
+        if (k > 0) a[3] += dpl / k;
+        a[4] += k * Bs;
+        a[5] += Bs;
+        a[6] += dst;
+        if (k > 0) a[7] += dst / k;
+    }
+    for (int q = 0; q < 8; q++) a[q] = block_sum(a[q], red);
+    if (threadIdx.x == 0) {
+        planck_pl[i] = a[0] / a[1];
+        ross_pl[i] = a[2] / a[3];
+        if (Ti < 70) ross_pl[i] = -3;
+        planck_st[i] = a[4] / a[5];
+        ross_st[i] = a[6] / a[7];
+        if (T_star < 70) {
+            planck_st[i] = -3;
+            ross_st[i] = -3;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(IF_THREADS)
+k_integrate_beamflux(double* __restrict__ F_dir_tot, const double* __restrict__ F_dir_band,
+                     const double* __restrict__ deltalambda, int nbin) {
+    __shared__ double red[IF_THREADS];
+    const int i = blockIdx.x;
+    double acc = 0.0;
+    for (int x = threadIdx.x; x < nbin; x += blockDim.x) acc += F_dir_band[x + (size_t)nbin * i] * deltalambda[x];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) F_dir_tot[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, double* F_down_tot,
+                                 double* F_up_tot, double* F_net, const double* F_down_wg,
+                                 const double* F_up_wg, const double* F_dir_wg, double* F_down_band,
+                                 double* F_up_band, double* F_dir_band, const double* gauss_weight,
+                                 int nbin, int numinterfaces, int ny) {
+    HCTX(ctx);
+    HARG(deltalambda && F_down_tot && F_up_tot && F_net && F_down_wg && F_up_wg && F_dir_wg &&
+         F_down_band && F_up_band && F_dir_band && gauss_weight);
+    HARG(nbin > 0 && numinterfaces > 0 && ny > 0);
+    // bins per block: as many as fit in ~36 kB of shared memory, at most 256
+    int xb = (int)(36 * 1024 / (3 * sizeof(double) * (ny + 1)));
+    if (xb > 256) xb = 256;
+    if (xb < 1) {
+        helios_set_error("helios_integrate_flux_double: ny = %d too large", ny);
+        return HELIOS_ERR_ARG;
+    }
+    const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
+    dim3 grid(ceil_div(nbin, xb), numinterfaces);
+    k_band_integrate<<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band,
+                                                              F_up_band, F_dir_band, gauss_weight, nbin,
+                                                              ny, xb);
+    HLAUNCHED(ctx);
+    k_total_integrate<<<numinterfaces, IF_THREADS, 0, ctx->stream>>>(
+        deltalambda, F_down_band, F_up_band, F_dir_band, F_down_tot, F_up_tot, F_net, nbin);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                         const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                         const double* tint, const double* pint, int* abrt, double* T_store,
+                         double* deltat_prefactor, const double* F_add_heat_lay,
+                         const double* F_add_heat_sum, double* F_smooth, double* F_smooth_sum,
+                         const double* c_p_lay, const double* meanmolmass_lay, int itervalue,
+                         double f_factor, int foreplay, double g, int numlayers, double physical_tstep,
+                         double local_limit, int adapt_interval, int smooth, int dim, int step,
+                         double F_intern, int no_atmo) {
+    HCTX(ctx);
+    (void)F_up_tot; (void)tint;
+    HARG(F_down_tot && F_net && F_net_diff && tlay && play && pint && abrt && T_store && deltat_prefactor &&
+         F_add_heat_lay && F_add_heat_sum && F_smooth && F_smooth_sum);
+    HARG(physical_tstep == 0 || (c_p_lay != nullptr && meanmolmass_lay != nullptr));
+    HARG(numlayers > 1 && adapt_interval > 0);
+    TempScalars s{itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, 0,
+                  f_factor, g, physical_tstep, local_limit, F_intern};
+    k_temp_iter<<<1, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
+                                            deltat_prefactor, nullptr, F_add_heat_lay, F_add_heat_sum,
+                                            F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                          const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                          const double* pint, double* T_store, double* deltat_prefactor,
+                          const int* marked_red, const double* F_add_heat_lay, double* F_smooth,
+                          double* F_smooth_sum, int numlayers, int itervalue, int adapt_interval,
+                          int smooth, double F_intern) {
+    HCTX(ctx);
+    (void)F_up_tot; (void)F_down_tot;
+    HARG(F_net && F_net_diff && tlay && play && pint && T_store && deltat_prefactor && marked_red &&
+         F_add_heat_lay && F_smooth && F_smooth_sum);
+    HARG(numlayers > 1 && adapt_interval > 0);
+    TempScalars s{itervalue, 0, numlayers, adapt_interval, smooth, 0, 0, 0, 1, 0.0, 0.0, 0.0, 0.0, F_intern};
+    k_temp_iter<<<1, 256, 0, ctx->stream>>>(nullptr, F_net, F_net_diff, tlay, play, pint, nullptr, T_store,
+                                            deltat_prefactor, marked_red, F_add_heat_lay, nullptr, F_smooth,
+                                            F_smooth_sum, nullptr, nullptr, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev) {
+    HCTX(ctx);
+    HARG(abrt && sum_dev && n > 0);
+    k_abort_sum<<<1, 256, 0, ctx->stream>>>(abrt, n, sum_dev);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_integrate_optdepth_transmission_iso(helios_ctx* ctx, const double* trans_wg,
+                                               double* trans_band, const double* delta_tau_wg,
+                                               double* delta_tau_band, const double* gauss_weight,
+                                               int nbin, int nlayer, int ny) {
+    HCTX(ctx);
+    HARG(trans_wg && trans_band && delta_tau_wg && delta_tau_band && gauss_weight && nbin > 0 && nlayer > 0 && ny > 0);
+    const long long n = (long long)nbin * nlayer;
+    k_optdepth_trans<false><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
+        trans_wg, nullptr, trans_band, delta_tau_wg, nullptr, delta_tau_band, gauss_weight, nullptr, nullptr,
+        nullptr, nbin, nlayer, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_integrate_optdepth_transmission_noniso(
+    helios_ctx* ctx, const double* trans_wg_upper, const double* trans_wg_lower, double* trans_band,
+    const double* delta_tau_wg_upper, const double* delta_tau_wg_lower, double* delta_tau_band,
+    const double* gauss_weight, double* delta_tau_all_clouds, const double* delta_tau_all_clouds_upper,
+    const double* delta_tau_all_clouds_lower, int nbin, int nlayer, int ny) {
+    HCTX(ctx);
+    HARG(trans_wg_upper && trans_wg_lower && trans_band && delta_tau_wg_upper && delta_tau_wg_lower &&
+         delta_tau_band && gauss_weight && delta_tau_all_clouds && delta_tau_all_clouds_upper &&
+         delta_tau_all_clouds_lower && nbin > 0 && nlayer > 0 && ny > 0);
+    const long long n = (long long)nbin * nlayer;
+    k_optdepth_trans<true><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
+        trans_wg_upper, trans_wg_lower, trans_band, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_band,
+        gauss_weight, delta_tau_all_clouds, delta_tau_all_clouds_upper, delta_tau_all_clouds_lower, nbin,
+        nlayer, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_calc_contr_func_iso(helios_ctx* ctx, const double* trans_wg, double* trans_weight_band,
+                               double* contr_func_band, const double* gauss_weight,
+                               const double* planckband_lay, double epsi, int nbin, int nlayer, int ny) {
+    HCTX(ctx);
+    HARG(trans_wg && trans_weight_band && contr_func_band && gauss_weight && planckband_lay && nbin > 0 &&
+         nlayer > 0 && ny > 0);
+    k_contr_func<false><<<ceil_div(nbin, 64), 64, 0, ctx->stream>>>(
+        trans_wg, nullptr, trans_weight_band, contr_func_band, gauss_weight, planckband_lay, epsi, nbin,
+        nlayer, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_calc_contr_func_noniso(helios_ctx* ctx, const double* trans_wg_upper,
+                                  const double* trans_wg_lower, double* trans_weight_band,
+                                  double* contr_func_band, const double* gauss_weight,
+                                  const double* planckband_lay, double epsi, int nbin, int nlayer, int ny) {
+    HCTX(ctx);
+    HARG(trans_wg_upper && trans_wg_lower && trans_weight_band && contr_func_band && gauss_weight &&
+         planckband_lay && nbin > 0 && nlayer > 0 && ny > 0);
+    k_contr_func<true><<<ceil_div(nbin, 64), 64, 0, ctx->stream>>>(
+        trans_wg_upper, trans_wg_lower, trans_weight_band, contr_func_band, gauss_weight, planckband_lay,
+        epsi, nbin, nlayer, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_calc_mean_opacities(helios_ctx* ctx, double* planck_opac_T_pl, double* ross_opac_T_pl,
+                               double* planck_opac_T_star, double* ross_opac_T_star,
+                               const double* opac_wg_lay, const double* abs_cross_all_clouds_lay,
+                               const double* meanmolmass_lay, const double* planckband_lay,
+                               const double* opac_interwave, const double* opac_deltawave,
+                               const double* T_lay, const double* gauss_weight, const double* gauss_y,
+                               double* opac_band_lay, int nlayer, int nbin, int ny, double T_star) {
+    HCTX(ctx);
+    HARG(planck_opac_T_pl && ross_opac_T_pl && planck_opac_T_star && ross_opac_T_star && opac_wg_lay &&
+         abs_cross_all_clouds_lay && meanmolmass_lay && planckband_lay && opac_interwave && opac_deltawave &&
+         T_lay && gauss_weight && gauss_y && opac_band_lay && nlayer > 0 && nbin > 0 && ny > 0);
+    k_mean_opacities<<<nlayer, IF_THREADS, 0, ctx->stream>>>(
+        planck_opac_T_pl, ross_opac_T_pl, planck_opac_T_star, ross_opac_T_star, opac_wg_lay,
+        abs_cross_all_clouds_lay, meanmolmass_lay, planckband_lay, opac_interwave, opac_deltawave, T_lay,
+        gauss_weight, gauss_y, opac_band_lay, nlayer, nbin, ny, T_star);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_integrate_beamflux(helios_ctx* ctx, double* F_dir_tot, const double* F_dir_band,
+                              const double* deltalambda, const double* gauss_weight, int nbin,
+                              int numinterfaces) {
+    HCTX(ctx);
+    (void)gauss_weight;
+    HARG(F_dir_tot && F_dir_band && deltalambda && nbin > 0 && numinterfaces > 0);
+    k_integrate_beamflux<<<numinterfaces, IF_THREADS, 0, ctx->stream>>>(F_dir_tot, F_dir_band, deltalambda,
+                                                                        nbin);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+}  // extern "C"

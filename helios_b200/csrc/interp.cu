@@ -1,0 +1,421 @@
+// Planck table, stellar energy correction, temperature / Planck / opacity interpolation.
+// From-scratch sm_100a kernels for K:362-1011 and K:3209-3259 of the reference.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// Planck table (K:362-416).  One thread per table entry (x, row); rows 0..dim-1 have
+// T = 1 + row*step, row `dim` is the stellar temperature.  The 199-term series is summed in the
+// reference's order so that the table agrees to rounding.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double planck_series_term(int n, double y1, double y2) {
+    // K:95-105
+    const double dn = n;
+    const double d2 = dn * dn, d3 = dn * dn * dn, d4 = dn * dn * dn * dn;
+    return exp(-dn * y2) * ((y2 * y2 * y2) / dn + 3.0 * (y2 * y2) / d2 + 6.0 * y2 / d3 + 6.0 / d4) -
+           exp(-dn * y1) * ((y1 * y1 * y1) / dn + 3.0 * (y1 * y1) / d2 + 6.0 * y1 / d3 + 6.0 / d4);
+}
+
+__global__ void __launch_bounds__(256)
+k_plancktable(double* __restrict__ grid, const double* __restrict__ lambda_edge,
+              const double* __restrict__ deltalambda, int nwave, double Tstar, int dim, int step) {
+    const long long total = (long long)(dim + 1) * nwave;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int row = (int)(e / nwave);
+        const int x = (int)(e - (long long)row * nwave);
+        const double T = (row < dim) ? (double)(row * step + 1) : Tstar;
+        double acc = 0.0;
+        if (T > 0.01) {
+            const double kh = hc::KBOLTZMANN / hc::HCONST;
+            const double D = 2.0 * ((kh * kh * kh) * hc::KBOLTZMANN * (T * T * T * T)) /
+                             (hc::CSPEED * hc::CSPEED);
+            double y_top = hc::HCONST * hc::CSPEED / (lambda_edge[x + 1] * hc::KBOLTZMANN * T);
+            double y_bot = hc::HCONST * hc::CSPEED / (lambda_edge[x] * hc::KBOLTZMANN * T);
+            if (y_bot < y_top) {
+                const double s = y_top;
+                y_top = y_bot;
+                y_bot = s;
+            }
+            for (int n = 1; n < 200; n++) acc += D * planck_series_term(n, y_bot, y_top);
+        }
+        grid[e] = acc / deltalambda[x];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stellar energy correction (K:420-468): one block sums the incident flux in a fixed order,
+// a second kernel rescales.  (The reference lets every thread redo the whole O(nbin) sum.)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_inc_energy_sum(const double* __restrict__ planck_grid, const double* __restrict__ starflux,
+                 const double* __restrict__ deltalambda, int realstar, int nwave, double Tstar, int dim,
+                 double* __restrict__ corr_out) {
+    __shared__ double red[1024];
+    double acc = 0.0;
+    for (int x = threadIdx.x; x < nwave; x += blockDim.x) {
+        acc += realstar == 1 ? deltalambda[x] * starflux[x]
+                             : deltalambda[x] * hc::PI * planck_grid[x + (size_t)dim * nwave];
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double theo = hc::STEFANBOLTZMANN * pow(Tstar, 4.0);
+        corr_out[0] = theo / red[0];
+    }
+}
+
+__global__ void k_inc_energy_scale(double* __restrict__ planck_grid, double* __restrict__ starflux,
+                                   int realstar, int nwave, int dim, const double* __restrict__ corr) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nwave) return;
+    const double f = corr[0];
+    if (realstar == 1) starflux[x] *= f;
+    else planck_grid[x + (size_t)dim * nwave] *= f;
+}
+
+// ------------------------------------------------------------------------------------------
+// temp_inter (K:496-520)
+// ------------------------------------------------------------------------------------------
+__global__ void k_temp_inter(const double* __restrict__ tlay, double* __restrict__ tint, int nint) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nint) return;
+    if (i == 0) tint[i] = tlay[i] - 0.5 * (tlay[i + 1] - tlay[i]);
+    else if (i == nint - 1) tint[i] = tlay[i - 1] + 0.5 * (tlay[i - 1] - tlay[i - 2]);
+    else tint[i] = tlay[i - 1] + 0.5 * (tlay[i] - tlay[i - 1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Planck interpolation (K:923-1011).  Output layout is the reference's [x][i] (i fastest); a
+// 32x32 shared tile turns the x-coalesced table reads into i-coalesced stores.
+//   mode 0: layer version, rows i<nl from temp[i], row nl = star slot, row nl+1 = temp[nl] (BOA)
+//   mode 1: interface version, rows i<nrows from temp[i]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_planck_interpol(const double* __restrict__ temp, double* __restrict__ out,
+                  const double* __restrict__ planck_grid, const double* __restrict__ starflux,
+                  int realstar, int mode, int nl, int nrows, int nwave, int dim, int step) {
+    __shared__ double tile[32][33];
+    const int x0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, x = x0 + tx;
+        double v = 0.0;
+        if (i < nrows && x < nwave) {
+            if (mode == 0 && i == nl) {
+                v = realstar == 1 ? starflux[x] / hc::PI : planck_grid[x + (size_t)dim * nwave];
+            } else {
+                const double Ti = (mode == 0 && i == nl + 1) ? temp[nl] : temp[i];
+                double t = (Ti - 1.0) / step;
+                t = fmax(0.001, fmin(dim - 1.001, t));
+                const int tdown = (int)floor(t), tup = (int)ceil(t);
+                if (tdown != tup)
+                    v = planck_grid[x + (size_t)tdown * nwave] * (tup - t) +
+                        planck_grid[x + (size_t)tup * nwave] * (t - tdown);
+                else
+                    v = planck_grid[x + (size_t)tdown * nwave];
+            }
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, i = i0 + tx;
+        if (x < nwave && i < nrows) out[i + (size_t)x * nrows] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// (P,T) table interpolation (K:524-645, 649-919, 3209-3259).
+// A tiny prep kernel resolves each layer's box once (the reference recomputes the log10 of the
+// grid ends in every thread, K:545-554); the gather kernel then streams the four table rows of
+// that box, which are contiguous nbin*ny-long vectors, into the output row.
+// ------------------------------------------------------------------------------------------
+struct PTBox {
+    double p, t;
+    int pdown, pup, tdown, tup;
+};
+
+// clamp_mode 0: [0.001, n-1.001] (K:549, 556);  1: [0, n-1] (K:3233, 3238)
+__global__ void k_pt_prep(const double* __restrict__ temp, const double* __restrict__ press,
+                          const double* __restrict__ gtemp, const double* __restrict__ gpress, int ntemp,
+                          int npress, int n, int clamp_mode, int log_t, PTBox* __restrict__ box) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t;
+    if (log_t) {
+        const double dT = (log10(gtemp[ntemp - 1]) - log10(gtemp[0])) / (ntemp - 1.0);
+        t = (log10(temp[i]) - log10(gtemp[0])) / dT;
+    } else {
+        const double dT = (gtemp[ntemp - 1] - gtemp[0]) / (ntemp - 1.0);
+        t = (temp[i] - gtemp[0]) / dT;
+    }
+    const double dP = (log10(gpress[npress - 1]) - log10(gpress[0])) / (npress - 1.0);
+    double p = (log10(press[i]) - log10(gpress[0])) / dP;
+    if (clamp_mode == 0) {
+        t = fmin(ntemp - 1.001, fmax(0.001, t));
+        p = fmin(npress - 1.001, fmax(0.001, p));
+    } else {
+        t = fmin(ntemp - 1.0, fmax(0.0, t));
+        p = fmin(npress - 1.0, fmax(0.0, p));
+    }
+    PTBox b;
+    b.p = p;
+    b.t = t;
+    b.tdown = (int)floor(t);
+    b.tup = (int)ceil(t);
+    b.pdown = (int)floor(p);
+    b.pup = (int)ceil(p);
+    box[i] = b;
+}
+
+// the four-branch bilinear form of K:561-608 / K:613-645
+__device__ __forceinline__ double bilin4(double dd, double ud, double du, double uu, const PTBox& b) {
+    const bool pe = b.pdown == b.pup, te = b.tdown == b.tup;
+    if (!pe && !te)
+        return dd * (b.pup - b.p) * (b.tup - b.t) + ud * (b.p - b.pdown) * (b.tup - b.t) +
+               du * (b.pup - b.p) * (b.t - b.tdown) + uu * (b.p - b.pdown) * (b.t - b.tdown);
+    if (te && !pe) return dd * (b.pup - b.p) + ud * (b.p - b.pdown);
+    if (pe && !te) return dd * (b.tup - b.t) + du * (b.t - b.tdown);
+    return dd;
+}
+
+// out[i][c] for c in [0, rowlen), table[t][p][c]; optional second table (cross sections)
+__global__ void __launch_bounds__(256)
+k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, double* __restrict__ out,
+            int rowlen, const double* __restrict__ table2, double* __restrict__ out2, int rowlen2,
+            int npress) {
+    const int i = blockIdx.y;
+    const PTBox b = box[i];
+    const size_t r_dd = (size_t)b.pdown + (size_t)npress * b.tdown;
+    const size_t r_ud = (size_t)b.pup + (size_t)npress * b.tdown;
+    const size_t r_du = (size_t)b.pdown + (size_t)npress * b.tup;
+    const size_t r_uu = (size_t)b.pup + (size_t)npress * b.tup;
+    {
+        const double* __restrict__ t_dd = table + r_dd * rowlen;
+        const double* __restrict__ t_ud = table + r_ud * rowlen;
+        const double* __restrict__ t_du = table + r_du * rowlen;
+        const double* __restrict__ t_uu = table + r_uu * rowlen;
+        double* __restrict__ o = out + (size_t)i * rowlen;
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < rowlen; c += gridDim.x * blockDim.x)
+            o[c] = bilin4(__ldg(t_dd + c), __ldg(t_ud + c), __ldg(t_du + c), __ldg(t_uu + c), b);
+    }
+    if (table2 != nullptr) {
+        const double* __restrict__ t_dd = table2 + r_dd * rowlen2;
+        const double* __restrict__ t_ud = table2 + r_ud * rowlen2;
+        const double* __restrict__ t_du = table2 + r_du * rowlen2;
+        const double* __restrict__ t_uu = table2 + r_uu * rowlen2;
+        double* __restrict__ o = out2 + (size_t)i * rowlen2;
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < rowlen2; c += gridDim.x * blockDim.x)
+            o[c] = bilin4(__ldg(t_dd + c), __ldg(t_ud + c), __ldg(t_du + c), __ldg(t_uu + c), b);
+    }
+}
+
+// scalar tables tab[p + npress*t] (K:649-919)
+__global__ void k_pt_scalar(const double* __restrict__ temp, const double* __restrict__ press,
+                            const double* __restrict__ gtemp, const double* __restrict__ gpress, int ntemp,
+                            int npress, int n, int log_t, const double* __restrict__ tab,
+                            double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t;
+    if (log_t) {
+        const double dT = (log10(gtemp[ntemp - 1]) - log10(gtemp[0])) / (ntemp - 1.0);
+        t = (log10(temp[i]) - log10(gtemp[0])) / dT;
+    } else {
+        const double dT = (gtemp[ntemp - 1] - gtemp[0]) / (ntemp - 1.0);
+        t = (temp[i] - gtemp[0]) / dT;
+    }
+    const double dP = (log10(gpress[npress - 1]) - log10(gpress[0])) / (npress - 1.0);
+    double p = (log10(press[i]) - log10(gpress[0])) / dP;
+    PTBox b;
+    b.t = fmin(ntemp - 1.001, fmax(0.001, t));
+    b.p = fmin(npress - 1.001, fmax(0.001, p));
+    b.tdown = (int)floor(b.t);
+    b.tup = (int)ceil(b.t);
+    b.pdown = (int)floor(b.p);
+    b.pup = (int)ceil(b.p);
+    out[i] = bilin4(tab[b.pdown + npress * b.tdown], tab[b.pup + npress * b.tdown],
+                    tab[b.pdown + npress * b.tup], tab[b.pup + npress * b.tup], b);
+}
+
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int helios_plancktable(helios_ctx* ctx, double* planck_grid, const double* lambda_edge,
+                       const double* deltalambda, int nwave, double Tstar, int dim, int step) {
+    HCTX(ctx);
+    HARG(planck_grid && lambda_edge && deltalambda && nwave > 0 && dim > 0 && step > 0);
+    const long long total = (long long)(dim + 1) * nwave;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->num_sms * 64;
+    if (blocks > cap) blocks = cap;
+    k_plancktable<<<(int)blocks, 256, 0, ctx->stream>>>(planck_grid, lambda_edge, deltalambda, nwave,
+                                                        Tstar, dim, step);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_corr_inc_energy(helios_ctx* ctx, double* planck_grid, double* starflux,
+                           const double* deltalambda, int realstar, int nwave, double Tstar, int dim,
+                           double* corr_factor_host) {
+    HCTX(ctx);
+    HARG(planck_grid && deltalambda && nwave > 0 && dim > 0);
+    HARG(realstar == 0 || starflux != nullptr);
+    double* scratch = nullptr;
+    int rc = helios_ctx_scratch(ctx, sizeof(double), &scratch);
+    if (rc) return rc;
+    k_inc_energy_sum<<<1, 1024, 0, ctx->stream>>>(planck_grid, starflux, deltalambda, realstar, nwave,
+                                                  Tstar, dim, scratch);
+    HLAUNCHED(ctx);
+    k_inc_energy_scale<<<ceil_div(nwave, 256), 256, 0, ctx->stream>>>(planck_grid, starflux, realstar,
+                                                                      nwave, dim, scratch);
+    HLAUNCHED(ctx);
+    if (corr_factor_host) {
+        HCUDA(cudaMemcpyAsync(corr_factor_host, scratch, sizeof(double), cudaMemcpyDeviceToHost,
+                              ctx->stream));
+        HCUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return HELIOS_OK;
+}
+
+int helios_temp_inter(helios_ctx* ctx, const double* tlay, double* tint, int numinterfaces) {
+    HCTX(ctx);
+    HARG(tlay && tint && numinterfaces >= 3);
+    k_temp_inter<<<ceil_div(numinterfaces, 128), 128, 0, ctx->stream>>>(tlay, tint, numinterfaces);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_planck_interpol_layer(helios_ctx* ctx, const double* temp, double* planckband_lay,
+                                 const double* planck_grid, const double* starflux, int realstar,
+                                 int numlayers, int nwave, int dim, int step) {
+    HCTX(ctx);
+    HARG(temp && planckband_lay && planck_grid && numlayers > 0 && nwave > 0 && dim > 1 && step > 0);
+    HARG(realstar == 0 || starflux != nullptr);
+    const int nrows = numlayers + 2;
+    dim3 grid(ceil_div(nwave, 32), ceil_div(nrows, 32));
+    k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_lay, planck_grid, starflux,
+                                                     realstar, 0, numlayers, nrows, nwave, dim, step);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_planck_interpol_interface(helios_ctx* ctx, const double* temp, double* planckband_int,
+                                     const double* planck_grid, int numinterfaces, int nwave, int dim,
+                                     int step) {
+    HCTX(ctx);
+    HARG(temp && planckband_int && planck_grid && numinterfaces > 0 && nwave > 0 && dim > 1 && step > 0);
+    dim3 grid(ceil_div(nwave, 32), ceil_div(numinterfaces, 32));
+    k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_int, planck_grid, nullptr, 0, 1, 0,
+                                                     numinterfaces, nwave, dim, step);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gtemp, const double* press,
+                           const double* gpress, const double* table, double* out, int rowlen,
+                           const double* table2, double* out2, int rowlen2, int npress, int ntemp, int n,
+                           int clamp_mode) {
+    double* scratch = nullptr;
+    int rc = helios_ctx_scratch(ctx, sizeof(PTBox) * (size_t)n + 64, &scratch);
+    if (rc) return rc;
+    // keep clear of the first 64 bytes, which small reductions use
+    PTBox* box = reinterpret_cast<PTBox*>(reinterpret_cast<char*>(scratch) + 64);
+    k_pt_prep<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
+                                                         clamp_mode, 0, box);
+    HLAUNCHED(ctx);
+    int bx = ceil_div(rowlen, 256);
+    const int cap = (ctx->num_sms * 8 + n - 1) / n;
+    if (bx > cap) bx = cap > 0 ? cap : 1;
+    dim3 grid(bx, n);
+    k_pt_gather<<<grid, 256, 0, ctx->stream>>>(box, table, out, rowlen, table2, out2, rowlen2, npress);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_opac_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                         const double* press, const double* opacpress, const double* ktable,
+                         double* opac, const double* crosstable, double* scat_cross, int npress,
+                         int ntemp, int ny, int nbin, int nlay_or_nint) {
+    HCTX(ctx);
+    HARG(temp && opactemp && press && opacpress && ktable && opac && crosstable && scat_cross);
+    HARG(npress > 1 && ntemp > 1 && ny > 0 && nbin > 0 && nlay_or_nint > 0);
+    return pt_table_interp(ctx, temp, opactemp, press, opacpress, ktable, opac, ny * nbin, crosstable,
+                           scat_cross, nbin, npress, ntemp, nlay_or_nint, 0);
+}
+
+int helios_opac_species_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                                 const double* press, const double* opacpress,
+                                 const double* opac_opacity_pretab, double* opac_spec_wg, int npress,
+                                 int ntemp, int ny, int nbin, int nlay_or_nint) {
+    HCTX(ctx);
+    HARG(temp && opactemp && press && opacpress && opac_opacity_pretab && opac_spec_wg);
+    HARG(npress > 1 && ntemp > 1 && ny > 0 && nbin > 0 && nlay_or_nint > 0);
+    return pt_table_interp(ctx, temp, opactemp, press, opacpress, opac_opacity_pretab, opac_spec_wg,
+                           ny * nbin, nullptr, nullptr, 0, npress, ntemp, nlay_or_nint, 1);
+}
+
+static int pt_scalar(helios_ctx* ctx, const double* temp, const double* gtemp, const double* press,
+                     const double* gpress, double* out, const double* tab, int npress, int ntemp, int n,
+                     int log_t) {
+    k_pt_scalar<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
+                                                           log_t, tab, out);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+#define SCALAR_ARGS_OK(t, gt, p, gp, o, tab, np, nt, n) \
+    HARG(t && gt && p && gp && o && tab && np > 1 && nt > 1 && n > 0)
+
+int helios_meanmolmass_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                                double* meanmolmass, const double* opac_meanmass, const double* press,
+                                const double* opacpress, int npress, int ntemp, int ninterface) {
+    HCTX(ctx);
+    SCALAR_ARGS_OK(temp, opactemp, press, opacpress, meanmolmass, opac_meanmass, npress, ntemp, ninterface);
+    return pt_scalar(ctx, temp, opactemp, press, opacpress, meanmolmass, opac_meanmass, npress, ntemp,
+                     ninterface, 0);
+}
+
+int helios_kappa_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                          const double* press, const double* entr_press, double* kappa,
+                          const double* entr_kappa, int entr_npress, int entr_ntemp, int nlay_or_nint) {
+    HCTX(ctx);
+    SCALAR_ARGS_OK(temp, entr_temp, press, entr_press, kappa, entr_kappa, entr_npress, entr_ntemp,
+                   nlay_or_nint);
+    return pt_scalar(ctx, temp, entr_temp, press, entr_press, kappa, entr_kappa, entr_npress, entr_ntemp,
+                     nlay_or_nint, 0);
+}
+
+int helios_cp_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp, const double* press,
+                       const double* entr_press, double* cp_lay, const double* entr_cp, int entr_npress,
+                       int entr_ntemp, int nlayer) {
+    HCTX(ctx);
+    SCALAR_ARGS_OK(temp, entr_temp, press, entr_press, cp_lay, entr_cp, entr_npress, entr_ntemp, nlayer);
+    return pt_scalar(ctx, temp, entr_temp, press, entr_press, cp_lay, entr_cp, entr_npress, entr_ntemp,
+                     nlayer, 1);
+}
+
+int helios_entropy_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                            const double* press, const double* entr_press, double* entropy,
+                            const double* entr_entropy, int entr_npress, int entr_ntemp, int nlayer) {
+    HCTX(ctx);
+    SCALAR_ARGS_OK(temp, entr_temp, press, entr_press, entropy, entr_entropy, entr_npress, entr_ntemp,
+                   nlayer);
+    return pt_scalar(ctx, temp, entr_temp, press, entr_press, entropy, entr_entropy, entr_npress,
+                     entr_ntemp, nlayer, 1);
+}
+
+int helios_phase_number_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                                 const double* press, const double* entr_press, double* state,
+                                 const double* entr_state, int entr_npress, int entr_ntemp, int nlayer) {
+    HCTX(ctx);
+    SCALAR_ARGS_OK(temp, entr_temp, press, entr_press, state, entr_state, entr_npress, entr_ntemp, nlayer);
+    return pt_scalar(ctx, temp, entr_temp, press, entr_press, state, entr_state, entr_npress, entr_ntemp,
+                     nlayer, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// Context, buffer and event management of libhelios_b200.so.
+// Replaces pycuda.autoinit / gpuarray.to_gpu / cuda.mem_alloc / .get() / cuda.Event of the
+// reference (C:24, Q:463-665, C:838-841).  The library owns every device allocation.
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void helios_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int helios_fail_cuda(cudaError_t e, const char* what, const char* file, int line) {
+    helios_set_error("CUDA error %d (%s) in `%s` at %s:%d", (int)e, cudaGetErrorString(e), what, file,
+                     line);
+    // clear the sticky-free error state so that later calls report their own failures
+    cudaGetLastError();
+    return e == cudaErrorMemoryAllocation ? HELIOS_ERR_NOMEM : HELIOS_ERR_CUDA;
+}
+
+extern "C" {
+
+int helios_abi_version(void) { return HELIOS_ABI_VERSION; }
+
+const char* helios_last_error(void) { return g_err; }
+
+int helios_device_count(int* count) {
+    HARG(count != nullptr);
+    HCUDA(cudaGetDeviceCount(count));
+    return HELIOS_OK;
+}
+
+int helios_ctx_create(int device, helios_ctx** out) {
+    HARG(out != nullptr);
+    int n = 0;
+    HCUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        helios_set_error("helios_ctx_create: device %d out of range (%d visible)", device, n);
+        return HELIOS_ERR_ARG;
+    }
+    HCUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HCUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        helios_set_error("helios_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                         device, prop.major, prop.minor);
+        return HELIOS_ERR_STATE;
+    }
+    helios_ctx* ctx = new helios_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    ctx->total_mem = prop.totalGlobalMem;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return helios_fail_cuda(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return HELIOS_OK;
+}
+
+int helios_comm_destroy(helios_ctx* ctx);
+
+int helios_ctx_destroy(helios_ctx* ctx) {
+    if (ctx == nullptr) return HELIOS_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm) helios_comm_destroy(ctx);
+    for (auto& kv : ctx->allocs) cudaFree(kv.first);
+    ctx->allocs.clear();
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return HELIOS_OK;
+}
+
+int helios_ctx_set_stream(helios_ctx* ctx, void* cuda_stream) {
+    HCTX(ctx);
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return HELIOS_OK;
+}
+
+int helios_ctx_get_stream(helios_ctx* ctx, void** cuda_stream) {
+    HCTX(ctx);
+    HARG(cuda_stream != nullptr);
+    *cuda_stream = (void*)ctx->stream;
+    return HELIOS_OK;
+}
+
+int helios_ctx_sync(helios_ctx* ctx) {
+    HCTX(ctx);
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_ctx_device_info(helios_ctx* ctx, int* num_sms, size_t* l2_bytes, size_t* total_mem) {
+    HCTX(ctx);
+    if (num_sms) *num_sms = ctx->num_sms;
+    if (l2_bytes) *l2_bytes = ctx->l2_bytes;
+    if (total_mem) *total_mem = ctx->total_mem;
+    return HELIOS_OK;
+}
+
+int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count) {
+    HCTX(ctx);
+    HARG(count != nullptr);
+    *count = ctx->launches;
+    return HELIOS_OK;
+}
+
+int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes) {
+    HCTX(ctx);
+    HARG(nbytes != nullptr);
+    *nbytes = ctx->bytes_allocated;
+    return HELIOS_OK;
+}
+
+int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr) {
+    HCTX(ctx);
+    HARG(dptr != nullptr);
+    void* p = nullptr;
+    // zero-sized arrays exist in the reference (e.g. empty entr_* tables, Q:474-475)
+    size_t n = nbytes ? nbytes : 8;
+    HCUDA(cudaMalloc(&p, n));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->allocs[p] = n;
+    ctx->bytes_allocated += n;
+    *dptr = p;
+    return HELIOS_OK;
+}
+
+int helios_buf_free(helios_ctx* ctx, void* dptr) {
+    HCTX(ctx);
+    if (dptr == nullptr) return HELIOS_OK;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->allocs.find(dptr);
+        if (it == ctx->allocs.end()) {
+            helios_set_error("helios_buf_free: %p was not allocated by this context", dptr);
+            return HELIOS_ERR_ARG;
+        }
+        ctx->bytes_allocated -= it->second;
+        ctx->allocs.erase(it);
+    }
+    // kernels still in flight on the stream may use the buffer
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    HCUDA(cudaFree(dptr));
+    return HELIOS_OK;
+}
+
+int helios_buf_h2d(helios_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dst_dev != nullptr && src_host != nullptr);
+    HCUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    // the caller may reuse/free the (pageable) host array right away, as with gpuarray.to_gpu
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_buf_d2h(helios_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dst_host != nullptr && src_dev != nullptr);
+    HCUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_buf_h2d_async(helios_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dst_dev != nullptr && src_host != nullptr);
+    HCUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_buf_d2h_async(helios_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dst_host != nullptr && src_dev != nullptr);
+    HCUDA(cudaMemcpyAsync(dst_host, src_dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_buf_d2d(helios_ctx* ctx, void* dst_dev, const void* src_dev, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dst_dev != nullptr && src_dev != nullptr);
+    HCUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_buf_zero(helios_ctx* ctx, void* dptr, size_t nbytes) {
+    HCTX(ctx);
+    if (nbytes == 0) return HELIOS_OK;
+    HARG(dptr != nullptr);
+    HCUDA(cudaMemsetAsync(dptr, 0, nbytes, ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_host_alloc(size_t nbytes, void** hptr) {
+    HARG(hptr != nullptr);
+    HCUDA(cudaMallocHost(hptr, nbytes ? nbytes : 8));
+    return HELIOS_OK;
+}
+
+int helios_host_free(void* hptr) {
+    if (hptr == nullptr) return HELIOS_OK;
+    HCUDA(cudaFreeHost(hptr));
+    return HELIOS_OK;
+}
+
+int helios_event_create(helios_ctx* ctx, helios_event** ev) {
+    HCTX(ctx);
+    HARG(ev != nullptr);
+    helios_event* e = new helios_event();
+    e->device = ctx->device;
+    cudaError_t err = cudaEventCreate(&e->ev);
+    if (err != cudaSuccess) {
+        delete e;
+        return helios_fail_cuda(err, "cudaEventCreate", __FILE__, __LINE__);
+    }
+    *ev = e;
+    return HELIOS_OK;
+}
+
+int helios_event_destroy(helios_event* ev) {
+    if (ev == nullptr) return HELIOS_OK;
+    cudaSetDevice(ev->device);
+    cudaEventDestroy(ev->ev);
+    delete ev;
+    return HELIOS_OK;
+}
+
+int helios_event_record(helios_ctx* ctx, helios_event* ev) {
+    HCTX(ctx);
+    HARG(ev != nullptr);
+    HCUDA(cudaEventRecord(ev->ev, ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_event_synchronize(helios_event* ev) {
+    HARG(ev != nullptr);
+    HCUDA(cudaSetDevice(ev->device));
+    HCUDA(cudaEventSynchronize(ev->ev));
+    return HELIOS_OK;
+}
+
+int helios_event_elapsed_ms(helios_event* start, helios_event* stop, float* ms) {
+    HARG(start != nullptr && stop != nullptr && ms != nullptr);
+    HCUDA(cudaSetDevice(start->device));
+    HCUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    return HELIOS_OK;
+}
+
+}  // extern "C"
+
+int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out) {
+    if (nbytes > ctx->scratch_bytes) {
+        if (ctx->scratch) {
+            HCUDA(cudaStreamSynchronize(ctx->stream));
+            HCUDA(cudaFree(ctx->scratch));
+            ctx->scratch = nullptr;
+            ctx->scratch_bytes = 0;
+        }
+        size_t n = nbytes < (1u << 20) ? (1u << 20) : nbytes;
+        HCUDA(cudaMalloc((void**)&ctx->scratch, n));
+        ctx->scratch_bytes = n;
+    }
+    *out = ctx->scratch;
+    return HELIOS_OK;
+}

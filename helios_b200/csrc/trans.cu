@@ -1,0 +1,334 @@
+// Transmission functions / two-stream coefficients, layer heights and the direct stellar beam.
+// From-scratch sm_100a kernels for K:128-290 and K:1015-1362 of the reference.
+#include "common.cuh"
+
+struct TransScalars {
+    double g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition;
+    int scat, nbin, ny, nlayer, clouds, scat_corr, debug;
+};
+
+struct CellCoeffs {
+    double w0, dtau, trans, M, N, P, Gp, Gm;
+};
+
+// G+/- limiter (K:218-231)
+__device__ __forceinline__ double g_limit(double G) {
+    return fabs(G) < 1e8 ? G : 1e8 * G / fabs(G);
+}
+
+// everything calc_trans_* derives for one (half-)layer cell: K:1076-1099 / K:1199-1237 with the helper
+// functions K:128-290 inlined.  E, sqrt((E-w0)/(E(1-w0 g0))) and the G denominator are formed once
+// (the reference re-evaluates them in five device functions).
+__device__ __forceinline__ CellCoeffs cell_coeffs(double ray, double cloud_scat, double cloud_abs,
+                                                  double opac, double mmm, double dcol, double dtau_cloud,
+                                                  double g0, const TransScalars& s) {
+    CellCoeffs c;
+    c.w0 = fmin((ray + cloud_scat) / ((ray + cloud_scat) + (opac * mmm + cloud_abs)), s.w_0_limit);
+    c.dtau = dcol * (opac + ray / mmm);
+    const double del_tau = c.dtau + dtau_cloud;
+    const double w0 = c.w0;
+    const double E = s.scat_corr == 1 ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
+    const double one_m_wg = 1.0 - w0 * g0;
+    c.trans = exp(-1.0 / s.epsi * sqrt(E * one_m_wg * (E - w0)) * del_tau);
+    const double root = sqrt((E - w0) / (E * one_m_wg));
+    const double zm = 0.5 * (1.0 - root);
+    const double zp = 0.5 * (1.0 + root);
+    const double t2 = c.trans * c.trans;
+    c.M = (zm * zm) * t2 - (zp * zp);
+    c.N = zp * zm * (1.0 - t2);
+    c.P = ((zm * zm) - (zp * zp)) * c.trans;
+    // G+ / G- (K:149-213)
+    const double num = w0 * (E * one_m_wg + g0 * s.epsi / s.epsi2);
+    const double denom = E * pow(s.epsi, -2.0) * (E - w0) * one_m_wg - pow(s.mu_star, -2.0);
+    const double inv_eps = 1.0 / s.epsi;
+    const double cross = 1.0 / (s.mu_star * E * one_m_wg);
+    const double third = s.epsi * w0 * g0 * s.mu_star / (s.epsi2 * E * one_m_wg);
+    c.Gp = g_limit(0.5 * (num / denom * (inv_eps + cross) + third));
+    c.Gm = g_limit(0.5 * (num / denom * (inv_eps - cross) - third));
+    return c;
+}
+
+// one thread per cell of the [i][x][y] arrays, flat index -> fully coalesced 8-array store
+__global__ void __launch_bounds__(256)
+k_calc_trans_iso(double* __restrict__ trans_wg, double* __restrict__ delta_tau_wg, double* __restrict__ M_term,
+                 double* __restrict__ N_term, double* __restrict__ P_term, double* __restrict__ G_plus,
+                 double* __restrict__ G_minus, const double* __restrict__ delta_colmass,
+                 const double* __restrict__ opac_wg_lay, const double* __restrict__ meanmolmass_lay,
+                 const double* __restrict__ scat_cross_lay, const double* __restrict__ abs_cross_cl,
+                 const double* __restrict__ scat_cross_cl, double* __restrict__ delta_tau_all_clouds,
+                 double* __restrict__ w_0, const double* __restrict__ g_0_tot_lay,
+                 int* __restrict__ scat_trigger, TransScalars s) {
+    const int ncol = s.nbin * s.ny;
+    const long long total = (long long)ncol * s.nlayer;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / ncol);
+        const int col = (int)(e - (long long)i * ncol);
+        const int x = col / s.ny;
+        const int y = col - x * s.ny;
+        const size_t b = (size_t)x + (size_t)s.nbin * i;
+        const double g0 = s.clouds == 1 ? g_0_tot_lay[b] : s.g_0;
+        const double ray = s.scat == 1 ? scat_cross_lay[b] : 0.0;
+        const double csc = s.scat == 1 ? scat_cross_cl[b] : 0.0;
+        const double cab = abs_cross_cl[b];
+        const double mmm = meanmolmass_lay[i];
+        const double dcol = delta_colmass[i];
+        const double dtc = dcol * (cab + csc) / mmm;
+        if (y == 0) delta_tau_all_clouds[b] = dtc;
+        const CellCoeffs c = cell_coeffs(ray, csc, cab, opac_wg_lay[e], mmm, dcol, dtc, g0, s);
+        w_0[e] = c.w0;
+        delta_tau_wg[e] = c.dtau;
+        trans_wg[e] = c.trans;
+        M_term[e] = c.M;
+        N_term[e] = c.N;
+        P_term[e] = c.P;
+        G_plus[e] = c.Gp;
+        G_minus[e] = c.Gm;
+        if (c.w0 > s.w_0_scat_limit) scat_trigger[col] = 1;  // benign race, as K:1102
+    }
+}
+
+struct NonisoOut {
+    double *trans_u, *trans_l, *dtau_u, *dtau_l, *M_u, *M_l, *N_u, *N_l, *P_u, *P_l, *Gp_u, *Gp_l, *Gm_u,
+        *Gm_l, *dtc_u, *dtc_l, *w0_u, *w0_l;
+};
+struct NonisoIn {
+    const double *dcol_u, *dcol_l, *opac_lay, *opac_int, *mmm_lay, *mmm_int, *scat_lay, *scat_int,
+        *cab_lay, *cab_int, *csc_lay, *csc_int, *g0_lay, *g0_int;
+};
+
+__global__ void __launch_bounds__(256)
+k_calc_trans_noniso(NonisoOut o, NonisoIn in, int* __restrict__ scat_trigger, TransScalars s) {
+    const int ncol = s.nbin * s.ny;
+    const long long total = (long long)ncol * s.nlayer;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / ncol);
+        const int col = (int)(e - (long long)i * ncol);
+        const int x = col / s.ny;
+        const int y = col - x * s.ny;
+        const size_t b = (size_t)x + (size_t)s.nbin * i;   // layer i / interface i
+        const size_t bu = b + s.nbin;                       // interface i+1
+        double g0_up = s.g_0, g0_low = s.g_0;
+        if (s.clouds == 1) {
+            g0_up = (in.g0_lay[b] + in.g0_int[bu]) / 2.0;
+            g0_low = (in.g0_int[b] + in.g0_lay[b]) / 2.0;
+        }
+        double ray_up = 0.0, ray_low = 0.0, csc_up = 0.0, csc_low = 0.0;
+        if (s.scat == 1) {
+            ray_up = (in.scat_lay[b] + in.scat_int[bu]) / 2.0;
+            ray_low = (in.scat_int[b] + in.scat_lay[b]) / 2.0;
+            csc_up = (in.csc_lay[b] + in.csc_int[bu]) / 2.0;
+            csc_low = (in.csc_int[b] + in.csc_lay[b]) / 2.0;
+        }
+        const double cab_up = (in.cab_lay[b] + in.cab_int[bu]) / 2.0;
+        const double cab_low = (in.cab_int[b] + in.cab_lay[b]) / 2.0;
+        const double k_lay = in.opac_lay[e];
+        const double opac_up = (k_lay + in.opac_int[e + ncol]) / 2.0;
+        const double opac_low = (in.opac_int[e] + k_lay) / 2.0;
+        const double mmm_up = (in.mmm_lay[i] + in.mmm_int[i + 1]) / 2.0;
+        const double mmm_low = (in.mmm_int[i] + in.mmm_lay[i]) / 2.0;
+        const double dtc_up = in.dcol_u[i] * (cab_up + csc_up) / mmm_up;
+        const double dtc_low = in.dcol_l[i] * (cab_low + csc_low) / mmm_low;
+        if (y == 0) {
+            o.dtc_u[b] = dtc_up;
+            o.dtc_l[b] = dtc_low;
+        }
+        const CellCoeffs u = cell_coeffs(ray_up, csc_up, cab_up, opac_up, mmm_up, in.dcol_u[i], dtc_up, g0_up, s);
+        const CellCoeffs l = cell_coeffs(ray_low, csc_low, cab_low, opac_low, mmm_low, in.dcol_l[i], dtc_low, g0_low, s);
+        o.w0_u[e] = u.w0;      o.w0_l[e] = l.w0;
+        o.dtau_u[e] = u.dtau;  o.dtau_l[e] = l.dtau;
+        o.trans_u[e] = u.trans; o.trans_l[e] = l.trans;
+        o.M_u[e] = u.M;  o.M_l[e] = l.M;
+        o.N_u[e] = u.N;  o.N_l[e] = l.N;
+        o.P_u[e] = u.P;  o.P_l[e] = l.P;
+        o.Gp_u[e] = u.Gp; o.Gp_l[e] = l.Gp;
+        o.Gm_u[e] = u.Gm; o.Gm_l[e] = l.Gm;
+        if (u.w0 > s.w_0_scat_limit || l.w0 > s.w_0_scat_limit) scat_trigger[col] = 1;
+    }
+}
+
+// K:1247-1261
+__global__ void k_calc_delta_z(const double* __restrict__ tlay, const double* __restrict__ pint,
+                               const double* __restrict__ mmm, double* __restrict__ dz, double g, int nlayer) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nlayer) dz[i] = hc::KBOLTZMANN * tlay[i] / (mmm[i] * g) * log(pint[i] / pint[i + 1]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Direct beam (K:1265-1362).  One thread per column walks down from TOA.
+// Without the geometric zenith correction the attenuation is a running product
+// F[i] = F[i+1] * exp(dtau_i / mu*), which is exactly the reference's multiplication order, done in O(n)
+// instead of the reference's O(n^2) re-multiplication per interface.  With the correction mu depends
+// on (i, j) and the product is rebuilt per interface as in the reference.
+// NONISO additionally produces the layer-centre value Fc_dir (K:1358).
+// ------------------------------------------------------------------------------------------
+template <bool NONISO>
+__global__ void __launch_bounds__(128)
+k_fdir(double* __restrict__ F_dir, double* __restrict__ Fc_dir, const double* __restrict__ planck_lay,
+       const double* __restrict__ dtau_a,  // iso: delta_tau_wg ; noniso: upper
+       const double* __restrict__ dtau_b,  // noniso: lower
+       const double* __restrict__ z_lay, double mu_star, double R_planet, double R_star, double a,
+       int dir_beam, int geom, int nint, int nbin, int ny) {
+    const int ncol = nbin * ny;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const int x = col / ny;
+    const int nlay = nint - 1;
+    const double I_dir = ((R_star / a) * (R_star / a)) * hc::PI * planck_lay[nlay + (size_t)x * (nlay + 2)];
+    const double F_toa = -dir_beam * mu_star * I_dir;
+    F_dir[col + (size_t)ncol * nlay] = F_toa;
+    if (geom != 1) {
+        double F = F_toa;
+        for (int i = nlay - 1; i >= 0; i--) {
+            const size_t e = col + (size_t)ncol * i;
+            if (NONISO) {
+                const double du = dtau_a[e];
+                Fc_dir[e] = F * exp(du / mu_star);
+                F *= exp((du + dtau_b[e]) / mu_star);
+            } else {
+                F *= exp(dtau_a[e] / mu_star);
+            }
+            F_dir[e] = F;
+        }
+    } else {
+        const double one_m_mu2 = 1.0 - mu_star * mu_star;
+        for (int i = nlay - 1; i >= 0; i--) {
+            const double ri = R_planet + z_lay[i];
+            double F = F_toa, Fc = 0.0;
+            for (int j = nlay - 1; j >= i; j--) {
+                const double q = ri / (R_planet + z_lay[j]);
+                const double mu_j = -sqrt(1.0 - (q * q) * one_m_mu2);
+                const size_t e = col + (size_t)ncol * j;
+                if (NONISO) {
+                    const double du = dtau_a[e];
+                    Fc = F * exp(du / mu_j);
+                    F *= exp((du + dtau_b[e]) / mu_j);
+                } else {
+                    F *= exp(dtau_a[e] / mu_j);
+                }
+            }
+            const size_t e = col + (size_t)ncol * i;
+            F_dir[e] = F;
+            if (NONISO) Fc_dir[e] = Fc;
+        }
+    }
+}
+
+extern "C" {
+
+int helios_calc_trans_iso(helios_ctx* ctx, double* trans_wg, double* delta_tau_wg, double* M_term,
+                          double* N_term, double* P_term, double* G_plus, double* G_minus,
+                          const double* delta_colmass, const double* opac_wg_lay,
+                          const double* meanmolmass_lay, const double* scat_cross_lay,
+                          const double* abs_cross_all_clouds_lay, const double* scat_cross_all_clouds_lay,
+                          double* delta_tau_all_clouds, double* w_0, const double* g_0_tot_lay,
+                          int* scat_trigger, double g_0, double epsi, double epsi2, double mu_star,
+                          double w_0_limit, double w_0_scat_limit, int scat, int nbin, int ny, int nlayer,
+                          int clouds, int scat_corr, int debug, double i2s_transition) {
+    HCTX(ctx);
+    HARG(trans_wg && delta_tau_wg && M_term && N_term && P_term && G_plus && G_minus && delta_colmass &&
+         opac_wg_lay && meanmolmass_lay && scat_cross_lay && abs_cross_all_clouds_lay &&
+         scat_cross_all_clouds_lay && delta_tau_all_clouds && w_0 && scat_trigger);
+    HARG(clouds == 0 || g_0_tot_lay != nullptr);
+    HARG(nbin > 0 && ny > 0 && nlayer > 0);
+    TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug};
+    const long long total = (long long)nbin * ny * nlayer;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    k_calc_trans_iso<<<(int)blocks, 256, 0, ctx->stream>>>(
+        trans_wg, delta_tau_wg, M_term, N_term, P_term, G_plus, G_minus, delta_colmass, opac_wg_lay,
+        meanmolmass_lay, scat_cross_lay, abs_cross_all_clouds_lay, scat_cross_all_clouds_lay,
+        delta_tau_all_clouds, w_0, g_0_tot_lay, scat_trigger, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_calc_trans_noniso(
+    helios_ctx* ctx, double* trans_wg_upper, double* trans_wg_lower, double* delta_tau_wg_upper,
+    double* delta_tau_wg_lower, double* M_upper, double* M_lower, double* N_upper, double* N_lower,
+    double* P_upper, double* P_lower, double* G_plus_upper, double* G_plus_lower, double* G_minus_upper,
+    double* G_minus_lower, const double* delta_col_upper, const double* delta_col_lower,
+    const double* opac_wg_lay, const double* opac_wg_int, const double* meanmolmass_lay,
+    const double* meanmolmass_int, const double* scat_cross_lay, const double* scat_cross_int,
+    const double* abs_cross_all_clouds_lay, const double* abs_cross_all_clouds_int,
+    const double* scat_cross_all_clouds_lay, const double* scat_cross_all_clouds_int,
+    double* delta_tau_all_clouds_upper, double* delta_tau_all_clouds_lower, double* w_0_upper,
+    double* w_0_lower, const double* g_0_tot_lay, const double* g_0_tot_int, int* scat_trigger,
+    double g_0, double epsi, double epsi2, double mu_star, double w_0_limit, double w_0_scat_limit,
+    int scat, int nbin, int ny, int nlayer, int clouds, int scat_corr, int debug,
+    double i2s_transition) {
+    HCTX(ctx);
+    HARG(trans_wg_upper && trans_wg_lower && delta_tau_wg_upper && delta_tau_wg_lower && M_upper &&
+         M_lower && N_upper && N_lower && P_upper && P_lower && G_plus_upper && G_plus_lower &&
+         G_minus_upper && G_minus_lower && delta_col_upper && delta_col_lower && opac_wg_lay &&
+         opac_wg_int && meanmolmass_lay && meanmolmass_int && scat_cross_lay && scat_cross_int &&
+         abs_cross_all_clouds_lay && abs_cross_all_clouds_int && scat_cross_all_clouds_lay &&
+         scat_cross_all_clouds_int && delta_tau_all_clouds_upper && delta_tau_all_clouds_lower &&
+         w_0_upper && w_0_lower && scat_trigger);
+    HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
+    HARG(nbin > 0 && ny > 0 && nlayer > 0);
+    TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug};
+    NonisoOut o{trans_wg_upper, trans_wg_lower, delta_tau_wg_upper, delta_tau_wg_lower, M_upper, M_lower,
+                N_upper, N_lower, P_upper, P_lower, G_plus_upper, G_plus_lower, G_minus_upper,
+                G_minus_lower, delta_tau_all_clouds_upper, delta_tau_all_clouds_lower, w_0_upper,
+                w_0_lower};
+    NonisoIn in{delta_col_upper, delta_col_lower, opac_wg_lay, opac_wg_int, meanmolmass_lay,
+                meanmolmass_int, scat_cross_lay, scat_cross_int, abs_cross_all_clouds_lay,
+                abs_cross_all_clouds_int, scat_cross_all_clouds_lay, scat_cross_all_clouds_int,
+                g_0_tot_lay, g_0_tot_int};
+    const long long total = (long long)nbin * ny * nlayer;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    k_calc_trans_noniso<<<(int)blocks, 256, 0, ctx->stream>>>(o, in, scat_trigger, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_calc_delta_z(helios_ctx* ctx, const double* tlay, const double* pint, const double* play,
+                        const double* meanmolmass_lay, double* delta_z_lay, double g, int nlayer) {
+    HCTX(ctx);
+    (void)play;
+    HARG(tlay && pint && meanmolmass_lay && delta_z_lay && nlayer > 0);
+    k_calc_delta_z<<<ceil_div(nlayer, 128), 128, 0, ctx->stream>>>(tlay, pint, meanmolmass_lay,
+                                                                   delta_z_lay, g, nlayer);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_fdir_iso(helios_ctx* ctx, double* F_dir_wg, const double* planckband_lay,
+                    const double* delta_tau_wg, const double* z_lay, double mu_star, double R_planet,
+                    double R_star, double a, int dir_beam, int geom_zenith_corr, int ninterface, int nbin,
+                    int ny) {
+    HCTX(ctx);
+    HARG(F_dir_wg && planckband_lay && delta_tau_wg && ninterface > 1 && nbin > 0 && ny > 0);
+    HARG(geom_zenith_corr != 1 || z_lay != nullptr);
+    const int ncol = nbin * ny;
+    k_fdir<false><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(
+        F_dir_wg, nullptr, planckband_lay, delta_tau_wg, nullptr, z_lay, mu_star, R_planet, R_star, a,
+        dir_beam, geom_zenith_corr, ninterface, nbin, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_fdir_noniso(helios_ctx* ctx, double* F_dir_wg, double* Fc_dir_wg, const double* planckband_lay,
+                       const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
+                       const double* z_lay, double mu_star, double R_planet, double R_star, double a,
+                       int dir_beam, int geom_zenith_corr, int ninterface, int nbin, int ny) {
+    HCTX(ctx);
+    HARG(F_dir_wg && Fc_dir_wg && planckband_lay && delta_tau_wg_upper && delta_tau_wg_lower &&
+         ninterface > 1 && nbin > 0 && ny > 0);
+    HARG(geom_zenith_corr != 1 || z_lay != nullptr);
+    const int ncol = nbin * ny;
+    k_fdir<true><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(
+        F_dir_wg, Fc_dir_wg, planckband_lay, delta_tau_wg_upper, delta_tau_wg_lower, z_lay, mu_star,
+        R_planet, R_star, a, dir_beam, geom_zenith_corr, ninterface, nbin, ny);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+/*
+ * helios_b200.h -- C-ABI of libhelios_b200.so, the B200-native (sm_100a) backend for the
+ * radiative-transfer hot path of HELIOS.
+ *
+ * The reference has no FFI: its "interface" for this path is the set of PyCUDA launches
+ *   SourceModule.get_function(name)(args..., block=, grid=)
+ * in source/computation.py plus the gpuarray/mem_alloc buffer calls in source/quantities.py.
+ * Every entry point below replaces exactly one of those launch sites (cited as K: = source/kernels.cu,
+ * C: = source/computation.py, Q: = source/quantities.py, H: = source/host_functions.py) and keeps
+ * the reference kernel's argument order and meaning, with the context handle prepended.
+ *
+ * Conventions
+ *   - every function returns 0 (HELIOS_OK) or a non-zero status; helios_last_error() returns the
+ *     message of the last failure on the calling thread.
+ *   - all `double*` / `int*` array arguments are DEVICE pointers obtained from helios_buf_alloc
+ *     (the library owns device memory); scalars are passed by value.
+ *   - launches are asynchronous on the context's stream; helios_buf_d2h and helios_ctx_sync
+ *     synchronise.  (The reference synchronises the whole device after every launch, C:60 etc.)
+ *   - array layouts are the reference's: "wg" arrays are [i][x][y] with y fastest
+ *     (idx = y + ny*x + ny*nbin*i, K:1076); band arrays are [i][x] (K:2456); the Planck arrays are
+ *     [x][i] with i fastest (K:940, K:1004).
+ *   - fp64 only (`precision = double`, K:24-32).
+ */
+#ifndef HELIOS_B200_H
+#define HELIOS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HELIOS_OK 0
+#define HELIOS_ERR_CUDA 1
+#define HELIOS_ERR_ARG 2
+#define HELIOS_ERR_NOMEM 3
+#define HELIOS_ERR_STATE 4
+
+#define HELIOS_ABI_VERSION 1
+
+typedef struct helios_ctx helios_ctx;
+typedef struct helios_event helios_event;
+
+/* ------------------------------------------------------------------ runtime ------------------ */
+
+int helios_abi_version(void);
+const char* helios_last_error(void);
+int helios_device_count(int* count);
+
+/* replaces `import pycuda.autoinit` (C:24): binds a context to one device and creates its stream */
+int helios_ctx_create(int device, helios_ctx** out);
+int helios_ctx_destroy(helios_ctx* ctx);
+/* run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL restores the own stream */
+int helios_ctx_set_stream(helios_ctx* ctx, void* cuda_stream);
+int helios_ctx_get_stream(helios_ctx* ctx, void** cuda_stream);
+int helios_ctx_sync(helios_ctx* ctx);                       /* cuda.Context.synchronize(), C:60 */
+int helios_ctx_device_info(helios_ctx* ctx, int* num_sms, size_t* l2_bytes, size_t* total_mem);
+/* number of kernel launches issued through this context since creation (bench bookkeeping) */
+int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count);
+/* bytes currently allocated through helios_buf_alloc */
+int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes);
+
+/* buffers: replace gpuarray.to_gpu / cuda.mem_alloc / .get() (Q:463-665) */
+int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr);
+int helios_buf_free(helios_ctx* ctx, void* dptr);
+int helios_buf_h2d(helios_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
+int helios_buf_d2h(helios_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes);
+int helios_buf_d2d(helios_ctx* ctx, void* dst_dev, const void* src_dev, size_t nbytes);
+int helios_buf_zero(helios_ctx* ctx, void* dptr, size_t nbytes);
+/* asynchronous copies for pinned host memory (no implicit sync) */
+int helios_buf_h2d_async(helios_ctx* ctx, void* dst_dev, const void* src_host, size_t nbytes);
+int helios_buf_d2h_async(helios_ctx* ctx, void* dst_host, const void* src_dev, size_t nbytes);
+int helios_host_alloc(size_t nbytes, void** hptr);          /* pinned host memory */
+int helios_host_free(void* hptr);
+
+/* events: replace cuda.Event() / record / time_till (C:838-841, 962-965) */
+int helios_event_create(helios_ctx* ctx, helios_event** ev);
+int helios_event_destroy(helios_event* ev);
+int helios_event_record(helios_ctx* ctx, helios_event* ev);
+int helios_event_synchronize(helios_event* ev);
+int helios_event_elapsed_ms(helios_event* start, helios_event* stop, float* ms);
+
+/* ------------------------------------------------------------------ set-up kernels ----------- */
+
+/* K:362 plancktable, launched 10x at C:43-58.  One call fills rows 0..dim-1 (T = 1 + t*step) and
+ * row dim (T = Tstar) of planck_grid[(dim+1)*nwave]. */
+int helios_plancktable(helios_ctx* ctx, double* planck_grid, const double* lambda_edge,
+                       const double* deltalambda, int nwave, double Tstar, int dim, int step);
+
+/* K:420 corr_inc_energy, C:67-78.  corr_factor_host (may be NULL) receives theo_flux/num_flux,
+ * which the reference prints from device code (K:455-456). */
+int helios_corr_inc_energy(helios_ctx* ctx, double* planck_grid, double* starflux,
+                           const double* deltalambda, int realstar, int nwave, double Tstar, int dim,
+                           double* corr_factor_host);
+
+/* ------------------------------------------------------------------ per-iteration kernels ---- */
+
+/* K:496 temp_inter, C:107-115 */
+int helios_temp_inter(helios_ctx* ctx, const double* tlay, double* tint, int numinterfaces);
+
+/* K:923 planck_interpol_layer, C:298-311 */
+int helios_planck_interpol_layer(helios_ctx* ctx, const double* temp, double* planckband_lay,
+                                 const double* planck_grid, const double* starflux, int realstar,
+                                 int numlayers, int nwave, int dim, int step);
+/* K:981 planck_interpol_interface, C:316-327 */
+int helios_planck_interpol_interface(helios_ctx* ctx, const double* temp, double* planckband_int,
+                                     const double* planck_grid, int numinterfaces, int nwave,
+                                     int dim, int step);
+
+/* K:524 opac_interpol, C:122-159 */
+int helios_opac_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                         const double* press, const double* opacpress, const double* ktable,
+                         double* opac, const double* crosstable, double* scat_cross, int npress,
+                         int ntemp, int ny, int nbin, int nlay_or_nint);
+
+/* K:649 meanmolmass_interpol, C:166-195 */
+int helios_meanmolmass_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                                double* meanmolmass, const double* opac_meanmass,
+                                const double* press, const double* opacpress, int npress, int ntemp,
+                                int ninterface);
+
+/* K:703 kappa_interpol, K:761 cp_interpol (C:204-248); K:815 entropy_interpol (C:257-269);
+ * K:869 phase_number_interpol (C:278-290) */
+int helios_kappa_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                          const double* press, const double* entr_press, double* kappa,
+                          const double* entr_kappa, int entr_npress, int entr_ntemp, int nlay_or_nint);
+int helios_cp_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                       const double* press, const double* entr_press, double* cp_lay,
+                       const double* entr_cp, int entr_npress, int entr_ntemp, int nlayer);
+int helios_entropy_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                            const double* press, const double* entr_press, double* entropy,
+                            const double* entr_entropy, int entr_npress, int entr_ntemp, int nlayer);
+int helios_phase_number_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,
+                                 const double* press, const double* entr_press, double* state,
+                                 const double* entr_state, int entr_npress, int entr_ntemp, int nlayer);
+
+/* K:3209 opac_species_interpol, C:1301-1334 */
+int helios_opac_species_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
+                                 const double* press, const double* opacpress,
+                                 const double* opac_opacity_pretab, double* opac_spec_wg, int npress,
+                                 int ntemp, int ny, int nbin, int nlay_or_nint);
+
+/* K:3263 add_to_mixed_opac, C:1350-1386.  Random overlap requires ny == 20 as in the reference
+ * (K:3314, K:3393); any other ny with ro_method=1 and s>0 is rejected with HELIOS_ERR_ARG unless
+ * ny == 1 (which the reference routes to correlated-k, K:3302). */
+int helios_add_to_mixed_opac(helios_ctx* ctx, const double* vmr, const double* opac_spec,
+                             double* opac_wg, const double* meanmolmass, const double* gauss_weight,
+                             const double* gauss_y, double mass_spec, int s, int ro_method, int ny,
+                             int nbin, int nlay_or_nint);
+
+/* K:3404 calc_h2o_scat, C:1394-1421 */
+int helios_calc_h2o_scat(helios_ctx* ctx, const double* temp, const double* press,
+                         const double* wave, double* scat_cross, const double* vmr, double mass_h2o,
+                         int nbin, int nlay_or_nint);
+/* K:3444 add_to_mixed_scat, C:1428-1450 */
+int helios_add_to_mixed_scat(helios_ctx* ctx, const double* vmr, const double* scat_cross_spec,
+                             double* scat_cross, int nbin, int nlay_or_nint);
+
+/* K:472 calc_total_g_0_of_gas_and_clouds, C:334-360 */
+int helios_calc_total_g_0_of_gas_and_clouds(helios_ctx* ctx, const double* scat_cross,
+                                            const double* g_0_all_clouds,
+                                            const double* scat_cross_all_clouds, double* g_0_tot,
+                                            double g_0, int nbin, int nlay_or_nint);
+
+/* K:1015 calc_trans_iso, C:371-406 */
+int helios_calc_trans_iso(helios_ctx* ctx, double* trans_wg, double* delta_tau_wg, double* M_term,
+                          double* N_term, double* P_term, double* G_plus, double* G_minus,
+                          const double* delta_colmass, const double* opac_wg_lay,
+                          const double* meanmolmass_lay, const double* scat_cross_lay,
+                          const double* abs_cross_all_clouds_lay,
+                          const double* scat_cross_all_clouds_lay, double* delta_tau_all_clouds,
+                          double* w_0, const double* g_0_tot_lay, int* scat_trigger, double g_0,
+                          double epsi, double epsi2, double mu_star, double w_0_limit,
+                          double w_0_scat_limit, int scat, int nbin, int ny, int nlayer, int clouds,
+                          int scat_corr, int debug, double i2s_transition);
+
+/* K:1107 calc_trans_noniso, C:409-460 */
+int helios_calc_trans_noniso(
+    helios_ctx* ctx, double* trans_wg_upper, double* trans_wg_lower, double* delta_tau_wg_upper,
+    double* delta_tau_wg_lower, double* M_upper, double* M_lower, double* N_upper, double* N_lower,
+    double* P_upper, double* P_lower, double* G_plus_upper, double* G_plus_lower,
+    double* G_minus_upper, double* G_minus_lower, const double* delta_col_upper,
+    const double* delta_col_lower, const double* opac_wg_lay, const double* opac_wg_int,
+    const double* meanmolmass_lay, const double* meanmolmass_int, const double* scat_cross_lay,
+    const double* scat_cross_int, const double* abs_cross_all_clouds_lay,
+    const double* abs_cross_all_clouds_int, const double* scat_cross_all_clouds_lay,
+    const double* scat_cross_all_clouds_int, double* delta_tau_all_clouds_upper,
+    double* delta_tau_all_clouds_lower, double* w_0_upper, double* w_0_lower,
+    const double* g_0_tot_lay, const double* g_0_tot_int, int* scat_trigger, double g_0, double epsi,
+    double epsi2, double mu_star, double w_0_limit, double w_0_scat_limit, int scat, int nbin, int ny,
+    int nlayer, int clouds, int scat_corr, int debug, double i2s_transition);
+
+/* K:1247 calc_delta_z, C:467-477 */
+int helios_calc_delta_z(helios_ctx* ctx, const double* tlay, const double* pint, const double* play,
+                        const double* meanmolmass_lay, double* delta_z_lay, double g, int nlayer);
+
+/* K:1265 fdir_iso, C:486-502 */
+int helios_fdir_iso(helios_ctx* ctx, double* F_dir_wg, const double* planckband_lay,
+                    const double* delta_tau_wg, const double* z_lay, double mu_star, double R_planet,
+                    double R_star, double a, int dir_beam, int geom_zenith_corr, int ninterface,
+                    int nbin, int ny);
+/* K:1313 fdir_noniso, C:506-524 */
+int helios_fdir_noniso(helios_ctx* ctx, double* F_dir_wg, double* Fc_dir_wg,
+                       const double* planckband_lay, const double* delta_tau_wg_upper,
+                       const double* delta_tau_wg_lower, const double* z_lay, double mu_star,
+                       double R_planet, double R_star, double a, int dir_beam, int geom_zenith_corr,
+                       int ninterface, int nbin, int ny);
+
+/* K:1366 fband_iso.  The reference launches it (3*scat+1) times per iteration, or 1000*scat+1 times in
+ * post-processing (C:531-571), each launch a full device sync.  `npass` fuses those launches: one
+ * call performs npass consecutive down+up sweeps with identical results (columns are independent,
+ * so pass p+1 of a column only needs that column's own pass-p fluxes). */
+int helios_fband_iso(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const double* F_dir_wg,
+                     const double* planckband_lay, const double* w_0, const double* M_term,
+                     const double* N_term, const double* P_term, const double* G_plus,
+                     const double* G_minus, const double* surf_albedo, const double* g_0_tot_lay,
+                     double g_0, int singlewalk, double Rstar, double a, int numinterfaces, int nbin,
+                     double f_factor, double mu_star, int ny, double epsi, int dir_beam, int clouds,
+                     int scat_corr, int debug, double i2s_transition, int npass);
+
+/* K:1521 fband_noniso, C:575-621; npass as above */
+int helios_fband_noniso(
+    helios_ctx* ctx, double* F_down_wg, double* F_up_wg, double* Fc_down_wg, double* Fc_up_wg,
+    const double* F_dir_wg, const double* Fc_dir_wg, const double* planckband_lay,
+    const double* planckband_int, const double* w_0_upper, const double* w_0_lower,
+    const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
+    const double* delta_tau_all_clouds_upper, const double* delta_tau_all_clouds_lower,
+    const double* M_upper, const double* M_lower, const double* N_upper, const double* N_lower,
+    const double* P_upper, const double* P_lower, const double* G_plus_upper,
+    const double* G_plus_lower, const double* G_minus_upper, const double* G_minus_lower,
+    const double* surf_albedo, const double* g_0_tot_lay, const double* g_0_tot_int, double g_0,
+    int singlewalk, double Rstar, double a, int numinterfaces, int nbin, double f_factor,
+    double mu_star, int ny, double epsi, double delta_tau_limit, int dir_beam, int clouds,
+    int scat_corr, int debug, double i2s_transition, int npass);
+
+/* K:1803 fband_matrix_iso, C:630-668.  alpha/beta/source_term_* are accepted for signature
+ * compatibility but not touched: the Thomas coefficients are formed on the fly; c_prime/d_prime
+ * (2*ninterface*ny*nbin doubles each) hold the forward elimination. */
+int helios_fband_matrix_iso(
+    helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const double* F_dir_wg,
+    const double* planckband_lay, const double* w_0, const double* M_term, const double* N_term,
+    const double* P_term, const double* G_plus, const double* G_minus, const double* g_0_tot_lay,
+    double* alpha, double* beta, double* source_term_down, double* source_term_up, double* c_prime,
+    double* d_prime, const int* scat_trigger, const double* trans_wg, const double* surf_albedo,
+    double g_0, int singlewalk, double Rstar, double a, int numinterfaces, int nbin, double f_factor,
+    double mu_star, int ny, double epsi, int dir_beam, int clouds, int scat_corr, int debug,
+    double i2s_transition);
+
+/* K:2028 fband_matrix_noniso, C:672-727.  c_prime/d_prime need (4*ninterface-2)*ny*nbin doubles. */
+int helios_fband_matrix_noniso(
+    helios_ctx* ctx, double* F_down_wg, double* F_up_wg, double* Fc_down_wg, double* Fc_up_wg,
+    const double* F_dir_wg, const double* Fc_dir_wg, const double* planckband_lay,
+    const double* planckband_int, const double* w_0_upper, const double* w_0_lower,
+    const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
+    const double* delta_tau_all_clouds_upper, const double* delta_tau_all_clouds_lower,
+    const double* M_upper, const double* M_lower, const double* N_upper, const double* N_lower,
+    const double* P_upper, const double* P_lower, const double* G_plus_upper,
+    const double* G_plus_lower, const double* G_minus_upper, const double* G_minus_lower,
+    const double* g_0_tot_lay, const double* g_0_tot_int, double* alpha, double* beta,
+    double* source_term_down, double* source_term_up, double* c_prime, double* d_prime,
+    const int* scat_trigger, const double* trans_wg_upper, const double* trans_wg_lower,
+    const double* surf_albedo, double g_0, int singlewalk, double Rstar, double a, int numinterfaces,
+    int nbin, double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
+    int dir_beam, int clouds, int scat_corr, int debug, double i2s_transition);
+
+/* K:2428 integrate_flux_double, C:739-755.  Multi-block, fixed summation order (the reference's
+ * single-block CAS-atomic order is nondeterministic). */
+int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, double* F_down_tot,
+                                 double* F_up_tot, double* F_net, const double* F_down_wg,
+                                 const double* F_up_wg, const double* F_dir_wg, double* F_down_band,
+                                 double* F_up_band, double* F_dir_band, const double* gauss_weight,
+                                 int nbin, int numinterfaces, int ny);
+
+/* K:2606 rad_temp_iter, C:762-795 */
+int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                         const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                         const double* tint, const double* pint, int* abrt, double* T_store,
+                         double* deltat_prefactor, const double* F_add_heat_lay,
+                         const double* F_add_heat_sum, double* F_smooth, double* F_smooth_sum,
+                         const double* c_p_lay, const double* meanmolmass_lay, int itervalue,
+                         double f_factor, int foreplay, double g, int numlayers,
+                         double physical_tstep, double local_limit, int adapt_interval, int smooth,
+                         int dim, int step, double F_intern, int no_atmo);
+
+/* K:2768 conv_temp_iter, C:802-823 */
+int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                          const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                          const double* pint, double* T_store, double* deltat_prefactor,
+                          const int* marked_red, const double* F_add_heat_lay, double* F_smooth,
+                          double* F_smooth_sum, int numlayers, int itervalue, int adapt_interval,
+                          int smooth, double F_intern);
+
+/* replaces the per-iteration `dev_abort.get()` + Python loop (C:927-932): sums abrt[0..n) on the
+ * device into *sum_dev (device int).  B200-side addition, no reference kernel. */
+int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev);
+
+/* ------------------------------------------------------------------ post-processing ---------- */
+
+/* K:2888 / K:2916, C:1180-1212 */
+int helios_integrate_optdepth_transmission_iso(helios_ctx* ctx, const double* trans_wg,
+                                               double* trans_band, const double* delta_tau_wg,
+                                               double* delta_tau_band, const double* gauss_weight,
+                                               int nbin, int nlayer, int ny);
+int helios_integrate_optdepth_transmission_noniso(
+    helios_ctx* ctx, const double* trans_wg_upper, const double* trans_wg_lower, double* trans_band,
+    const double* delta_tau_wg_upper, const double* delta_tau_wg_lower, double* delta_tau_band,
+    const double* gauss_weight, double* delta_tau_all_clouds,
+    const double* delta_tau_all_clouds_upper, const double* delta_tau_all_clouds_lower, int nbin,
+    int nlayer, int ny);
+
+/* K:2951 / K:2987, C:1220-1250.  trans_weight_band is accumulated into (+=) as in the reference. */
+int helios_calc_contr_func_iso(helios_ctx* ctx, const double* trans_wg, double* trans_weight_band,
+                               double* contr_func_band, const double* gauss_weight,
+                               const double* planckband_lay, double epsi, int nbin, int nlayer,
+                               int ny);
+int helios_calc_contr_func_noniso(helios_ctx* ctx, const double* trans_wg_upper,
+                                  const double* trans_wg_lower, double* trans_weight_band,
+                                  double* contr_func_band, const double* gauss_weight,
+                                  const double* planckband_lay, double epsi, int nbin, int nlayer,
+                                  int ny);
+
+/* K:3024 calc_mean_opacities, C:1257-1279 */
+int helios_calc_mean_opacities(helios_ctx* ctx, double* planck_opac_T_pl, double* ross_opac_T_pl,
+                               double* planck_opac_T_star, double* ross_opac_T_star,
+                               const double* opac_wg_lay, const double* abs_cross_all_clouds_lay,
+                               const double* meanmolmass_lay, const double* planckband_lay,
+                               const double* opac_interwave, const double* opac_deltawave,
+                               const double* T_lay, const double* gauss_weight,
+                               const double* gauss_y, double* opac_band_lay, int nlayer, int nbin,
+                               int ny, double T_star);
+
+/* K:3119 integrate_beamflux, C:1286-1296 */
+int helios_integrate_beamflux(helios_ctx* ctx, double* F_dir_tot, const double* F_dir_band,
+                              const double* deltalambda, const double* gauss_weight, int nbin,
+                              int numinterfaces);
+
+/* ------------------------------------------------------------------ multi-GPU ---------------- */
+/* Wavelength sharding: each rank integrates its own bins; the per-interface partial
+ * totals are summed across ranks.  The exchange is a one-shot peer-memory reduction over
+ * NVLink/NVSwitch: every rank stores its partial vector into a slot of every peer's mailbox
+ * (cudaIpc-mapped), then sums the slots in rank order, so all ranks get bitwise-identical totals.
+ * No reference counterpart (the reference is single-GPU). */
+#define HELIOS_IPC_HANDLE_BYTES 64
+/* allocate this rank's mailbox (world*slot_doubles doubles + flags) and export its IPC handle */
+int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles,
+                       unsigned char* handle_out /* HELIOS_IPC_HANDLE_BYTES */);
+/* map the peers' mailboxes; handles = world consecutive handles (own entry ignored) */
+int helios_comm_connect(helios_ctx* ctx, const unsigned char* handles);
+/* vec[0..n) (device, n <= slot_doubles) <- sum over ranks, fixed rank order */
+int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n);
+int helios_comm_destroy(helios_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HELIOS_B200_H */
