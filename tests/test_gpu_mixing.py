@@ -1,0 +1,145 @@
+"""GPU parity of the on-the-fly species path: per-species interpolation, correlated-k summation and
+random overlap (400-element sort + rebin per cell) against the NumPy oracle and the reference cubin."""
+import numpy as np
+import pytest
+
+from helios_b200 import synthetic, host
+from helios_b200.computation import Compute
+from oracle import ref_gpu
+from oracle import helios_oracle as O
+from oracle.pipeline import OracleCompute, HostMirror
+from util import stage_vs_oracle, stage_vs_ref, assert_close, restore
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(nbin=23, nlayer=12, ntemp=10, npress=8, plancktable_dim=700, plancktable_step=10)
+
+
+def _store(ctx, mixing, iso=1):
+    q = synthetic.make_store("C3", ctx=ctx, kcoeff_mixing=mixing, n_species=5, **SMALL)
+    q.iso = np.int32(iso)
+    n = int(q.nlayer)
+    q.T_lay = np.concatenate([np.linspace(2200.0, 800.0, n), [2300.0]])
+    synthetic.upload(q)
+    return q
+
+
+def _species_loop(q, comp, check):
+    """computation.py:1454-1501, stage by stage"""
+    comp.interpolate_temperatures(q)
+    host.calculate_meanmolecularmass(q)
+    host.nullify_opac_scat_arrays(q)
+    for s, sp in enumerate(q.species_list):
+        comp._upload(q, "vmr_spec_lay", np.asarray(sp.vmr_layer, np.float64))
+        if q.iso == 0:
+            comp._upload(q, "vmr_spec_int", np.asarray(sp.vmr_interface, np.float64))
+        q.dev_opacity_spec_pretab = comp._resident(("k", s), sp.opacity_pretab)
+        check("interpolate_species_opac", ["opac_spec_wg_lay"] + ([] if q.iso == 1 else ["opac_spec_wg_int"]), ())
+        check("add_to_mixed_opacity", ["opac_wg_lay"] + ([] if q.iso == 1 else ["opac_wg_int"]), (sp.weight, s))
+        if sp.scattering == "yes":
+            if sp.name == "H2O":
+                q.dev_scat_cross_spec_lay = q.ctx.zeros(int(q.nbin) * int(q.nlayer))
+                if q.iso == 0:
+                    q.dev_scat_cross_spec_int = q.ctx.zeros(int(q.nbin) * int(q.ninterface))
+                check("calculate_H2O_Rayleigh_scattering",
+                      ["scat_cross_spec_lay"] + ([] if q.iso == 1 else ["scat_cross_spec_int"]), (s,))
+            else:
+                q.dev_scat_cross_spec_lay = comp._resident(("sl", s), sp.scat_cross_sect_layer)
+                if q.iso == 0:
+                    q.dev_scat_cross_spec_int = comp._resident(("si", s), sp.scat_cross_sect_interface)
+            check("add_to_mixed_scat_cross_sect", ["scat_cross_lay"] + ([] if q.iso == 1 else ["scat_cross_int"]), ())
+
+
+@pytest.mark.parametrize("mixing", ["RO", "correlated-k"])
+@pytest.mark.parametrize("iso", [1, 0])
+def test_species_loop_vs_numpy_oracle(ctx, mixing, iso):
+    q = _store(ctx, mixing, iso)
+    comp = Compute(ctx, verbose=False)
+    oc = OracleCompute()
+    _species_loop(q, comp, lambda m, outs, args: stage_vs_oracle(q, comp, oc, m, outs, args=args))
+    assert np.all(np.isfinite(q.dev_opac_wg_lay.get()))
+
+
+class _RefSpecies(object):
+    """adapts RefCompute (which takes the species mass in grams and ro_method) to the Compute signature"""
+
+    def __init__(self, ref, q):
+        self.ref, self.q = ref, q
+
+    def interpolate_species_opac(self, q):
+        self.ref.interpolate_species_opac(q)
+
+    def add_to_mixed_opacity(self, q, weight, s):
+        ro = 0 if (q.kcoeff_mixing == "correlated-k" or "CIA" in q.species_list[s].name) else 1
+        self.ref.add_to_mixed_opacity(q, np.float64(weight * host.AMU), s, ro)
+
+    def calculate_H2O_Rayleigh_scattering(self, q, s):
+        mass = np.float64(q.species_list[s].weight * host.AMU)
+        for T, p, out, vmr, n in ((q.dev_T_lay, q.dev_p_lay, q.dev_scat_cross_spec_lay, q.dev_vmr_spec_lay, q.nlayer),) + \
+                (((q.dev_T_int, q.dev_p_int, q.dev_scat_cross_spec_int, q.dev_vmr_spec_int, q.ninterface),) if q.iso == 0 else ()):
+            self.ref.launch("calc_h2o_scat", T, p, q.dev_opac_wave, out, vmr, mass, np.int32(q.nbin), np.int32(n),
+                            block=(16, 16, 1), grid=((int(q.nbin) + 15) // 16, (int(n) + 15) // 16, 1))
+
+    def add_to_mixed_scat_cross_sect(self, q):
+        for vmr, spec, tot, n in ((q.dev_vmr_spec_lay, q.dev_scat_cross_spec_lay, q.dev_scat_cross_lay, q.nlayer),) + \
+                (((q.dev_vmr_spec_int, q.dev_scat_cross_spec_int, q.dev_scat_cross_int, q.ninterface),) if q.iso == 0 else ()):
+            self.ref.launch("add_to_mixed_scat", vmr, spec, tot, np.int32(q.nbin), np.int32(n), block=(16, 16, 1),
+                            grid=((int(q.nbin) + 15) // 16, (int(n) + 15) // 16, 1))
+
+
+@pytest.mark.parametrize("mixing", ["RO", "correlated-k"])
+def test_species_loop_vs_reference_cubin(ctx, mixing):
+    if not ref_gpu.available():
+        pytest.skip("reference cubin not built")
+    q = _store(ctx, mixing, 0)
+    comp = Compute(ctx, verbose=False)
+    ref = _RefSpecies(ref_gpu.RefCompute(ctx.device), q)
+    _species_loop(q, comp, lambda m, outs, args: stage_vs_ref(q, comp, ref, m, outs, args=args))
+
+
+def _direct_ro(ctx, mixed, new_spec, gw, gy, vmr=1.0, mass=1.0, mmm=1.0, s=1, ro=1):
+    """one add_to_mixed_opac launch on hand-made cells: mixed/new_spec are [ncell, 20]"""
+    ncell = mixed.shape[0]
+    d_mixed = ctx.to_device(mixed.reshape(-1))
+    d_spec = ctx.to_device(new_spec.reshape(-1))
+    d_vmr = ctx.to_device(np.array([vmr]))
+    d_mmm = ctx.to_device(np.array([mmm]))
+    d_gw, d_gy = ctx.to_device(gw), ctx.to_device(gy)
+    ctx.call("add_to_mixed_opac", d_vmr, d_spec, d_mixed, d_mmm, d_gw, d_gy, float(mass), int(s), int(ro), 20, ncell, 1)
+    want = O.add_to_mixed_opac(np.array([vmr]), new_spec.reshape(-1), mixed.reshape(-1), np.array([mmm]), gw, gy,
+                               mass, s, ro, 20, ncell, 1)
+    return d_mixed.get().reshape(ncell, 20), want.reshape(ncell, 20)
+
+
+def test_random_overlap_edge_cases(ctx):
+    from numpy.polynomial.legendre import leggauss
+    gy = 0.5 * leggauss(20)[0] + 0.5
+    gw = leggauss(20)[1]
+    rng = np.random.default_rng(11)
+    base = np.sort(10.0 ** rng.uniform(-4, 1, (64, 20)), axis=1)
+    other = np.sort(10.0 ** rng.uniform(-4, 1, (64, 20)), axis=1)
+    cells_m = [base, base.copy(), base.copy(), base.copy(), base.copy()]
+    cells_n = [other,                       # generic, curves cross several times
+               base.copy(),                 # identical curves: 190 exact ties per cell
+               np.ones_like(base) * 0.37,   # flat second curve: 20-fold ties
+               base[:, ::-1].copy(),        # non-monotone input
+               other * 1e-5]                # negligible -> correlated-k by the 1 % rule
+    got, want = _direct_ro(ctx, np.concatenate(cells_m), np.concatenate(cells_n), gw, gy)
+    assert_close(got, want, "random overlap edge cases")
+    # s == 0 and ro_method == 0 always add
+    got, want = _direct_ro(ctx, base, other, gw, gy, s=0)
+    assert np.array_equal(got, base + other) and np.array_equal(want, base + other)
+    got, want = _direct_ro(ctx, base, other, gw, gy, ro=0)
+    assert np.array_equal(got, base + other)
+    # the rebinned k-function is sorted and bounded by the extreme sums
+    got, _ = _direct_ro(ctx, base, other, gw, gy)
+    assert np.all(np.diff(got, axis=1) >= 0)
+    assert np.all(got[:, 0] >= base[:, 0] + other[:, 0]) and np.all(got[:, -1] <= base[:, -1] + other[:, -1])
+
+
+def test_random_overlap_rejects_unsupported_ny(ctx):
+    from helios_b200.backend import HeliosError
+    d = ctx.zeros(8 * 4)
+    one = ctx.to_device(np.ones(4))
+    with pytest.raises(HeliosError):
+        ctx.call("add_to_mixed_opac", one, d, d, one, one, one, 1.0, 1, 1, 8, 4, 1)
