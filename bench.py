@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- flux-solve throughput of the HELIOS RT hot path on B200 (one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C4]
+
+Workload at N=1: BASELINE.json configs[1] ("C2"): 100 layers x 385 bins x 20 Gauss points,
+non-isothermal layers, scattering iteration (3*scat+1 = 4 passes), one cloud deck, non-gray albedo and a
+direct beam, on seeded synthetic tables (helios_b200/synthetic.py; the Zenodo inputs are not available
+offline).  A "step" is one flux solve of the RT iteration: `populate_spectral_flux_iteratively` (all
+passes) + `integrate_flux` (computation.py:881-888).
+
+  value   layer*lambda*g-points/s = nlayer*nbin*ny*n_pass / t, inputs resident in HBM, CUDA-event timed per
+          step on the launching stream, L2 flushed (256 MiB memset) between steps, max over ranks
+  e2e     the same metric for one full RT iteration through the public API (`Compute.*`): the step's
+          temperature profile comes from pinned host memory (H2D), every temperature-dependent quantity is
+          rebuilt (interpolation, transmission, direct beam), the flux solve runs, the temperature step is
+          taken and the per-interface fluxes + new profile + convergence flags are read back (D2H)
+  N > 1   every rank owns its own atmosphere of the same shape (batched grids shard by
+          atmosphere, no data-path collective) -> weak scaling
+
+--impl reference runs the reference's own kernels.cu (compiled verbatim to oracle/_ref/, launched with the
+block/grid shapes and per-launch device syncs of computation.py) on ONE B200: the reference has no CPU
+path, so this is "the reference run on the same box" of BASELINE.json:north_star.  The NumPy oracle timed
+on the host cores is reported as `cpu_baseline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "flux_solve_layer_lambda_g_points_per_s"
+UNIT = "points/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.file,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.split(",") for r in open(self.file.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.file.name)
+        if not rows:
+            return out
+        sm = [float(r[1]) for r in rows if r[1].strip().replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].strip().replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if "Active" in r[col] and "Not" not in r[col]:
+                    reasons.add(name)
+        out["sm_mhz"] = float(np.median(sm)) if sm else None
+        out["sm_max_mhz"] = max(mx) if mx else None
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(rows)
+        return out
+
+
+def _dist():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def _prepare(workload, ctx, seed_offset=0):
+    """a Store with every coefficient of the flux solve resident on the device"""
+    from helios_b200 import synthetic
+    from helios_b200.computation import Compute
+    q = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)
+    n = int(q.nlayer)
+    # a realistic, non-isothermal hot-Jupiter profile (deep 2300 K -> 1100 K aloft)
+    q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    q.iter_value = np.int32(0)
+    refresh(comp, q)
+    ctx.synchronize()
+    return q, comp
+
+
+def refresh(comp, q):
+    """everything that depends on the temperature profile (computation.py:856-879)"""
+    comp.interpolate_temperatures(q)
+    comp.interpolate_planck(q)
+    comp.interpolate_opacities_and_scattering_cross_sections(q)
+    comp.interpolate_meanmolmass(q)
+    if q.clouds == 1:
+        comp.calc_total_g_0_of_gas_and_clouds(q)
+    comp.calculate_transmission(q)
+    comp.calculate_delta_z(q)
+    q.delta_z_lay = q.dev_delta_z_lay.get()
+    comp.hsfunc.calculate_height_z(q)
+    q.dev_z_lay.set(q.z_lay)
+    comp.calculate_direct_beamflux(q)
+
+
+def _bytes_per_cell(q):
+    """algorithmic bytes of ONE fused flux solve per layer*lambda*g cell (DESIGN.md 'roofline')"""
+    ny = float(q.ny)
+    if q.iso == 1:
+        return 6 * 8 + 8 + 8 + 16 + (8 + (8 if q.clouds == 1 else 0)) / ny
+    return 14 * 8 + 16 + 16 + 32 + (2 * 8 + 2 * 8 + (2 * 8 if q.clouds == 1 else 0)) / ny
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from helios_b200 import backend, runtime
+    world, rank, local = _dist()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = runtime.set_default_context(backend.Context(local))
+    q, comp = _prepare(args.workload, ctx, seed_offset=rank)
+    npass = comp.n_scat_passes(q)
+    cells = int(q.nlayer) * int(q.nbin) * int(q.ny)
+    points = cells * npass
+    flush = ctx.zeros(256 * 1024 * 1024 // 8)
+
+    def flux_solve(events=None):
+        if events:
+            events[0].record()
+        comp.populate_spectral_flux_iteratively(q)
+        if events:
+            events[1].record()
+        comp.integrate_flux(q)
+        if events:
+            events[2].record()
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_zero()
+        flux_solve()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [[ctx.event() for _ in range(3)] for _ in range(args.steps)]
+    launches0 = ctx.launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.fill_zero()  # L2 flush between timed steps (not inside the event bracket)
+        flux_solve(ev[k])
+    barrier()
+    launches = ctx.launch_count() - launches0 - args.steps * 0  # memsets are not kernel launches of ours
+    t_solve = sum(e[0].time_till(e[2]) for e in ev)
+    t_fband = sum(e[0].time_till(e[1]) for e in ev)
+
+    # ---- end to end through the public API, host buffers, pinned staging
+    T_host = backend.PinnedArray(int(q.nlayer) + 1)
+    T_host.array[:] = q.dev_T_lay.get()
+    nint = int(q.ninterface)
+    res_host = backend.PinnedArray(3 * nint + int(q.nlayer) + 1)
+    abort_host = backend.PinnedArray(int(q.nlayer) + 1, np.int32)
+    d2h = res_host.nbytes + abort_host.nbytes
+    h2d = T_host.nbytes
+    res_dev = ctx.zeros(3 * nint + int(q.nlayer) + 1)
+
+    def iteration():
+        T_host.h2d_async(ctx, q.dev_T_lay)
+        refresh(comp, q)
+        flux_solve()
+        comp.rad_temp_iteration(q)
+        for j, name in enumerate(("F_net", "F_up_tot", "F_down_tot")):
+            res_dev.view(j * nint, nint).copy_from(getattr(q, "dev_" + name))
+        res_dev.view(3 * nint, int(q.nlayer) + 1).copy_from(q.dev_T_lay)
+        res_host.d2h_async(ctx, res_dev)
+        abort_host.d2h_async(ctx, q.dev_abort)
+        ctx.synchronize()
+
+    for _ in range(3):
+        iteration()
+    barrier()
+    e0, e1 = ctx.event(), ctx.event()
+    e2e_steps = args.steps
+    t_e2e = 0.0
+    for _ in range(e2e_steps):
+        flush.fill_zero()
+        e0.record()
+        iteration()
+        e1.record()
+        e1.synchronize()
+        t_e2e += e0.time_till(e1)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+
+    times = torch.tensor([t_solve, t_fband, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_solve, t_fband, t_e2e = [float(v) for v in times.tolist()]
+    if rank == 0:
+        peak, peak_src = _peaks()
+        bpc = _bytes_per_cell(q)
+        t_k = t_fband / args.steps * 1e-3
+        achieved = bpc * cells / t_k / 1e9
+        line = {
+            "metric": METRIC, "value": world * points * args.steps / (t_solve * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_solve / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %d layers x %d bins x %d gauss points, %s layers, %d fused flux passes, "
+                                   "clouds=%d, dir_beam=%d; one atmosphere per GPU" %
+                                   (args.workload, q.nlayer, q.nbin, q.ny, "isothermal" if q.iso == 1 else "non-isothermal",
+                                    npass, q.clouds, q.dir_beam),
+                       "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
+                       "sharding": "one atmosphere per rank, no collective"},
+            "e2e": {"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
+                    "what": "one full RT iteration via Compute.* (T profile from pinned host, rebuild, flux solve, "
+                            "temperature step, results to host)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_fband_%s (all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_cell_per_solve": bpc,
+                         "kernel_ms": t_k * 1e3,
+                         "per_pass_equiv_GBs": achieved * npass},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(q, args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(q_dev, workload):
+    """the NumPy oracle's flux solve on this box's host cores (single process: NumPy ufuncs are single-threaded)"""
+    from oracle.pipeline import HostMirror, OracleCompute
+    m = HostMirror(q_dev)
+    oc = OracleCompute()
+    npass = (3 if m.singlewalk == 0 else 1000) * int(m.scat) + 1
+    points = int(m.nlayer) * int(m.nbin) * int(m.ny) * npass
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        oc.populate_spectral_flux_iteratively(m)
+        oc.integrate_flux(m)
+        reps += 1
+        if time.perf_counter() - t0 > 10.0 or reps >= 20:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": points * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d full %s flux solves (fband x%d + integrate_flux), NumPy fp64 oracle, %.1f s" % (reps, workload, npass, dt)}
+
+
+def run_reference(args):
+    """the reference's kernels.cu on one B200, launch shapes + per-launch syncs of computation.py"""
+    world, rank, local = _dist()
+    if rank != 0:
+        return
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/helios_ref.cubin was not built (needs /root/reference at build time)"}))
+        return
+    from helios_b200 import backend, runtime
+    ctx = runtime.set_default_context(backend.Context(local))
+    q, comp = _prepare(args.workload, ctx)
+    ref = ref_gpu.RefCompute(local)
+    npass = comp.n_scat_passes(q)
+    points = int(q.nlayer) * int(q.nbin) * int(q.ny) * npass
+    flush = ctx.zeros(256 * 1024 * 1024 // 8)
+    sampler = ClockSampler(local)
+
+    def flux_solve():
+        ref.populate_spectral_flux_iteratively(q)
+        ref.integrate_flux(q)
+
+    for _ in range(max(args.warmup, 3)):
+        flux_solve()
+    t = 0.0
+    n0 = ref.mod.launches
+    for _ in range(args.steps):
+        flush.fill_zero()
+        ctx.synchronize()
+        t0 = time.perf_counter()  # the reference syncs the device after every launch, so wall clock == device time
+        flux_solve()
+        t += time.perf_counter() - t0
+    clocks = sampler.stop()
+    value = points * args.steps / t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d layers x %d bins x %d gauss points, %d fband launches + integrate_flux_double, "
+                               "reference kernels.cu on one B200 (the reference is single-GPU, no CPU path)" %
+                               (args.workload, q.nlayer, q.nbin, q.ny, npass),
+                   "l2": "flushed between timed steps"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
+                         "sample": "reference kernels.cu (verbatim cubin) on GPU 0; %d launches per step" % ((ref.mod.launches - n0) // args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": int(ref.mod.launches - n0), "clocks": clocks}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

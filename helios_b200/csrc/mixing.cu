@@ -168,7 +168,9 @@ k_add_to_mixed_opac(const double* __restrict__ vmr, const double* __restrict__ o
     }
 }
 
-// K:3404-3440 with K:3174-3205
+// K:3404-3440 with K:3174-3205.  The cross-section goes through (n^2 - 1) with n - 1 ~ 1e-7, i.e. it
+// amplifies any last-bit difference in n by ~1e7; the libdevice calls (pow with the reference's exponents)
+// are therefore kept exactly as the reference makes them.
 __device__ __forceinline__ double h2o_refr_index(double wave, double press, double temp, double f_h2o,
                                                  double mass_h2o) {
     const double dens = f_h2o * press * mass_h2o / (hc::KBOLTZMANN * temp);
@@ -178,11 +180,12 @@ __device__ __forceinline__ double h2o_refr_index(double wave, double press, doub
     const double lamda_UV = 0.229202, lamda_IR = 5.432937;
     const double a0 = 0.244257733, a1 = 0.974634476e-2, a2 = -0.373234996e-2, a3 = 0.268678472e-3,
                  a4 = 0.158920570e-2, a5 = 0.245934259e-2, a6 = 0.900704920, a7 = -0.166626219e-1;
-    const double l2 = lamda * lamda;
-    const double A = delta * (a0 + a1 * delta + a2 * theta + a3 * l2 * theta + a4 * pow(lamda, -2.0) +
-                              a5 / (l2 - lamda_UV * lamda_UV) + a6 / (l2 - lamda_IR * lamda_IR) +
-                              a7 * (delta * delta));
-    return sqrt((2.0 * A + 1.0) / (1.0 - A));
+    const double A = delta * (a0 + a1 * delta + a2 * theta + a3 * pow(1.0 * lamda, 2.0) * theta +
+                              a4 * pow(1.0 * lamda, -2.0) +
+                              a5 / (pow(1.0 * lamda, 2.0) - pow(1.0 * lamda_UV, 2.0)) +
+                              a6 / (pow(1.0 * lamda, 2.0) - pow(1.0 * lamda_IR, 2.0)) +
+                              a7 * pow(1.0 * delta, 2.0));
+    return pow((2.0 * A + 1.0) / (1.0 - A), 0.5);
 }
 
 __global__ void k_calc_h2o_scat(const double* __restrict__ temp, const double* __restrict__ press,
@@ -196,10 +199,8 @@ __global__ void k_calc_h2o_scat(const double* __restrict__ temp, const double* _
         const double index = h2o_refr_index(wave[x], press[i], temp[i], vmr[i], mass_h2o);
         const double n_ref = vmr[i] * press[i] / (hc::KBOLTZMANN * temp[i]);
         const double King = (6.0 + 3.0 * 3e-4) / (6.0 - 7.0 * 3e-4);
-        const double i2 = index * index;
-        const double r = (i2 - 1.0) / (i2 + 2.0);
-        const double w2 = wave[x] * wave[x];
-        sc = 24.0 * (hc::PI * hc::PI * hc::PI) / ((n_ref * n_ref) * (w2 * w2)) * (r * r) * King;
+        sc = 24.0 * pow(1.0 * hc::PI, 3.0) / (pow(1.0 * n_ref, 2.0) * pow(1.0 * wave[x], 4.0)) *
+             pow((pow(1.0 * index, 2.0) - 1.0) / (pow(1.0 * index, 2.0) + 2.0), 2.0) * King;
     }
     scat_cross[e] = sc;
 }

@@ -56,7 +56,12 @@ def test_species_loop_vs_numpy_oracle(ctx, mixing, iso):
     q = _store(ctx, mixing, iso)
     comp = Compute(ctx, verbose=False)
     oc = OracleCompute()
-    _species_loop(q, comp, lambda m, outs, args: stage_vs_oracle(q, comp, oc, m, outs, args=args))
+    # calc_h2o_scat goes through n^2 - 1 with n - 1 ~ 1e-7: a last-bit difference between libdevice's
+    # pow(x, 0.5) and NumPy's sqrt is amplified ~1e7-fold, so against NumPy (only) this kernel gets 1e-7;
+    # against the reference cubin (same libdevice) it is held to 1e-10 below.
+    loose = {"calculate_H2O_Rayleigh_scattering": 1e-7, "add_to_mixed_scat_cross_sect": 1e-7}
+    _species_loop(q, comp, lambda m, outs, args: stage_vs_oracle(q, comp, oc, m, outs, args=args,
+                                                                  rtol=loose.get(m, 1e-10)))
     assert np.all(np.isfinite(q.dev_opac_wg_lay.get()))
 
 
