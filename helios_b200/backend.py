@@ -170,6 +170,10 @@ class Context:
         _check(lib().helios_ctx_set_stream(self._h, ctypes.c_void_p(int(cuda_stream) if cuda_stream else 0)),
                "helios_ctx_set_stream")
 
+    def set_fband_mode(self, mode: int):
+        """0 = automatic, 1 = one thread per column, 2 = layer-parallel only"""
+        _check(lib().helios_ctx_set_fband_mode(self._h, int(mode)), "helios_ctx_set_fband_mode")
+
     def device_info(self):
         sms = ctypes.c_int()
         l2 = ctypes.c_size_t()

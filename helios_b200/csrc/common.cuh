@@ -29,6 +29,7 @@ struct helios_ctx {
     size_t l2_bytes = 0;
     size_t total_mem = 0;
     unsigned long long launches = 0;
+    int fband_mode = 0;
     size_t bytes_allocated = 0;
     std::unordered_map<void*, size_t> allocs;
     // small per-context scratch (reductions, flags)

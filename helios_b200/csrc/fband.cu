@@ -13,6 +13,7 @@
 // on the coefficient slab of the tile (about 7 kB per column) is served by the 126 MB L2 and HBM sees
 // the coefficients once per flux solve instead of twice per pass.
 #include "common.cuh"
+#include "sweep_math.cuh"
 
 #define FB_THREADS 128
 
@@ -37,7 +38,6 @@ k_fband_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     const int ncol = s.nbin * s.ny;
     const int ntile = (ncol + FB_THREADS - 1) / FB_THREADS;
     const double neg_mu = -s.mu_star;
-    const double two_pi_eps = 2.0 * hc::PI * s.epsi;
 
     for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const int col = tile * FB_THREADS + threadIdx.x;
@@ -63,18 +63,15 @@ k_fband_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
                 const double Fup_i = F_up[e];
                 const double g0 = CLOUDS ? g0tot[x + (size_t)s.nbin * i] : s.g_0;
                 E = SCORR ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
-                const double flux_terms = P * Fd - N * Fup_i;
-                const double planck_terms = B[i] * (N + M - P);
-                double direct_terms = Fdir_i / neg_mu * (G_min * M + G_pl * N) - Fdir_above / neg_mu * P * G_min;
-                direct_terms = fmin(0.0, direct_terms);
-                Fd = 1.0 / M * (flux_terms + two_pi_eps * (1.0 - w0) / (E - w0) * planck_terms + direct_terms);
-                Fd = tiny_abs(Fd);
+                const double direct_terms = beam_source(Fdir_i, Fdir_above, neg_mu, M, G_min, N, G_pl, P, G_min);
+                Fd = tiny_to_abs(sweep_update(1.0 / M, P, N, Fd, Fup_i, source_factor(s.epsi, w0, E),
+                                              planck_iso(B[i], M, N, P), direct_terms));
                 F_down[e] = Fd;
                 Fdir_above = Fdir_i;
             }
             // ---- upward sweep, BOA -> TOA.  w0/E still hold layer 0 (K:1472) ----
             double Fdir_below = Fdir_above;  // F_dir at interface 0
-            double Fu = A_s * (Fdir_below + Fd) + (1.0 - A_s) * hc::PI * (1.0 - w0) / (E - w0) * B_surf;
+            double Fu = boa_flux(A_s, Fdir_below, Fd, w0, E, B_surf);
             F_up[col] = Fu;
 #pragma unroll 4
             for (int i = 1; i < nint; i++) {
@@ -86,12 +83,9 @@ k_fband_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
                 const double Fd_i = F_down[e];
                 const double g0 = CLOUDS ? g0tot[x + (size_t)s.nbin * (i - 1)] : s.g_0;
                 E = SCORR ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
-                const double flux_terms = P * Fu - N * Fd_i;
-                const double planck_terms = B[i - 1] * (N + M - P);
-                double direct_terms = Fdir_i / neg_mu * (G_min * N + G_pl * M) - Fdir_below / neg_mu * P * G_pl;
-                direct_terms = fmin(0.0, direct_terms);
-                Fu = 1.0 / M * (flux_terms + two_pi_eps * (1.0 - w0) / (E - w0) * planck_terms + direct_terms);
-                Fu = tiny_abs(Fu);
+                const double direct_terms = beam_source(Fdir_i, Fdir_below, neg_mu, N, G_min, M, G_pl, P, G_pl);
+                Fu = tiny_to_abs(sweep_update(1.0 / M, P, N, Fu, Fd_i, source_factor(s.epsi, w0, E),
+                                              planck_iso(B[i - 1], M, N, P), direct_terms));
                 F_up[e] = Fu;
                 Fdir_below = Fdir_i;
             }
@@ -145,7 +139,6 @@ k_fband_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     const int ncol = s.nbin * s.ny;
     const int ntile = (ncol + FB_THREADS - 1) / FB_THREADS;
     const double neg_mu = -s.mu_star;
-    const double two_pi_eps = 2.0 * hc::PI * s.epsi;
 
     for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
         const int col = tile * FB_THREADS + threadIdx.x;
@@ -173,41 +166,32 @@ k_fband_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
                 load_halves<CLOUDS, SCORR>(c, g0_lay, g0_int, e, b, s.nbin, s, up, low);
                 const double Blay = BL[i], Bint = BI[i];
                 const double Fdir_i = F_dir[e], Fcdir_i = Fc_dir[e];
-                double planck_terms, flux_terms, direct_terms;
-                // upper half: interface i+1 -> layer centre
-                if (up.dtau < s.delta_tau_limit) {
-                    planck_terms = (Bint_above + Blay) / 2.0 * (up.N + up.M - up.P);
-                } else {
-                    const double pgrad = (Blay - Bint_above) / up.dtau;
-                    planck_terms = Blay * (up.M + up.N) - Bint_above * up.P +
-                                   s.epsi / (up.E * (1.0 - up.w0 * up.g0)) * (up.P - up.M + up.N) * pgrad;
-                }
-                flux_terms = up.P * Fd - up.N * Fc_up[e];
-                direct_terms = Fcdir_i / neg_mu * (up.Gm * up.M + up.Gp * up.N) - Fdir_above / neg_mu * up.Gm * up.P;
-                direct_terms = fmin(0.0, direct_terms);
-                double Fc = 1.0 / up.M * (flux_terms + two_pi_eps * (1.0 - up.w0) / (up.E - up.w0) * planck_terms + direct_terms);
-                Fc = tiny_abs(Fc);
+                // upper half: interface i+1 -> layer centre (K:1640-1664)
+                double pt = up.dtau < s.delta_tau_limit
+                                ? planck_thin(Bint_above, Blay, up.M, up.N, up.P)
+                                : planck_grad_down(Blay, Bint_above, up.M, up.N, up.P,
+                                                   gradient_factor(s.epsi, up.w0, up.g0, up.E),
+                                                   __ddiv_rn(__dsub_rn(Blay, Bint_above), up.dtau));
+                double dr = beam_source(Fcdir_i, Fdir_above, neg_mu, up.M, up.Gm, up.N, up.Gp, up.Gm, up.P);
+                const double Fc = tiny_to_abs(sweep_update(1.0 / up.M, up.P, up.N, Fd, Fc_up[e],
+                                                           source_factor(s.epsi, up.w0, up.E), pt, dr));
                 Fc_down[e] = Fc;
-                // lower half: layer centre -> interface i
-                if (low.dtau < s.delta_tau_limit) {
-                    planck_terms = (Bint + Blay) / 2.0 * (low.N + low.M - low.P);
-                } else {
-                    const double pgrad = (Bint - Blay) / low.dtau;
-                    planck_terms = Bint * (low.M + low.N) - Blay * low.P +
-                                   s.epsi / (low.E * (1.0 - low.w0 * low.g0)) * (low.P - low.M + low.N) * pgrad;
-                }
-                flux_terms = low.P * Fc - low.N * F_up[e];
-                direct_terms = Fdir_i / neg_mu * (low.Gm * low.M + low.Gp * low.N) - Fcdir_i / neg_mu * low.P * low.Gm;
-                direct_terms = fmin(0.0, direct_terms);
-                Fd = 1.0 / low.M * (flux_terms + two_pi_eps * (1.0 - low.w0) / (low.E - low.w0) * planck_terms + direct_terms);
-                Fd = tiny_abs(Fd);
+                // lower half: layer centre -> interface i (K:1667-1691)
+                pt = low.dtau < s.delta_tau_limit
+                         ? planck_thin(Bint, Blay, low.M, low.N, low.P)
+                         : planck_grad_down(Bint, Blay, low.M, low.N, low.P,
+                                            gradient_factor(s.epsi, low.w0, low.g0, low.E),
+                                            __ddiv_rn(__dsub_rn(Bint, Blay), low.dtau));
+                dr = beam_source(Fdir_i, Fcdir_i, neg_mu, low.M, low.Gm, low.N, low.Gp, low.P, low.Gm);
+                Fd = tiny_to_abs(sweep_update(1.0 / low.M, low.P, low.N, Fc, F_up[e],
+                                              source_factor(s.epsi, low.w0, low.E), pt, dr));
                 F_down[e] = Fd;
                 Fdir_above = Fdir_i;
                 Bint_above = Bint;
             }
             // ---- upward sweep; low.w0 / low.E still hold the lower half of layer 0 (K:1704) ----
             double Fdir_below = Fdir_above;
-            double Fu = A_s * (Fdir_below + Fd) + (1.0 - A_s) * hc::PI * (1.0 - low.w0) / (low.E - low.w0) * B_surf;
+            double Fu = boa_flux(A_s, Fdir_below, Fd, low.w0, low.E, B_surf);
             F_up[col] = Fu;
             double Bint_below = BI[0];
 #pragma unroll 2
@@ -218,34 +202,26 @@ k_fband_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
                 load_halves<CLOUDS, SCORR>(c, g0_lay, g0_int, el, b, s.nbin, s, up, low);
                 const double Blay = BL[i - 1], Bint = BI[i];
                 const double Fdir_i = F_dir[e], Fcdir_l = Fc_dir[el];
-                double planck_terms, flux_terms, direct_terms;
-                // lower half: interface i-1 -> layer centre
-                if (low.dtau < s.delta_tau_limit) {
-                    planck_terms = (Bint_below + Blay) / 2.0 * (low.N + low.M - low.P);
-                } else {
-                    const double pgrad = (Bint_below - Blay) / low.dtau;
-                    planck_terms = Blay * (low.M + low.N) - Bint_below * low.P +
-                                   s.epsi / (low.E * (1.0 - low.w0 * low.g0)) * pgrad * (low.M - low.P - low.N);
-                }
-                flux_terms = low.P * Fu - low.N * Fc_down[el];
-                direct_terms = Fcdir_l / neg_mu * (low.Gm * low.N + low.Gp * low.M) - Fdir_below / neg_mu * low.P * low.Gp;
-                direct_terms = fmin(0.0, direct_terms);
-                // no tiny_abs here: the reference applies it to index i instead of i-1 (K:1763)
-                const double Fcu = 1.0 / low.M * (flux_terms + two_pi_eps * (1.0 - low.w0) / (low.E - low.w0) * planck_terms + direct_terms);
+                // lower half: interface i-1 -> layer centre (K:1744-1768)
+                double pt = low.dtau < s.delta_tau_limit
+                                ? planck_thin(Bint_below, Blay, low.M, low.N, low.P)
+                                : planck_grad_up(Blay, Bint_below, low.M, low.N, low.P,
+                                                 gradient_factor(s.epsi, low.w0, low.g0, low.E),
+                                                 __ddiv_rn(__dsub_rn(Bint_below, Blay), low.dtau));
+                double dr = beam_source(Fcdir_l, Fdir_below, neg_mu, low.N, low.Gm, low.M, low.Gp, low.P, low.Gp);
+                // no tiny-value clean-up here: the reference applies it to index i instead of i-1 (K:1763)
+                const double Fcu = sweep_update(1.0 / low.M, low.P, low.N, Fu, Fc_down[el],
+                                                source_factor(s.epsi, low.w0, low.E), pt, dr);
                 Fc_up[el] = Fcu;
-                // upper half: layer centre -> interface i
-                if (up.dtau < s.delta_tau_limit) {
-                    planck_terms = (Bint + Blay) / 2.0 * (up.N + up.M - up.P);
-                } else {
-                    const double pgrad = (Blay - Bint) / up.dtau;
-                    planck_terms = Bint * (up.M + up.N) - Blay * up.P +
-                                   s.epsi / (up.E * (1.0 - up.w0 * up.g0)) * pgrad * (up.M - up.P - up.N);
-                }
-                flux_terms = up.P * Fcu - up.N * F_down[e];
-                direct_terms = Fdir_i / neg_mu * (up.Gm * up.N + up.Gp * up.M) - Fcdir_l / neg_mu * up.P * up.Gp;
-                direct_terms = fmin(0.0, direct_terms);
-                Fu = 1.0 / up.M * (flux_terms + two_pi_eps * (1.0 - up.w0) / (up.E - up.w0) * planck_terms + direct_terms);
-                Fu = tiny_abs(Fu);
+                // upper half: layer centre -> interface i (K:1771-1795)
+                pt = up.dtau < s.delta_tau_limit
+                         ? planck_thin(Bint, Blay, up.M, up.N, up.P)
+                         : planck_grad_up(Bint, Blay, up.M, up.N, up.P,
+                                          gradient_factor(s.epsi, up.w0, up.g0, up.E),
+                                          __ddiv_rn(__dsub_rn(Blay, Bint), up.dtau));
+                dr = beam_source(Fdir_i, Fcdir_l, neg_mu, up.N, up.Gm, up.M, up.Gp, up.P, up.Gp);
+                Fu = tiny_to_abs(sweep_update(1.0 / up.M, up.P, up.N, Fcu, F_down[e],
+                                              source_factor(s.epsi, up.w0, up.E), pt, dr));
                 F_up[e] = Fu;
                 Fdir_below = Fdir_i;
                 Bint_below = Bint;
@@ -516,6 +492,23 @@ k_fband_matrix_noniso(double* __restrict__ F_down, double* __restrict__ F_up, do
 }
 
 // ------------------------------------------------------------------------------------------------
+// layer-parallel variants (fband_cp.cu)
+struct CpNonisoCoef {
+    const double *w0_u, *w0_l, *dtau_u, *dtau_l, *dtc_u, *dtc_l, *M_u, *M_l, *N_u, *N_l, *P_u, *P_l, *Gp_u,
+        *Gp_l, *Gm_u, *Gm_l;
+};
+int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double* F_dir, const double* planck,
+                     const double* w_0, const double* M, const double* N, const double* P, const double* Gp,
+                     const double* Gm, const double* albedo, const double* g0tot, double g_0, double Rstar,
+                     double a, int nint, int nbin, double f_factor, double mu_star, int ny, double epsi,
+                     int dir_beam, int clouds, int scat_corr, double i2s, int npass);
+int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                        const double* F_dir, const double* Fc_dir, const double* planck_lay,
+                        const double* planck_int, CpNonisoCoef c, const double* albedo, const double* g0_lay,
+                        const double* g0_int, double g_0, double Rstar, double a, int nint, int nbin,
+                        double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
+                        int dir_beam, int clouds, int scat_corr, double i2s, int npass);
+
 static int fband_grid(helios_ctx* ctx, int ncol) {
     const int ntile = (ncol + FB_THREADS - 1) / FB_THREADS;
     // persistent grid: at most 8 resident 128-thread blocks per SM
@@ -549,6 +542,17 @@ int helios_fband_iso(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const 
          G_plus && G_minus && surf_albedo);
     HARG(clouds == 0 || g_0_tot_lay != nullptr);
     HARG(numinterfaces > 1 && nbin > 0 && ny > 0 && npass > 0);
+    if (ctx->fband_mode != 1) {
+        const int rc = fband_iso_cp_try(ctx, F_down_wg, F_up_wg, F_dir_wg, planckband_lay, w_0, M_term, N_term,
+                                        P_term, G_plus, G_minus, surf_albedo, g_0_tot_lay, g_0, Rstar, a,
+                                        numinterfaces, nbin, f_factor, mu_star, ny, epsi, dir_beam, clouds == 1,
+                                        scat_corr == 1, i2s_transition, npass);
+        if (rc >= 0) return rc;
+        if (ctx->fband_mode == 2) {
+            helios_set_error("helios_fband_iso: shape does not fit the layer-parallel kernel");
+            return HELIOS_ERR_ARG;
+        }
+    }
     FbandScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s_transition,
                    numinterfaces, nbin, ny, dir_beam, clouds, scat_corr, npass};
     const int grid = fband_grid(ctx, nbin * ny);
@@ -587,6 +591,21 @@ int helios_fband_noniso(
     NonisoCoef c{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
                  delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
                  G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
+    if (ctx->fband_mode != 1) {
+        CpNonisoCoef cc{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
+                        delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
+                        G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
+        const int rc = fband_noniso_cp_try(ctx, F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, F_dir_wg, Fc_dir_wg,
+                                           planckband_lay, planckband_int, cc, surf_albedo, g_0_tot_lay,
+                                           g_0_tot_int, g_0, Rstar, a, numinterfaces, nbin, f_factor, mu_star, ny,
+                                           epsi, delta_tau_limit, dir_beam, clouds == 1, scat_corr == 1,
+                                           i2s_transition, npass);
+        if (rc >= 0) return rc;
+        if (ctx->fband_mode == 2) {
+            helios_set_error("helios_fband_noniso: shape does not fit the layer-parallel kernel");
+            return HELIOS_ERR_ARG;
+        }
+    }
     const int grid = fband_grid(ctx, nbin * ny);
     DISPATCH2(k_fband_noniso, clouds == 1, scat_corr == 1,
               <<<grid, FB_THREADS, 0, ctx->stream>>>(F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, F_dir_wg,

@@ -113,6 +113,13 @@ int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count) {
     return HELIOS_OK;
 }
 
+int helios_ctx_set_fband_mode(helios_ctx* ctx, int mode) {
+    HCTX(ctx);
+    HARG(mode >= 0 && mode <= 2);
+    ctx->fband_mode = mode;
+    return HELIOS_OK;
+}
+
 int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes) {
     HCTX(ctx);
     HARG(nbytes != nullptr);

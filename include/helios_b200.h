@@ -60,6 +60,10 @@ int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count);
 /* bytes currently allocated through helios_buf_alloc */
 int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes);
 
+/* flux-sweep algorithm: 0 = automatic (layer-parallel kernel whenever the shape fits, default),
+ * 1 = one thread per column (fband.cu), 2 = layer-parallel only (error if the shape does not fit) */
+int helios_ctx_set_fband_mode(helios_ctx* ctx, int mode);
+
 /* buffers: replace gpuarray.to_gpu / cuda.mem_alloc / .get() (Q:463-665) */
 int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr);
 int helios_buf_free(helios_ctx* ctx, void* dptr);

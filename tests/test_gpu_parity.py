@@ -24,6 +24,10 @@ NONISO_OUT = [b + s for s in ("_upper", "_lower") for b in
 
 def _variant(name, ctx):
     kw = dict(SMALL)
+    if name == "C1_scorr":
+        kw["nlayer"] = 26  # not a multiple of the layer-chunk size of the layer-parallel sweep
+    if name == "C2_scorr":
+        kw["nlayer"] = 23
     cfg = {"C1": "C1", "C1_scorr": "C1", "C1_beam_geom": "C1", "C2": "C2", "C2_scorr": "C2", "C1_noscat": "C1",
            "C2_60deg": "C2"}[name]
     q = synthetic.make_store(cfg, ctx=ctx, **kw)
@@ -41,6 +45,8 @@ def _variant(name, ctx):
         q.mu_star = np.float64(np.cos((180 - 80.0) * np.pi / 180.0))
     if name == "C1_noscat":
         q.scat = np.int32(0)
+    if name in ("C1_scorr", "C2_scorr"):
+        pass
     # a non-trivial temperature profile so that interpolation boxes, Planck slopes etc. are exercised
     rng = np.random.default_rng(7)
     n = int(q.nlayer)
@@ -86,6 +92,16 @@ VARIANTS = ["C1", "C1_scorr", "C1_beam_geom", "C1_noscat", "C2", "C2_scorr", "C2
 # with the singular G+/- of the 60 degree default, direct_terms = F_dir/mu (G- M + G+ N) - ... subtracts terms
 # of size 1e8 * F_dir; the fluxes of two correct evaluations then agree to ~1e-9, not 1e-10
 FLUX_TOL = {"C2_60deg": {"F_down_wg": 1e-8, "Fc_down_wg": 1e-8, "F_up_wg": 1e-8, "Fc_up_wg": 1e-8}}
+# NumPy evaluates the direct-beam source without fused multiply-adds.  That source is a difference of
+# products ~1e5-1e6 times larger than itself near the top of the atmosphere, so the diffuse downward flux of
+# a correct unfused evaluation differs from the fused one by a few 1e-10 wherever the beam is on.  Against
+# NumPy those fluxes are held to 1e-9; against the reference's own kernels they are held to 1e-10 (and in
+# fact agree to ~1e-14, see sweep_math.cuh).  In the singular 60 degree case G+/- themselves are not compared
+# against NumPy (None): G+ additionally cancels in 1/eps + 1/(mu* E (1 - w0 g0)).
+_BEAM = {"F_down_wg": 1e-9, "Fc_down_wg": 1e-9, "F_up_wg": 1e-9, "Fc_up_wg": 1e-9}
+NUMPY_TOL = {"C2": _BEAM, "C2_scorr": _BEAM, "C1_beam_geom": _BEAM,
+             "C2_60deg": dict(FLUX_TOL["C2_60deg"], G_plus_upper=None, G_plus_lower=None, G_minus_upper=None,
+                              G_minus_lower=None)}
 
 
 def _print_report(against, variant, report):
@@ -104,7 +120,7 @@ def test_every_kernel_against_numpy_oracle(ctx, variant):
     bad = Failures()
 
     def checker(method, outputs):
-        report[method] = stage_vs_oracle(q, comp, oc, method, outputs, soft=bad, rtol=FLUX_TOL.get(variant, 1e-10))
+        report[method] = stage_vs_oracle(q, comp, oc, method, outputs, soft=bad, rtol=NUMPY_TOL.get(variant, 1e-10))
 
     _drive(q, comp, checker)
     _print_report("NumPy oracle", variant, report)
@@ -191,7 +207,10 @@ def test_fused_passes_equal_separate_launches(ctx):
     comp.fuse_passes = False
     comp.populate_spectral_flux_iteratively(q)
     for n, f in zip(("F_down_wg", "F_up_wg", "Fc_down_wg", "Fc_up_wg"), fused):
-        assert np.array_equal(getattr(q, "dev_" + n).get(), f), n
+        sep = getattr(q, "dev_" + n).get()
+        diff = np.flatnonzero(~((sep == f) | (np.isnan(sep) & np.isnan(f))))
+        assert diff.size == 0, "%s: %d entries differ, first at %d: %r vs %r (NaNs: %d)" % (
+            n, diff.size, diff[0], sep[diff[0]], f[diff[0]], int(np.isnan(f).sum()))
 
 
 def test_closed_form_pure_absorption_column(ctx):
@@ -210,3 +229,32 @@ def test_closed_form_pure_absorption_column(ctx):
         want = T[i] * Fd[i + 1] + np.pi * B[:, i] * (1.0 - T[i])
         assert_close(Fd[i], want, "closed form layer %d" % i, rtol=1e-9)
     assert np.all(q.dev_w_0.get()[:nl * nb * ny] == 0.0)
+
+
+@pytest.mark.parametrize("variant", ["C1", "C1_scorr", "C1_beam_geom", "C2", "C2_scorr"])
+def test_layer_parallel_sweep_equals_column_sweep(ctx, variant):
+    """the two flux-sweep algorithms (fband.cu: one thread per column, serial over layers; fband_cp.cu:
+    layer-parallel with composed affine maps) agree to rounding, over several consecutive flux solves"""
+    q = _variant(variant, ctx)
+    comp = Compute(ctx, verbose=False)
+    steps = ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+             "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass"]
+    if q.clouds == 1:
+        steps.append("calc_total_g_0_of_gas_and_clouds")
+    steps += ["calculate_transmission", "calculate_direct_beamflux"]
+    for m in steps:
+        getattr(comp, m)(q)
+    names = ["F_down_wg", "F_up_wg"] + ([] if q.iso == 1 else ["Fc_down_wg", "Fc_up_wg"])
+    results = {}
+    try:
+        for mode in (1, 2):
+            ctx.set_fband_mode(mode)
+            for n in names:
+                getattr(q, "dev_" + n).fill_zero()
+            for _ in range(3):
+                comp.populate_spectral_flux_iteratively(q)
+            results[mode] = [getattr(q, "dev_" + n).get() for n in names]
+    finally:
+        ctx.set_fband_mode(0)
+    for n, a, b in zip(names, results[1], results[2]):
+        assert_close(b, a, "layer-parallel vs column sweep: " + n, rtol=1e-12)

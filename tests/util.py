@@ -83,14 +83,15 @@ def assert_close_G(q, got, ref, name, rtol=RTOL, soft=None):
     """G+/-: the denominator E/eps^2 (E-w0)(1-w0 g0) - 1/mu*^2 cancels to O(w0) -- exactly, for the default
     eps = 1/2 with a 60 degree beam -- so every correct fp64 evaluation carries a relative error of a few
     ulp times the condition number of that subtraction.  Cells are held to rtol + 64 ulp * cond; cells
-    where the subtraction keeps less than ~4 digits (cond > 1e12: the result is the +-1e8 limiter or
-    rounding noise in the reference itself) are not compared."""
+    where the subtraction keeps less than ~8 digits (cond > 1e8: with the denominator within a few ulp of
+    zero the result is the +-1e8 limiter or rounding noise in the reference itself, and the condition
+    estimate is no longer meaningful) are not compared."""
     got = np.asarray(got, np.float64).reshape(-1)
     ref = np.asarray(ref, np.float64).reshape(-1)
-    n = min(got.size, ref.size)
-    cond = g_conditioning(q, name)[:n]
-    got, ref = got[:n], ref[:n]
-    ok = cond <= 1e12
+    cond = g_conditioning(q, name)
+    n = min(got.size, ref.size, cond.size)
+    cond, got, ref = cond[:n], got[:n], ref[:n]
+    ok = cond <= 1e8
     allowed = rtol + 64 * 2.2e-16 * cond
     scale = np.max(np.abs(ref[ok])) if ok.any() else 0.0
     with np.errstate(invalid="ignore", divide="ignore"):
@@ -129,6 +130,8 @@ def stage_vs_oracle(q, comp, oc, method, outputs, rtol=RTOL, args=(), soft=None)
         got = getattr(q, "dev_" + name).get()
         ref = np.asarray(getattr(m, "dev_" + name))
         n = min(got.size, ref.size)
+        if isinstance(rtol, dict) and name in rtol and rtol[name] is None:
+            continue
         if name.startswith("G_"):
             errs[name] = assert_close_G(q, got, ref, name, RTOL if isinstance(rtol, dict) else rtol, soft)
             continue
