@@ -56,6 +56,8 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
     double* mUA = mDB + (size_t)nch * COLS;
     double* mUB = mUA + (size_t)nch * COLS;
     double* fu0 = mUB + (size_t)nch * COLS;            // [COLS]
+    double* edgeD = fu0 + COLS;                        // [nch][COLS] walked F_down at each chunk's bottom
+    double* edgeU = edgeD + (size_t)nch * COLS;        // [nch][COLS] walked F_up at each chunk's top
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + COLS - 1) / COLS;
 
@@ -138,9 +140,14 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
                         if (last && live) F_down[col + (size_t)ncol * i] = F;
                     }
                 }
+                edgeD[w * COLS + c] = Fd_reg[0];
             }
             // ================= upward sweep =================
             if (w == 0) fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
+            __syncthreads();
+            // the flux at the chunk's top interface is the value the chunk above WALKED (and stored), not the
+            // composed one: every flux consumed later is bit-identical to what the output arrays hold
+            Fd_in = (w == nch - 1) ? toa : edgeD[(w + 1) * COLS + c];
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
@@ -179,7 +186,10 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
                         if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
                     }
                 }
+                edgeU[w * COLS + c] = F;
             }
+            __syncthreads();
+            Fu_reg[0] = (w == 0) ? fu0[c] : edgeU[(w - 1) * COLS + c];
         }
         (void)Fu_in;
         __syncthreads();  // the next tile overwrites the shared coefficient planes
@@ -220,6 +230,8 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
     double* mUA = mDB + (size_t)nch * COLS;
     double* mUB = mUA + (size_t)nch * COLS;
     double* fu0 = mUB + (size_t)nch * COLS;
+    double* edgeD = fu0 + COLS;
+    double* edgeU = edgeD + (size_t)nch * COLS;
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + COLS - 1) / COLS;
 
@@ -351,9 +363,12 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
                         if (last && live) F_down[col + (size_t)ncol * i] = F;
                     }
                 }
+                edgeD[w * COLS + c] = Fd_reg[0];
             }
             // ================= upward sweep: lower half, then upper half =================
             if (w == 0) fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
+            __syncthreads();
+            Fd_in = (w == nch - 1) ? toa : edgeD[(w + 1) * COLS + c];  // walked value, see the iso kernel
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
@@ -395,7 +410,10 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
                         if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
                     }
                 }
+                edgeU[w * COLS + c] = F;
             }
+            __syncthreads();
+            Fu_reg[0] = (w == 0) ? fu0[c] : edgeU[(w - 1) * COLS + c];
         }
         __syncthreads();
     }
@@ -414,7 +432,7 @@ struct CpPlan {
 static bool cp_plan(helios_ctx* ctx, int nlay, int ncol, int planes, int cols, int ch, CpPlan* p) {
     const int nchunk = (nlay + ch - 1) / ch;
     const int threads = nchunk * cols;
-    const size_t smem = ((size_t)planes * nlay * cols + (size_t)4 * nchunk * cols + cols) * sizeof(double);
+    const size_t smem = ((size_t)planes * nlay * cols + (size_t)6 * nchunk * cols + cols) * sizeof(double);
     if (nchunk > 32 || threads > 1024 || smem > 227 * 1024) return false;
     p->cols = cols;
     p->ch = ch;
