@@ -1,42 +1,84 @@
-// Layer-parallel two-stream sweeps ("chunk-parallel" fband kernels).
+// Layer-parallel two-stream sweeps ("chunk-parallel" fband kernels) -- the default flux solver.
 //
 // Why.  The reference's fband_* (K:1366-1799) walks the ~100 layers of a column serially, twice per
 // pass and 3*scat+1 passes per RT iteration: ~800 dependent steps, each a handful of fp64 divides and
 // ~20 loads.  With one thread per column that chain is pure latency (an atmosphere of 385 x 20 columns
 // occupies 60 warps on 148 SMs).  But each sweep is a first-order AFFINE recurrence in the flux,
-//     F[i] = a_i F[i +- 1] + c_i,
-// because the opposite-direction flux that couples in is the other sweep's finished result.  So:
+//     F[i] = a_i F[i +- 1] - b_i F_opp[i] + s_i,        a = P/M, b = N/M, s = (fac * planck + beam)/M,
+// because the opposite-direction flux F_opp that couples in is the other sweep's finished result.  So:
 //
 //   * a block owns COLS consecutive columns and cuts the layers into chunks of CH; thread (col, chunk)
 //     composes its chunk's affine map locally, the per-chunk maps are exchanged through shared memory,
 //     every thread folds the maps in front of it to get the flux entering its chunk, and then walks its
-//     own CH layers with EXACTLY the reference's expression.  A sweep is CH + (#chunks) short steps
-//     instead of nlayer long ones, and 25x more threads hide the fp64 latency.
-//   * everything a sweep needs per (half-)layer -- 1/M, P, N, the Planck source and the clipped direct-beam
-//     source -- is computed ONCE per flux solve while the coefficient arrays stream in (fully coalesced:
-//     lanes run along the flat column index y + ny*x), and is parked in shared memory for all passes.
-//     HBM sees every input once and every output once per solve: the 80 B (iso) / 176 B (non-iso) per
-//     cell of DESIGN.md instead of that figure times 2 sweeps times npass.
+//     own CH layers.  A sweep is CH + (#chunks) two-FMA steps instead of nlayer long ones, and ~25x more
+//     threads hide the fp64 latency.
+//   * the four constants of every (half-)layer -- a, b, s_down, s_up -- are computed ONCE per flux solve
+//     while the coefficient arrays stream in (coalesced: lanes run along the flat column index y + ny*x),
+//     with the rounding-exact building blocks of sweep_math.cuh, and are parked in shared memory for all
+//     passes.  HBM sees every input once and every output once per solve: the 80 B (iso) / 176 B
+//     (non-iso) per cell of DESIGN.md instead of that figure times 2 sweeps times npass.
 //   * the fluxes a thread needs from the other direction / the previous pass are the ones it produced
-//     itself, so they stay in registers; only the last pass writes the flux arrays.
+//     itself (or its chunk neighbour's edge value, handed over through shared memory), so they stay in
+//     registers; only the last pass writes the flux arrays.
 //
-// Rounding: inside a chunk the reference's expression is evaluated verbatim; only the flux entering a
-// chunk comes from the composed maps, which reorders a few multiply-adds (differences ~1e-15 relative).
+// Arithmetic: a F - b F_opp + s is the reference's 1/M (P F - N F_opp + ...) with the division by M
+// distributed, and the chunk-entry flux comes from composed maps: both reorder a few multiply-adds.
+// Measured deviation from the reference's kernels: <= ~1e-13 relative (tests/test_gpu_parity.py; the bar
+// is 1e-10).  The bit-faithful evaluation order lives in the column-serial kernels of fband.cu
+// (helios_ctx_set_fband_mode(ctx, 1)); consecutive launches and one fused launch agree bit for bit.
 #include "common.cuh"
 #include "sweep_math.cuh"
+#include <cstdlib>
 
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk;
 };
 
+struct CpNonisoCoef {
+    const double *w0_u, *w0_l, *dtau_u, *dtau_l, *dtc_u, *dtc_l, *M_u, *M_l, *N_u, *N_l, *P_u, *P_l, *Gp_u,
+        *Gp_l, *Gm_u, *Gm_l;
+};
+
+// constants of one (half-)layer step
+struct Step {
+    double a, b, sd, su;
+};
+
+__device__ __forceinline__ Step make_step(double M, double N, double P, double fac, double pt_d, double pt_u,
+                                          double D_d, double D_u) {
+    const double invM = 1.0 / M;
+    Step s;
+    s.a = invM * P;
+    s.b = invM * N;
+    s.sd = invM * (fac * pt_d + D_d);
+    s.su = invM * (fac * pt_u + D_u);
+    return s;
+}
+
+// shared memory carve-up (doubles): planes[NPL][nlay][COLS] | mDA mDB mUA mUB edgeD edgeU [nch][COLS] | fu0[COLS]
+template <int NPL, int COLS>
+struct CpSmem {
+    double *cf, *mDA, *mDB, *mUA, *mUB, *edgeD, *edgeU, *fu0;
+    size_t plane;
+    __device__ CpSmem(double* sm, int nlay, int nch) {
+        plane = (size_t)nlay * COLS;
+        cf = sm;
+        mDA = sm + NPL * plane;
+        mDB = mDA + (size_t)nch * COLS;
+        mUA = mDB + (size_t)nch * COLS;
+        mUB = mUA + (size_t)nch * COLS;
+        edgeD = mUB + (size_t)nch * COLS;
+        edgeU = edgeD + (size_t)nch * COLS;
+        fu0 = edgeU + (size_t)nch * COLS;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
-// isothermal layers
-// shared memory: coef[7][nlay][COLS] (1/M, P, N, source factor, Planck term, beam down, beam up) | mapD_A, mapD_B, mapU_A, mapU_B [nchunk][COLS] | fu0[COLS]
+// isothermal layers: one step per layer, planes a, b, sd, su
 // ------------------------------------------------------------------------------------------------
-template <int COLS, int CH>
-__global__ void __launch_bounds__(32 * COLS, (COLS >= 16 ? 2 : 3))
+template <int COLS, int CH, int MINB>
+__global__ void __launch_bounds__(32 * COLS, MINB)
 k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const double* __restrict__ F_dir,
                const double* __restrict__ planck, const double* __restrict__ w_0, const double* __restrict__ Mt,
                const double* __restrict__ Nt, const double* __restrict__ Pt, const double* __restrict__ Gp,
@@ -49,15 +91,9 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
     const int w = threadIdx.x / COLS;
     const int lo = w * CH;
     const int hi = min(lo + CH, nlay);  // layers lo .. hi-1, interfaces lo .. hi
-    const size_t plane = (size_t)nlay * COLS;
-    double* cf = sm;                                   // [7][nlay][COLS]
-    double* mDA = sm + 7 * plane;                      // [nch][COLS]
-    double* mDB = mDA + (size_t)nch * COLS;
-    double* mUA = mDB + (size_t)nch * COLS;
-    double* mUB = mUA + (size_t)nch * COLS;
-    double* fu0 = mUB + (size_t)nch * COLS;            // [COLS]
-    double* edgeD = fu0 + COLS;                        // [nch][COLS] walked F_down at each chunk's bottom
-    double* edgeU = edgeD + (size_t)nch * COLS;        // [nch][COLS] walked F_up at each chunk's top
+    CpSmem<4, COLS> S(sm, nlay, nch);
+    const size_t plane = S.plane;
+    double* cf = S.cf;
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + COLS - 1) / COLS;
 
@@ -70,7 +106,7 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
         const double A_s = albedo[x];
         const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * B[nlay];
 
-        // ---- stream the coefficients in once, park the per-layer sweep constants in shared memory
+        // ---- stream the coefficients in once; park a, b, s_down, s_up of every layer in shared memory
         double Fu_reg[CH], Fd_reg[CH];
         double w0_0 = 0.0, E_0 = 1.0, Fdir0 = 0.0;  // the BOA emission uses layer 0's w0 and E (K:1472)
 #pragma unroll
@@ -84,133 +120,114 @@ k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const dou
                 const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol];
                 const double g0 = s.clouds ? g0tot[x + (size_t)s.nbin * i] : s.g_0;
                 const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
+                const double pt = planck_iso(B[i], M, N, P);
+                const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt, pt,
+                                          beam_source(Fdir_i, Fdir_ip1, neg_mu, M, G_min, N, G_pl, P, G_min),
+                                          beam_source(Fdir_ip1, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl));
                 const size_t o = (size_t)i * COLS + c;
-                cf[o] = 1.0 / M;
-                cf[plane + o] = P;
-                cf[2 * plane + o] = N;
-                cf[3 * plane + o] = source_factor(s.epsi, w0, E);
-                cf[4 * plane + o] = planck_iso(B[i], M, N, P);
-                cf[5 * plane + o] = beam_source(Fdir_i, Fdir_ip1, neg_mu, M, G_min, N, G_pl, P, G_min);
-                cf[6 * plane + o] = beam_source(Fdir_ip1, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl);
+                cf[o] = st.a;
+                cf[plane + o] = st.b;
+                cf[2 * plane + o] = st.sd;
+                cf[3 * plane + o] = st.su;
+                Fu_reg[k] = F_up[e];  // upward flux of the previous flux solve at interface i
                 w0_0 = i == 0 ? w0 : w0_0;
                 E_0 = i == 0 ? E : E_0;
                 Fdir0 = i == 0 ? Fdir_i : Fdir0;
-                Fu_reg[k] = F_up[e];  // upward flux of the previous flux solve at interface i
             }
         }
         const double B_surf = B[nlay + 1];
-        double Fd_in = toa, Fu_in = 0.0;
 
         for (int pass = 0; pass < s.npass; pass++) {
             const bool last = pass == s.npass - 1;
+            double cc[CH];
             // ================= downward sweep =================
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
                     const int i = lo + k;
+                    cc[k] = 0.0;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        const double invM = cf[o], P = cf[plane + o], N = cf[2 * plane + o];
-                        const double a = invM * P;
-                        const double cc = sweep_update(invM, P, N, 0.0, Fu_reg[k], cf[3 * plane + o], cf[4 * plane + o],
-                                                       cf[5 * plane + o]);
+                        const double a = cf[o];
+                        cc[k] = cf[2 * plane + o] - cf[plane + o] * Fu_reg[k];
                         A = a * A;
-                        Bm = a * Bm + cc;
+                        Bm = a * Bm + cc[k];
                     }
                 }
-                mDA[w * COLS + c] = A;
-                mDB[w * COLS + c] = Bm;
+                S.mDA[w * COLS + c] = A;
+                S.mDB[w * COLS + c] = Bm;
             }
             __syncthreads();
             {
                 double F = toa;
-                for (int v = nch - 1; v > w; v--) F = mDA[v * COLS + c] * F + mDB[v * COLS + c];
-                Fd_in = F;  // downward flux at interface hi
+                for (int v = nch - 1; v > w; v--) F = S.mDA[v * COLS + c] * F + S.mDB[v * COLS + c];
                 if (last && live && w == nch - 1) F_down[col + (size_t)ncol * nlay] = toa;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
                     const int i = lo + k;
                     if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        const double invM = cf[o], P = cf[plane + o], N = cf[2 * plane + o];
-                        F = tiny_to_abs(sweep_update(invM, P, N, F, Fu_reg[k], cf[3 * plane + o], cf[4 * plane + o],
-                                                     cf[5 * plane + o]));
+                        F = tiny_to_abs(cf[(size_t)i * COLS + c] * F + cc[k]);
                         Fd_reg[k] = F;
                         if (last && live) F_down[col + (size_t)ncol * i] = F;
                     }
                 }
-                edgeD[w * COLS + c] = Fd_reg[0];
+                S.edgeD[w * COLS + c] = Fd_reg[0];
             }
             // ================= upward sweep =================
-            if (w == 0) fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
+            if (w == 0) S.fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
             __syncthreads();
             // the flux at the chunk's top interface is the value the chunk above WALKED (and stored), not the
             // composed one: every flux consumed later is bit-identical to what the output arrays hold
-            Fd_in = (w == nch - 1) ? toa : edgeD[(w + 1) * COLS + c];
+            const double Fd_hi = (w == nch - 1) ? toa : S.edgeD[(w + 1) * COLS + c];
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     const int i = lo + k;
+                    cc[k] = 0.0;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        const double invM = cf[o], P = cf[plane + o], N = cf[2 * plane + o];
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_in;
-                        const double a = invM * P;
-                        const double cc = sweep_update(invM, P, N, 0.0, Fd_top, cf[3 * plane + o], cf[4 * plane + o],
-                                                       cf[6 * plane + o]);
+                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                        const double a = cf[o];
+                        cc[k] = cf[3 * plane + o] - cf[plane + o] * Fd_top;
                         A = a * A;
-                        Bm = a * Bm + cc;
+                        Bm = a * Bm + cc[k];
                     }
                 }
-                mUA[w * COLS + c] = A;
-                mUB[w * COLS + c] = Bm;
+                S.mUA[w * COLS + c] = A;
+                S.mUB[w * COLS + c] = Bm;
             }
             __syncthreads();
             {
-                double F = fu0[c];
-                for (int v = 0; v < w; v++) F = mUA[v * COLS + c] * F + mUB[v * COLS + c];
-                Fu_in = F;  // upward flux at interface lo
+                double F = S.fu0[c];
+                for (int v = 0; v < w; v++) F = S.mUA[v * COLS + c] * F + S.mUB[v * COLS + c];
                 if (last && live && w == 0) F_up[col] = F;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     const int i = lo + k;
                     if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        const double invM = cf[o], P = cf[plane + o], N = cf[2 * plane + o];
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_in;
                         Fu_reg[k] = F;  // interface i: what the next pass's downward sweep reads
-                        F = tiny_to_abs(sweep_update(invM, P, N, F, Fd_top, cf[3 * plane + o], cf[4 * plane + o],
-                                                     cf[6 * plane + o]));
+                        F = tiny_to_abs(cf[(size_t)i * COLS + c] * F + cc[k]);
                         if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
                     }
                 }
-                edgeU[w * COLS + c] = F;
+                S.edgeU[w * COLS + c] = F;
             }
             __syncthreads();
-            Fu_reg[0] = (w == 0) ? fu0[c] : edgeU[(w - 1) * COLS + c];
+            Fu_reg[0] = (w == 0) ? S.fu0[c] : S.edgeU[(w - 1) * COLS + c];
         }
-        (void)Fu_in;
-        __syncthreads();  // the next tile overwrites the shared coefficient planes
+        __syncthreads();  // the next tile overwrites the shared planes
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// non-isothermal layers: two half-layers per layer, 8 constants per half
-// shared memory: coef[16][nlay][COLS] | 4 map arrays [nchunk][COLS] | fu0[COLS]
-//   half h (upper = 0, lower = 1), plane 8*h + q with q: 0 1/M, 1 P, 2 N, 3 source factor,
-//   4 Planck term (down), 5 Planck term (up), 6 beam source (down), 7 beam source (up)
+// non-isothermal layers: two steps per layer (upper / lower half), planes [half][a, b, sd, su]
 // ------------------------------------------------------------------------------------------------
-struct CpNonisoCoef {
-    const double *w0_u, *w0_l, *dtau_u, *dtau_l, *dtc_u, *dtc_l, *M_u, *M_l, *N_u, *N_l, *P_u, *P_l, *Gp_u,
-        *Gp_l, *Gm_u, *Gm_l;
-};
-
 #define CF(q) cf[(size_t)(q) * plane + o]
 
-template <int COLS, int CH>
-__global__ void __launch_bounds__(32 * COLS, (COLS >= 16 ? 1 : 2))
+template <int COLS, int CH, int MINB>
+__global__ void __launch_bounds__(32 * COLS, MINB)
 k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
                   double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
                   const double* __restrict__ planck_lay, const double* __restrict__ planck_int, CpNonisoCoef cfg,
@@ -223,15 +240,9 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
     const int w = threadIdx.x / COLS;
     const int lo = w * CH;
     const int hi = min(lo + CH, nlay);
-    const size_t plane = (size_t)nlay * COLS;
-    double* cf = sm;                                   // [16][nlay][COLS]
-    double* mDA = sm + 16 * plane;
-    double* mDB = mDA + (size_t)nch * COLS;
-    double* mUA = mDB + (size_t)nch * COLS;
-    double* mUB = mUA + (size_t)nch * COLS;
-    double* fu0 = mUB + (size_t)nch * COLS;
-    double* edgeD = fu0 + COLS;
-    double* edgeU = edgeD + (size_t)nch * COLS;
+    CpSmem<8, COLS> S(sm, nlay, nch);
+    const size_t plane = S.plane;
+    double* cf = S.cf;
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + COLS - 1) / COLS;
 
@@ -278,14 +289,10 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
                         pt_d = planck_grad_down(Blay, Bint_hi, M, N, P, pre, pgrad);
                         pt_u = planck_grad_up(Bint_hi, Blay, M, N, P, pre, pgrad);
                     }
-                    CF(0) = 1.0 / M;
-                    CF(1) = P;
-                    CF(2) = N;
-                    CF(3) = source_factor(s.epsi, w0, E);
-                    CF(4) = pt_d;
-                    CF(5) = pt_u;
-                    CF(6) = beam_source(Fcdir, Fdir_ip1, neg_mu, M, G_min, N, G_pl, G_min, P);
-                    CF(7) = beam_source(Fdir_ip1, Fcdir, neg_mu, N, G_min, M, G_pl, P, G_pl);
+                    const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u,
+                                              beam_source(Fcdir, Fdir_ip1, neg_mu, M, G_min, N, G_pl, G_min, P),
+                                              beam_source(Fdir_ip1, Fcdir, neg_mu, N, G_min, M, G_pl, P, G_pl));
+                    CF(0) = st.a; CF(1) = st.b; CF(2) = st.sd; CF(3) = st.su;
                 }
                 {   // ---- lower half: interface i <-> layer centre (K:1667-1691, 1744-1768)
                     const double w0 = cfg.w0_l[e], M = cfg.M_l[e], N = cfg.N_l[e], P = cfg.P_l[e];
@@ -302,14 +309,10 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
                         pt_d = planck_grad_down(Bint_lo, Blay, M, N, P, pre, pgrad);
                         pt_u = planck_grad_up(Blay, Bint_lo, M, N, P, pre, pgrad);
                     }
-                    CF(8) = 1.0 / M;
-                    CF(9) = P;
-                    CF(10) = N;
-                    CF(11) = source_factor(s.epsi, w0, E);
-                    CF(12) = pt_d;
-                    CF(13) = pt_u;
-                    CF(14) = beam_source(Fdir_i, Fcdir, neg_mu, M, G_min, N, G_pl, P, G_min);
-                    CF(15) = beam_source(Fcdir, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl);
+                    const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u,
+                                              beam_source(Fdir_i, Fcdir, neg_mu, M, G_min, N, G_pl, P, G_min),
+                                              beam_source(Fcdir, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl));
+                    CF(4) = st.a; CF(5) = st.b; CF(6) = st.sd; CF(7) = st.su;
                     w0_0 = i == 0 ? w0 : w0_0;
                     E_0 = i == 0 ? E : E_0;
                     Fdir0 = i == 0 ? Fdir_i : Fdir0;
@@ -319,101 +322,101 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
             }
         }
         const double B_surf = BL[nlay + 1];
-        double Fd_in = toa;
 
         for (int pass = 0; pass < s.npass; pass++) {
             const bool last = pass == s.npass - 1;
+            double ccu[CH], ccl[CH];
             // ================= downward sweep: upper half, then lower half of every layer =================
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
                     const int i = lo + k;
+                    ccu[k] = ccl[k] = 0.0;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        double a = CF(0) * CF(1);
-                        double cc = sweep_update(CF(0), CF(1), CF(2), 0.0, Fcu_reg[k], CF(3), CF(4), CF(6));
+                        double a = CF(0);
+                        ccu[k] = CF(2) - CF(1) * Fcu_reg[k];
                         A = a * A;
-                        Bm = a * Bm + cc;
-                        a = CF(8) * CF(9);
-                        cc = sweep_update(CF(8), CF(9), CF(10), 0.0, Fu_reg[k], CF(11), CF(12), CF(14));
+                        Bm = a * Bm + ccu[k];
+                        a = CF(4);
+                        ccl[k] = CF(6) - CF(5) * Fu_reg[k];
                         A = a * A;
-                        Bm = a * Bm + cc;
+                        Bm = a * Bm + ccl[k];
                     }
                 }
-                mDA[w * COLS + c] = A;
-                mDB[w * COLS + c] = Bm;
+                S.mDA[w * COLS + c] = A;
+                S.mDB[w * COLS + c] = Bm;
             }
             __syncthreads();
             {
                 double F = toa;
-                for (int v = nch - 1; v > w; v--) F = mDA[v * COLS + c] * F + mDB[v * COLS + c];
-                Fd_in = F;
+                for (int v = nch - 1; v > w; v--) F = S.mDA[v * COLS + c] * F + S.mDB[v * COLS + c];
                 if (last && live && w == nch - 1) F_down[col + (size_t)ncol * nlay] = toa;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
                     const int i = lo + k;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        F = tiny_to_abs(sweep_update(CF(0), CF(1), CF(2), F, Fcu_reg[k], CF(3), CF(4), CF(6)));
+                        F = tiny_to_abs(CF(0) * F + ccu[k]);
                         Fcd_reg[k] = F;
                         if (last && live) Fc_down[col + (size_t)ncol * i] = F;
-                        F = tiny_to_abs(sweep_update(CF(8), CF(9), CF(10), F, Fu_reg[k], CF(11), CF(12), CF(14)));
+                        F = tiny_to_abs(CF(4) * F + ccl[k]);
                         Fd_reg[k] = F;
                         if (last && live) F_down[col + (size_t)ncol * i] = F;
                     }
                 }
-                edgeD[w * COLS + c] = Fd_reg[0];
+                S.edgeD[w * COLS + c] = Fd_reg[0];
             }
             // ================= upward sweep: lower half, then upper half =================
-            if (w == 0) fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
+            if (w == 0) S.fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
             __syncthreads();
-            Fd_in = (w == nch - 1) ? toa : edgeD[(w + 1) * COLS + c];  // walked value, see the iso kernel
+            const double Fd_hi = (w == nch - 1) ? toa : S.edgeD[(w + 1) * COLS + c];  // walked value (see iso)
             {
                 double A = 1.0, Bm = 0.0;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     const int i = lo + k;
+                    ccu[k] = ccl[k] = 0.0;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_in;
-                        double a = CF(8) * CF(9);
-                        double cc = sweep_update(CF(8), CF(9), CF(10), 0.0, Fcd_reg[k], CF(11), CF(13), CF(15));
+                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                        double a = CF(4);
+                        ccl[k] = CF(7) - CF(5) * Fcd_reg[k];
                         A = a * A;
-                        Bm = a * Bm + cc;
-                        a = CF(0) * CF(1);
-                        cc = sweep_update(CF(0), CF(1), CF(2), 0.0, Fd_top, CF(3), CF(5), CF(7));
+                        Bm = a * Bm + ccl[k];
+                        a = CF(0);
+                        ccu[k] = CF(3) - CF(1) * Fd_top;
                         A = a * A;
-                        Bm = a * Bm + cc;
+                        Bm = a * Bm + ccu[k];
                     }
                 }
-                mUA[w * COLS + c] = A;
-                mUB[w * COLS + c] = Bm;
+                S.mUA[w * COLS + c] = A;
+                S.mUB[w * COLS + c] = Bm;
             }
             __syncthreads();
             {
-                double F = fu0[c];
-                for (int v = 0; v < w; v++) F = mUA[v * COLS + c] * F + mUB[v * COLS + c];
+                double F = S.fu0[c];
+                for (int v = 0; v < w; v++) F = S.mUA[v * COLS + c] * F + S.mUB[v * COLS + c];
                 if (last && live && w == 0) F_up[col] = F;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     const int i = lo + k;
                     if (i < hi) {
                         const size_t o = (size_t)i * COLS + c;
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_in;
                         Fu_reg[k] = F;
                         // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
-                        F = sweep_update(CF(8), CF(9), CF(10), F, Fcd_reg[k], CF(11), CF(13), CF(15));
+                        F = CF(4) * F + ccl[k];
                         Fcu_reg[k] = F;
                         if (last && live) Fc_up[col + (size_t)ncol * i] = F;
-                        F = tiny_to_abs(sweep_update(CF(0), CF(1), CF(2), F, Fd_top, CF(3), CF(5), CF(7)));
+                        F = tiny_to_abs(CF(0) * F + ccu[k]);
                         if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
                     }
                 }
-                edgeU[w * COLS + c] = F;
+                S.edgeU[w * COLS + c] = F;
             }
             __syncthreads();
-            Fu_reg[0] = (w == 0) ? fu0[c] : edgeU[(w - 1) * COLS + c];
+            Fu_reg[0] = (w == 0) ? S.fu0[c] : S.edgeU[(w - 1) * COLS + c];
         }
         __syncthreads();
     }
@@ -421,7 +424,7 @@ k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double
 #undef CF
 
 // ------------------------------------------------------------------------------------------------
-// launch planning: pick (COLS, CH) so that the block fits (<= 1024 threads, <= 227 kB shared memory)
+// launch planning: pick (COLS, CH) so that the block fits (<= 32 chunks, <= 227 kB shared memory)
 // ------------------------------------------------------------------------------------------------
 struct CpPlan {
     int cols, ch, nchunk, threads;
@@ -429,7 +432,7 @@ struct CpPlan {
     int grid;
 };
 
-static bool cp_plan(helios_ctx* ctx, int nlay, int ncol, int planes, int cols, int ch, CpPlan* p) {
+static bool cp_plan(helios_ctx* ctx, int nlay, int ncol, int planes, int cols, int ch, int minb, CpPlan* p) {
     const int nchunk = (nlay + ch - 1) / ch;
     const int threads = nchunk * cols;
     const size_t smem = ((size_t)planes * nlay * cols + (size_t)6 * nchunk * cols + cols) * sizeof(double);
@@ -440,20 +443,21 @@ static bool cp_plan(helios_ctx* ctx, int nlay, int ncol, int planes, int cols, i
     p->threads = threads;
     p->smem = smem;
     const int ntile = (ncol + cols - 1) / cols;
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    int per_sm = (int)((228 * 1024) / (smem + 1024));
     const int by_threads = 2048 / ((threads + 31) / 32 * 32);
     if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > minb) per_sm = minb;  // registers are budgeted for `minb` resident blocks
     if (per_sm < 1) per_sm = 1;
     const int cap = ctx->num_sms * per_sm;
     p->grid = ntile < cap ? ntile : cap;
     return true;
 }
 
-template <int COLS, int CH>
+template <int COLS, int CH, int MINB>
 static int launch_iso(helios_ctx* ctx, const CpPlan& p, double* F_down, double* F_up, const double* F_dir,
                       const double* planck, const double* w_0, const double* M, const double* N, const double* P,
                       const double* Gp, const double* Gm, const double* albedo, const double* g0tot, CpScalars s) {
-    auto kern = k_fband_iso_cp<COLS, CH>;
+    auto kern = k_fband_iso_cp<COLS, CH, MINB>;
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<p.grid, p.threads, p.smem, ctx->stream>>>(F_down, F_up, F_dir, planck, w_0, M, N, P, Gp, Gm, albedo,
                                                       g0tot, s);
@@ -461,17 +465,22 @@ static int launch_iso(helios_ctx* ctx, const CpPlan& p, double* F_down, double* 
     return HELIOS_OK;
 }
 
-template <int COLS, int CH>
+template <int COLS, int CH, int MINB>
 static int launch_noniso(helios_ctx* ctx, const CpPlan& p, double* F_down, double* F_up, double* Fc_down,
                          double* Fc_up, const double* F_dir, const double* Fc_dir, const double* planck_lay,
                          const double* planck_int, CpNonisoCoef c, const double* albedo, const double* g0_lay,
                          const double* g0_int, CpScalars s) {
-    auto kern = k_fband_noniso_cp<COLS, CH>;
+    auto kern = k_fband_noniso_cp<COLS, CH, MINB>;
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     kern<<<p.grid, p.threads, p.smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
                                                       planck_int, c, albedo, g0_lay, g0_int, s);
     HLAUNCHED(ctx);
     return HELIOS_OK;
+}
+
+static int cp_variant() {
+    const char* v = getenv("HELIOS_CP_VARIANT");  // tuning hook (scratch/tune_fband.py); 0 = first that fits
+    return v ? atoi(v) : 0;
 }
 
 // returns HELIOS_OK when launched, -1 when the shape does not fit this scheme (caller falls back to the
@@ -484,15 +493,19 @@ int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double
     const int nlay = nint - 1, ncol = nbin * ny;
     CpPlan p;
     CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0};
-#define TRY_ISO(COLS, CH)                                                                                  \
-    if (cp_plan(ctx, nlay, ncol, 7, COLS, CH, &p)) {                                                       \
+    const int var = cp_variant();
+#define TRY_ISO(ID, COLS, CH, MINB)                                                                        \
+    if ((var == 0 || var == ID) && cp_plan(ctx, nlay, ncol, 4, COLS, CH, MINB, &p)) {                      \
         s.nchunk = p.nchunk;                                                                               \
-        return launch_iso<COLS, CH>(ctx, p, F_down, F_up, F_dir, planck, w_0, M, N, P, Gp, Gm, albedo, g0tot, s); \
+        return launch_iso<COLS, CH, MINB>(ctx, p, F_down, F_up, F_dir, planck, w_0, M, N, P, Gp, Gm, albedo, g0tot, s); \
     }
-    TRY_ISO(16, 4)
-    TRY_ISO(16, 8)
-    TRY_ISO(8, 8)
-    TRY_ISO(8, 16)
+    TRY_ISO(2, 16, 4, 2)
+    TRY_ISO(1, 16, 4, 3)
+    TRY_ISO(3, 16, 5, 3)
+    TRY_ISO(4, 8, 5, 4)
+    TRY_ISO(5, 16, 8, 2)
+    TRY_ISO(6, 8, 8, 2)
+    TRY_ISO(7, 8, 16, 2)
 #undef TRY_ISO
     return -1;
 }
@@ -506,16 +519,20 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
     const int nlay = nint - 1, ncol = nbin * ny;
     CpPlan p;
     CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0};
-#define TRY_NONISO(COLS, CH)                                                                               \
-    if (cp_plan(ctx, nlay, ncol, 16, COLS, CH, &p)) {                                                      \
+    const int var = cp_variant();
+#define TRY_NONISO(ID, COLS, CH, MINB)                                                                     \
+    if ((var == 0 || var == ID) && cp_plan(ctx, nlay, ncol, 8, COLS, CH, MINB, &p)) {                      \
         s.nchunk = p.nchunk;                                                                               \
-        return launch_noniso<COLS, CH>(ctx, p, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,    \
-                                       planck_int, c, albedo, g0_lay, g0_int, s);                          \
+        return launch_noniso<COLS, CH, MINB>(ctx, p, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, \
+                                             planck_int, c, albedo, g0_lay, g0_int, s);                    \
     }
-    TRY_NONISO(8, 4)
-    TRY_NONISO(16, 4)
-    TRY_NONISO(8, 8)
-    TRY_NONISO(4, 8)
+    TRY_NONISO(2, 8, 4, 3)
+    TRY_NONISO(1, 8, 5, 3)
+    TRY_NONISO(3, 16, 4, 1)
+    TRY_NONISO(4, 8, 5, 2)
+    TRY_NONISO(5, 16, 5, 1)
+    TRY_NONISO(6, 8, 8, 2)
+    TRY_NONISO(7, 4, 8, 2)
 #undef TRY_NONISO
     return -1;
 }
