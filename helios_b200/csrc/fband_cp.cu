@@ -1,4 +1,4 @@
-// Layer-parallel two-stream sweeps ("chunk-parallel" fband kernels) -- the default flux solver.
+// Layer-parallel two-stream sweeps -- the default flux solver.
 //
 // Why.  The reference's fband_* (K:1366-1799) walks the ~100 layers of a column serially, twice per
 // pass and 3*scat+1 passes per RT iteration: ~800 dependent steps, each a handful of fp64 divides and
@@ -7,19 +7,17 @@
 //     F[i] = a_i F[i +- 1] - b_i F_opp[i] + s_i,        a = P/M, b = N/M, s = (fac * planck + beam)/M,
 // because the opposite-direction flux F_opp that couples in is the other sweep's finished result.  So:
 //
-//   * a block owns COLS consecutive columns and cuts the layers into chunks of CH; thread (col, chunk)
-//     composes its chunk's affine map locally, the per-chunk maps are exchanged through shared memory,
-//     every thread folds the maps in front of it to get the flux entering its chunk, and then walks its
-//     own CH layers.  A sweep is CH + (#chunks) two-FMA steps instead of nlayer long ones, and ~25x more
-//     threads hide the fp64 latency.
-//   * the four constants of every (half-)layer -- a, b, s_down, s_up -- are computed ONCE per flux solve
-//     while the coefficient arrays stream in (coalesced: lanes run along the flat column index y + ny*x),
-//     with the rounding-exact building blocks of sweep_math.cuh, and are parked in shared memory for all
-//     passes.  HBM sees every input once and every output once per solve: the 80 B (iso) / 176 B
-//     (non-iso) per cell of DESIGN.md instead of that figure times 2 sweeps times npass.
-//   * the fluxes a thread needs from the other direction / the previous pass are the ones it produced
-//     itself (or its chunk neighbour's edge value, handed over through shared memory), so they stay in
-//     registers; only the last pass writes the flux arrays.
+//   phase A (block-wide, lanes along the flat column index y + ny*x => coalesced): the coefficient arrays
+//     stream in ONCE per flux solve; the four constants a, b, s_down, s_up of every (half-)layer are
+//     formed with the rounding-exact building blocks of sweep_math.cuh and parked, transposed, in shared
+//     memory.  HBM sees every input once and every output once per solve: the 80 B (iso) / 176 B (non-iso)
+//     per cell of DESIGN.md instead of that figure times 2 sweeps times npass.
+//   phase B (16 lanes per column, i.e. two columns per warp; lane = chunk of CH consecutive layers): every
+//     lane composes the affine map of its chunk, a Kogge-Stone scan over the lanes (4 shuffle steps) gives each lane the flux
+//     entering its chunk, and the lane then walks its own CH layers.  A sweep is 2*CH + 5 short steps
+//     instead of nlayer long ones; all passes run back to back inside the warp with no block barrier, the
+//     fluxes needed from the other direction / the previous pass stay in registers (chunk-edge values are
+//     handed over by shuffle), and only the last pass writes the flux arrays.
 //
 // Arithmetic: a F - b F_opp + s is the reference's 1/M (P F - N F_opp + ...) with the division by M
 // distributed, and the chunk-entry flux comes from composed maps: both reorder a few multiply-adds.
@@ -32,7 +30,7 @@
 
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
-    int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk;
+    int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
 };
 
 struct CpNonisoCoef {
@@ -40,7 +38,6 @@ struct CpNonisoCoef {
         *Gp_l, *Gm_u, *Gm_l;
 };
 
-// constants of one (half-)layer step
 struct Step {
     double a, b, sd, su;
 };
@@ -56,458 +53,393 @@ __device__ __forceinline__ Step make_step(double M, double N, double P, double f
     return s;
 }
 
-// shared memory carve-up (doubles): planes[NPL][nlay][COLS] | mDA mDB mUA mUB edgeD edgeU [nch][COLS] | fu0[COLS]
-template <int NPL, int COLS>
-struct CpSmem {
-    double *cf, *mDA, *mDB, *mUA, *mUB, *edgeD, *edgeU, *fu0;
-    size_t plane;
-    __device__ CpSmem(double* sm, int nlay, int nch) {
-        plane = (size_t)nlay * COLS;
-        cf = sm;
-        mDA = sm + NPL * plane;
-        mDB = mDA + (size_t)nch * COLS;
-        mUA = mDB + (size_t)nch * COLS;
-        mUB = mUA + (size_t)nch * COLS;
-        edgeD = mUB + (size_t)nch * COLS;
-        edgeU = edgeD + (size_t)nch * COLS;
-        fu0 = edgeU + (size_t)nch * COLS;
-    }
+// affine maps x -> A x + B; compose(f, g) = f after g
+struct Aff {
+    double A, B;
 };
+__device__ __forceinline__ Aff aff_after(const Aff& f, const Aff& g) { return Aff{f.A * g.A, f.A * g.B + f.B}; }
+
+// Kogge-Stone scans inside segments of LPC lanes (one segment = one column).
+// from_top:    lane j receives the composition of the maps of lanes j, j+1, ..., n-1 (highest applied first)
+// from_bottom: lane j receives the composition of the maps of lanes j, j-1, ..., 0   (lane 0 applied first)
+template <int LPC>
+__device__ __forceinline__ Aff scan_from_top(Aff m, int sl, int n) {
+#pragma unroll
+    for (int d = 1; d < LPC; d <<= 1) {
+        Aff o;
+        o.A = __shfl_down_sync(0xffffffffu, m.A, d, LPC);
+        o.B = __shfl_down_sync(0xffffffffu, m.B, d, LPC);
+        if (sl + d < n) m = aff_after(m, o);
+    }
+    return m;
+}
+template <int LPC>
+__device__ __forceinline__ Aff scan_from_bottom(Aff m, int sl) {
+#pragma unroll
+    for (int d = 1; d < LPC; d <<= 1) {
+        Aff o;
+        o.A = __shfl_up_sync(0xffffffffu, m.A, d, LPC);
+        o.B = __shfl_up_sync(0xffffffffu, m.B, d, LPC);
+        if (sl >= d) m = aff_after(m, o);
+    }
+    return m;
+}
+
+// direct-beam sources of one (half-)layer; skipped when no beam reaches the layer (all-zero F_dir), which
+// also saves the four fp64 divisions: min(0, +-0) contributes nothing to the sums it enters
+__device__ __forceinline__ void beam_pair(double Fa, double Fb, double neg_mu, double M, double N, double P,
+                                          double G_pl, double G_min, double m1d, double m2d, double& Dd,
+                                          double& Du) {
+    Dd = 0.0;
+    Du = 0.0;
+    if (Fa != 0.0 || Fb != 0.0) {
+        Dd = beam_source(Fa, Fb, neg_mu, M, G_min, N, G_pl, m1d, m2d);
+        Du = beam_source(Fb, Fa, neg_mu, N, G_min, M, G_pl, P, G_pl);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
-// isothermal layers: one step per layer, planes a, b, sd, su
+// The kernel.  NONISO = false: one step per layer, shared planes a, b, sd, su, F_up(prev)            (5)
+//              NONISO = true : two steps per layer (upper half, lower half): [a, b, sd, su] x 2,
+//                              F_up(prev), Fc_up(prev)                                               (10)
+// Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
-template <int COLS, int CH, int MINB>
-__global__ void __launch_bounds__(32 * COLS, MINB)
-k_fband_iso_cp(double* __restrict__ F_down, double* __restrict__ F_up, const double* __restrict__ F_dir,
-               const double* __restrict__ planck, const double* __restrict__ w_0, const double* __restrict__ Mt,
-               const double* __restrict__ Nt, const double* __restrict__ Pt, const double* __restrict__ Gp,
-               const double* __restrict__ Gm, const double* __restrict__ albedo,
-               const double* __restrict__ g0tot, CpScalars s) {
+template <bool NONISO, int CH, int LPC, int NCOLS>
+__global__ void __launch_bounds__(NCOLS * LPC, 2)
+k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
+           double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
+           const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
+           // iso: w0_u = w_0, M_u = M_term, ... ; the *_l members are unused
+           CpNonisoCoef cfg, const double* __restrict__ albedo, const double* __restrict__ g0_lay,
+           const double* __restrict__ g0_int, CpScalars s) {
     extern __shared__ double sm[];
-    const int nint = s.nint, nlay = nint - 1, nch = s.nchunk;
+    constexpr int NPL = NONISO ? 10 : 5;
+    constexpr int STRIDE = CH + ((CH % 2 == 0) ? 1 : 0);
+    const int nint = s.nint, nlay = nint - 1, nch = s.nchunk, pitch = s.colpitch;
     const int ncol = s.nbin * s.ny;
-    const int c = threadIdx.x % COLS;
-    const int w = threadIdx.x / COLS;
-    const int lo = w * CH;
-    const int hi = min(lo + CH, nlay);  // layers lo .. hi-1, interfaces lo .. hi
-    CpSmem<4, COLS> S(sm, nlay, nch);
-    const size_t plane = S.plane;
-    double* cf = S.cf;
+    const size_t plane = (size_t)NCOLS * pitch;
+    double* c_toa = sm + NPL * plane;  // per-column scalars, [NCOLS] each
+    double* c_alb = c_toa + NCOLS;
+    double* c_fdir0 = c_alb + NCOLS;
+    double* c_emis = c_fdir0 + NCOLS;
     const double neg_mu = -s.mu_star;
-    const int ntile = (ncol + COLS - 1) / COLS;
+    const int ntile = (ncol + NCOLS - 1) / NCOLS;
 
     for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-        const int col = tile * COLS + c;
-        const bool live = col < ncol;
-        const int colc = live ? col : ncol - 1;  // dead lanes shadow the last column and never store
-        const int x = colc / s.ny;
-        const double* __restrict__ B = planck + (size_t)x * (nlay + 2);
-        const double A_s = albedo[x];
-        const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * B[nlay];
-
-        // ---- stream the coefficients in once; park a, b, s_down, s_up of every layer in shared memory
-        double Fu_reg[CH], Fd_reg[CH];
-        double w0_0 = 0.0, E_0 = 1.0, Fdir0 = 0.0;  // the BOA emission uses layer 0's w0 and E (K:1472)
+        // ================= phase A: coalesced streaming, lanes along columns =================
+        // Every thread owns at most CH layer rows (nlay <= LPC*CH).
+        {
+            const int c = threadIdx.x % NCOLS;
+            const int r = threadIdx.x / NCOLS;  // 0 .. LPC-1
+            const int col = min(tile * NCOLS + c, ncol - 1);
+            const int x = col / s.ny;
+            const double* __restrict__ BL = planck_lay + (size_t)x * (nlay + 2);
+            const double* __restrict__ BI = NONISO ? planck_int + (size_t)x * nint : nullptr;
+            constexpr int NRAW = NONISO ? 24 : 11;
+            double raw[1][NRAW];
+            auto load_cell = [&](int m, double* q) {
+                const int i = r + LPC * m;
+                if (i < nlay) {
+                    const size_t e = col + (size_t)ncol * i;
+                    const size_t bb = (size_t)x + (size_t)s.nbin * i;
+                    q[0] = F_dir[e];
+                    q[1] = F_dir[e + ncol];
+                    q[2] = cfg.w0_u[e]; q[3] = cfg.M_u[e]; q[4] = cfg.N_u[e]; q[5] = cfg.P_u[e];
+                    q[6] = cfg.Gp_u[e]; q[7] = cfg.Gm_u[e];
+                    q[8] = BL[i];
+                    q[9] = F_up[e];
+                    q[10] = s.clouds ? g0_lay[bb] : s.g_0;
+                    if (NONISO) {
+                        q[11] = cfg.w0_l[e]; q[12] = cfg.M_l[e]; q[13] = cfg.N_l[e]; q[14] = cfg.P_l[e];
+                        q[15] = cfg.Gp_l[e]; q[16] = cfg.Gm_l[e];
+                        q[17] = cfg.dtau_u[e] + cfg.dtc_u[bb];
+                        q[18] = cfg.dtau_l[e] + cfg.dtc_l[bb];
+                        q[19] = Fc_dir[e];
+                        q[20] = BI[i];
+                        q[21] = BI[i + 1];
+                        q[22] = Fc_up[e];
+                        q[23] = s.clouds ? g0_int[bb] : s.g_0;
+                        if (s.clouds) q[10] = (q[10] + g0_int[bb + s.nbin]) / 2.0;  // g0 of the upper half
+                    }
+                }
+            };
 #pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const int i = lo + k;
-            Fu_reg[k] = 0.0;
-            Fd_reg[k] = 0.0;
-            if (i < hi) {
-                const size_t e = colc + (size_t)ncol * i;
-                const double w0 = w_0[e], M = Mt[e], N = Nt[e], P = Pt[e], G_pl = Gp[e], G_min = Gm[e];
-                const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol];
-                const double g0 = s.clouds ? g0tot[x + (size_t)s.nbin * i] : s.g_0;
-                const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
-                const double pt = planck_iso(B[i], M, N, P);
-                const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt, pt,
-                                          beam_source(Fdir_i, Fdir_ip1, neg_mu, M, G_min, N, G_pl, P, G_min),
-                                          beam_source(Fdir_ip1, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl));
-                const size_t o = (size_t)i * COLS + c;
-                cf[o] = st.a;
-                cf[plane + o] = st.b;
-                cf[2 * plane + o] = st.sd;
-                cf[3 * plane + o] = st.su;
-                Fu_reg[k] = F_up[e];  // upward flux of the previous flux solve at interface i
-                w0_0 = i == 0 ? w0 : w0_0;
-                E_0 = i == 0 ? E : E_0;
-                Fdir0 = i == 0 ? Fdir_i : Fdir0;
+            for (int m = 0; m < CH; m++) {
+                load_cell(m, raw[0]);  // all loads of the cell are issued back to back, then consumed
+                {
+                    const int i = r + LPC * m;
+                    if (i < nlay) {
+                        const double* q = raw[0];
+                        const int o = c * pitch + (i / CH) * STRIDE + (i % CH);
+                        const double Fdir_i = q[0], Fdir_ip1 = q[1];
+                        if (!NONISO) {
+                            const double w0 = q[2], M = q[3], N = q[4], P = q[5];
+                            const double E = s.scat_corr ? E_parameter(w0, q[10], s.i2s_transition) : 1.0;
+                            double Dd, Du;
+                            beam_pair(Fdir_i, Fdir_ip1, neg_mu, M, N, P, q[6], q[7], P, q[7], Dd, Du);
+                            const double pt = planck_iso(q[8], M, N, P);
+                            const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt, pt, Dd, Du);
+                            sm[o] = st.a;
+                            sm[plane + o] = st.b;
+                            sm[2 * plane + o] = st.sd;
+                            sm[3 * plane + o] = st.su;
+                            sm[4 * plane + o] = q[9];  // upward flux of the previous flux solve at interface i
+                            if (i == 0) {  // the BOA emission uses layer 0's w0 and E (K:1472)
+                                const double A_s = albedo[x];
+                                c_alb[c] = A_s;
+                                c_fdir0[c] = Fdir_i;
+                                c_emis[c] = boa_emission(A_s, w0, E, BL[nlay + 1]);
+                                c_toa[c] = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
+                            }
+                        } else {
+                            const double Blay = q[8], Bint_lo = q[20], Bint_hi = q[21], Fcdir = q[19];
+                            double g0_up = s.g_0, g0_low = s.g_0;
+                            if (s.clouds) {
+                                g0_up = q[10];
+                                // the layer value is recovered exactly: q[10] held (gl + gi_hi)/2 only for the upper
+                                // half, so the lower half re-reads gl (cheap, L1-resident)
+                                const double gl = g0_lay[(size_t)x + (size_t)s.nbin * i];
+                                g0_low = (q[23] + gl) / 2.0;
+                            }
+                            {   // ---- upper half: layer centre <-> interface i+1 (K:1640-1664, 1771-1795)
+                                const double w0 = q[2], M = q[3], N = q[4], P = q[5], dt = q[17];
+                                const double E = s.scat_corr ? E_parameter(w0, g0_up, s.i2s_transition) : 1.0;
+                                double pt_d, pt_u;
+                                if (dt < s.delta_tau_limit) {
+                                    pt_d = planck_thin(Bint_hi, Blay, M, N, P);
+                                    pt_u = pt_d;
+                                } else {
+                                    const double pre = gradient_factor(s.epsi, w0, g0_up, E);
+                                    const double pgrad = __ddiv_rn(__dsub_rn(Blay, Bint_hi), dt);
+                                    pt_d = planck_grad_down(Blay, Bint_hi, M, N, P, pre, pgrad);
+                                    pt_u = planck_grad_up(Bint_hi, Blay, M, N, P, pre, pgrad);
+                                }
+                                double Dd, Du;
+                                beam_pair(Fcdir, Fdir_ip1, neg_mu, M, N, P, q[6], q[7], q[7], P, Dd, Du);
+                                const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u, Dd, Du);
+                                sm[o] = st.a;
+                                sm[plane + o] = st.b;
+                                sm[2 * plane + o] = st.sd;
+                                sm[3 * plane + o] = st.su;
+                            }
+                            {   // ---- lower half: interface i <-> layer centre (K:1667-1691, 1744-1768)
+                                const double w0 = q[11], M = q[12], N = q[13], P = q[14], dt = q[18];
+                                const double E = s.scat_corr ? E_parameter(w0, g0_low, s.i2s_transition) : 1.0;
+                                double pt_d, pt_u;
+                                if (dt < s.delta_tau_limit) {
+                                    pt_d = planck_thin(Bint_lo, Blay, M, N, P);
+                                    pt_u = pt_d;
+                                } else {
+                                    const double pre = gradient_factor(s.epsi, w0, g0_low, E);
+                                    const double pgrad = __ddiv_rn(__dsub_rn(Bint_lo, Blay), dt);
+                                    pt_d = planck_grad_down(Bint_lo, Blay, M, N, P, pre, pgrad);
+                                    pt_u = planck_grad_up(Blay, Bint_lo, M, N, P, pre, pgrad);
+                                }
+                                double Dd, Du;
+                                beam_pair(Fdir_i, Fcdir, neg_mu, M, N, P, q[15], q[16], P, q[16], Dd, Du);
+                                const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u, Dd, Du);
+                                sm[4 * plane + o] = st.a;
+                                sm[5 * plane + o] = st.b;
+                                sm[6 * plane + o] = st.sd;
+                                sm[7 * plane + o] = st.su;
+                                if (i == 0) {  // lower half of layer 0 feeds the BOA emission (K:1704)
+                                    const double A_s = albedo[x];
+                                    c_alb[c] = A_s;
+                                    c_fdir0[c] = Fdir_i;
+                                    c_emis[c] = boa_emission(A_s, w0, E, BL[nlay + 1]);
+                                    c_toa[c] = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
+                                }
+                            }
+                            sm[8 * plane + o] = q[9];
+                            sm[9 * plane + o] = q[22];
+                        }
+                    }
+                }
             }
         }
-        const double B_surf = B[nlay + 1];
-
-        for (int pass = 0; pass < s.npass; pass++) {
-            const bool last = pass == s.npass - 1;
-            double cc[CH];
-            // ================= downward sweep =================
-            {
-                double A = 1.0, Bm = 0.0;
+        __syncthreads();
+        // ================= phase B: LPC lanes per column, lane = chunk of CH layers =================
+        {
+            const int cw = threadIdx.x / LPC;  // column of this lane segment
+            const int sl = threadIdx.x % LPC;  // chunk index
+            const int col = tile * NCOLS + cw;
+            const bool live = col < ncol;      // uniform per segment; dead segments still shuffle
+            const int colc = live ? col : ncol - 1;
+            const int lo = sl * CH;
+            const bool act = sl < nch;
+            const int hi = min(lo + CH, nlay);
+            const int base = cw * pitch + sl * STRIDE;
+            const double toa = c_toa[cw], A_s = c_alb[cw], Fdir0 = c_fdir0[cw], emis = c_emis[cw];
+            // step constants kept in registers: a, b of every step; sd / su are re-read from shared memory
+            constexpr int NS = NONISO ? 2 : 1;  // steps per layer
+            double a[NS][CH], b[NS][CH], Fu_reg[CH], Fd_reg[CH], Fcu_reg[CH], Fcd_reg[CH], cc[NS][CH];
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const bool in = act && lo + k < hi;
+                a[0][k] = in ? sm[base + k] : 1.0;  // identity step outside the column
+                b[0][k] = in ? sm[plane + base + k] : 0.0;
+                if (NONISO) {
+                    a[1][k] = in ? sm[4 * plane + base + k] : 1.0;
+                    b[1][k] = in ? sm[5 * plane + base + k] : 0.0;
+                }
+                Fu_reg[k] = in ? sm[(NONISO ? 8 : 4) * plane + base + k] : 0.0;
+                Fcu_reg[k] = (NONISO && in) ? sm[9 * plane + base + k] : 0.0;
+                Fd_reg[k] = Fcd_reg[k] = 0.0;
+            }
+            for (int pass = 0; pass < s.npass; pass++) {
+                const bool wr = live && pass == s.npass - 1;  // only the last pass writes the flux arrays
+                // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
+                Aff m{1.0, 0.0};
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
-                    const int i = lo + k;
-                    cc[k] = 0.0;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        const double a = cf[o];
-                        cc[k] = cf[2 * plane + o] - cf[plane + o] * Fu_reg[k];
-                        A = a * A;
-                        Bm = a * Bm + cc[k];
+                    const bool in = act && lo + k < hi;
+                    if (NONISO) {
+                        cc[0][k] = (in ? sm[2 * plane + base + k] : 0.0) - b[0][k] * Fcu_reg[k];
+                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                        cc[1][k] = (in ? sm[6 * plane + base + k] : 0.0) - b[1][k] * Fu_reg[k];
+                        m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+                    } else {
+                        cc[0][k] = (in ? sm[2 * plane + base + k] : 0.0) - b[0][k] * Fu_reg[k];
+                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
                     }
                 }
-                S.mDA[w * COLS + c] = A;
-                S.mDB[w * COLS + c] = Bm;
-            }
-            __syncthreads();
-            {
-                double F = toa;
-                for (int v = nch - 1; v > w; v--) F = S.mDA[v * COLS + c] * F + S.mDB[v * COLS + c];
-                if (last && live && w == nch - 1) F_down[col + (size_t)ncol * nlay] = toa;
+                Aff sc = scan_from_top<LPC>(m, sl, nch);
+                const double Fbot = sc.A * toa + sc.B;                       // flux leaving my chunk (interface lo)
+                double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);      // = flux entering it (interface hi)
+                if (sl >= nch - 1) F = toa;
+                if (wr && sl == nch - 1) F_down[colc + (size_t)ncol * nlay] = toa;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
-                    const int i = lo + k;
-                    if (i < hi) {
-                        F = tiny_to_abs(cf[(size_t)i * COLS + c] * F + cc[k]);
+                    if (act && lo + k < hi) {
+                        if (NONISO) {
+                            F = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                            Fcd_reg[k] = F;
+                            if (wr) Fc_down[colc + (size_t)ncol * (lo + k)] = F;
+                            F = tiny_to_abs(a[1][k] * F + cc[1][k]);
+                        } else {
+                            F = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                        }
                         Fd_reg[k] = F;
-                        if (last && live) F_down[col + (size_t)ncol * i] = F;
+                        if (wr) F_down[colc + (size_t)ncol * (lo + k)] = F;
                     }
                 }
-                S.edgeD[w * COLS + c] = Fd_reg[0];
-            }
-            // ================= upward sweep =================
-            if (w == 0) S.fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
-            __syncthreads();
-            // the flux at the chunk's top interface is the value the chunk above WALKED (and stored), not the
-            // composed one: every flux consumed later is bit-identical to what the output arrays hold
-            const double Fd_hi = (w == nch - 1) ? toa : S.edgeD[(w + 1) * COLS + c];
-            {
-                double A = 1.0, Bm = 0.0;
+                // the flux at my top interface as WALKED (and stored) by the lane above: every flux consumed
+                // later is bit-identical to what the output arrays hold
+                double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+                if (sl >= nch - 1) Fd_hi = toa;
+                // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
+                double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+                fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+                m = Aff{1.0, 0.0};
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
-                    const int i = lo + k;
-                    cc[k] = 0.0;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                        const double a = cf[o];
-                        cc[k] = cf[3 * plane + o] - cf[plane + o] * Fd_top;
-                        A = a * A;
-                        Bm = a * Bm + cc[k];
+                    const bool in = act && lo + k < hi;
+                    const double Fd_top = (k + 1 < CH && lo + k + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                    if (NONISO) {
+                        cc[1][k] = (in ? sm[7 * plane + base + k] : 0.0) - b[1][k] * Fcd_reg[k];
+                        m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+                        cc[0][k] = (in ? sm[3 * plane + base + k] : 0.0) - b[0][k] * Fd_top;
+                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                    } else {
+                        cc[0][k] = (in ? sm[3 * plane + base + k] : 0.0) - b[0][k] * Fd_top;
+                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
                     }
                 }
-                S.mUA[w * COLS + c] = A;
-                S.mUB[w * COLS + c] = Bm;
-            }
-            __syncthreads();
-            {
-                double F = S.fu0[c];
-                for (int v = 0; v < w; v++) F = S.mUA[v * COLS + c] * F + S.mUB[v * COLS + c];
-                if (last && live && w == 0) F_up[col] = F;
+                sc = scan_from_bottom<LPC>(m, sl);
+                const double Ftop = sc.A * fu0 + sc.B;                       // flux leaving my chunk (interface hi)
+                F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);               // = flux entering it (interface lo)
+                if (sl == 0) F = fu0;
+                if (wr && sl == 0) F_up[colc] = fu0;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
-                    const int i = lo + k;
-                    if (i < hi) {
-                        Fu_reg[k] = F;  // interface i: what the next pass's downward sweep reads
-                        F = tiny_to_abs(cf[(size_t)i * COLS + c] * F + cc[k]);
-                        if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
+                    if (act && lo + k < hi) {
+                        Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
+                        if (NONISO) {
+                            // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
+                            F = a[1][k] * F + cc[1][k];
+                            Fcu_reg[k] = F;
+                            if (wr) Fc_up[colc + (size_t)ncol * (lo + k)] = F;
+                        }
+                        F = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                        if (wr) F_up[colc + (size_t)ncol * (lo + k + 1)] = F;
                     }
                 }
-                S.edgeU[w * COLS + c] = F;
+                // next pass: the flux at my bottom interface as walked by the lane below
+                const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+                Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
             }
-            __syncthreads();
-            Fu_reg[0] = (w == 0) ? S.fu0[c] : S.edgeU[(w - 1) * COLS + c];
         }
         __syncthreads();  // the next tile overwrites the shared planes
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// non-isothermal layers: two steps per layer (upper / lower half), planes [half][a, b, sd, su]
+// launch planning: LPC = 16 lanes per column (two columns per warp) while nlay <= 128, else 32
 // ------------------------------------------------------------------------------------------------
-#define CF(q) cf[(size_t)(q) * plane + o]
-
-template <int COLS, int CH, int MINB>
-__global__ void __launch_bounds__(32 * COLS, MINB)
-k_fband_noniso_cp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
-                  double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
-                  const double* __restrict__ planck_lay, const double* __restrict__ planck_int, CpNonisoCoef cfg,
-                  const double* __restrict__ albedo, const double* __restrict__ g0_lay,
-                  const double* __restrict__ g0_int, CpScalars s) {
-    extern __shared__ double sm[];
-    const int nint = s.nint, nlay = nint - 1, nch = s.nchunk;
-    const int ncol = s.nbin * s.ny;
-    const int c = threadIdx.x % COLS;
-    const int w = threadIdx.x / COLS;
-    const int lo = w * CH;
-    const int hi = min(lo + CH, nlay);
-    CpSmem<8, COLS> S(sm, nlay, nch);
-    const size_t plane = S.plane;
-    double* cf = S.cf;
-    const double neg_mu = -s.mu_star;
-    const int ntile = (ncol + COLS - 1) / COLS;
-
-    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-        const int col = tile * COLS + c;
-        const bool live = col < ncol;
-        const int colc = live ? col : ncol - 1;
-        const int x = colc / s.ny;
-        const double* __restrict__ BL = planck_lay + (size_t)x * (nlay + 2);
-        const double* __restrict__ BI = planck_int + (size_t)x * nint;
-        const double A_s = albedo[x];
-        const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
-
-        double Fu_reg[CH], Fcu_reg[CH], Fd_reg[CH], Fcd_reg[CH];
-        double w0_0 = 0.0, E_0 = 1.0, Fdir0 = 0.0;  // lower half of layer 0 feeds the BOA emission (K:1704)
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const int i = lo + k;
-            Fu_reg[k] = Fcu_reg[k] = Fd_reg[k] = Fcd_reg[k] = 0.0;
-            if (i < hi) {
-                const size_t e = colc + (size_t)ncol * i;
-                const size_t b = (size_t)x + (size_t)s.nbin * i;
-                const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
-                const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol], Fcdir = Fc_dir[e];
-                double g0_up = s.g_0, g0_low = s.g_0;
-                if (s.clouds) {
-                    const double gl = g0_lay[b];
-                    g0_up = (gl + g0_int[b + s.nbin]) / 2.0;
-                    g0_low = (g0_int[b] + gl) / 2.0;
-                }
-                const size_t o = (size_t)i * COLS + c;
-                {   // ---- upper half: layer centre <-> interface i+1 (K:1640-1664, 1771-1795)
-                    const double w0 = cfg.w0_u[e], M = cfg.M_u[e], N = cfg.N_u[e], P = cfg.P_u[e];
-                    const double G_pl = cfg.Gp_u[e], G_min = cfg.Gm_u[e];
-                    const double dt = cfg.dtau_u[e] + cfg.dtc_u[b];
-                    const double E = s.scat_corr ? E_parameter(w0, g0_up, s.i2s_transition) : 1.0;
-                    double pt_d, pt_u;
-                    if (dt < s.delta_tau_limit) {
-                        pt_d = planck_thin(Bint_hi, Blay, M, N, P);
-                        pt_u = pt_d;
-                    } else {
-                        const double pre = gradient_factor(s.epsi, w0, g0_up, E);
-                        const double pgrad = __ddiv_rn(__dsub_rn(Blay, Bint_hi), dt);
-                        pt_d = planck_grad_down(Blay, Bint_hi, M, N, P, pre, pgrad);
-                        pt_u = planck_grad_up(Bint_hi, Blay, M, N, P, pre, pgrad);
-                    }
-                    const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u,
-                                              beam_source(Fcdir, Fdir_ip1, neg_mu, M, G_min, N, G_pl, G_min, P),
-                                              beam_source(Fdir_ip1, Fcdir, neg_mu, N, G_min, M, G_pl, P, G_pl));
-                    CF(0) = st.a; CF(1) = st.b; CF(2) = st.sd; CF(3) = st.su;
-                }
-                {   // ---- lower half: interface i <-> layer centre (K:1667-1691, 1744-1768)
-                    const double w0 = cfg.w0_l[e], M = cfg.M_l[e], N = cfg.N_l[e], P = cfg.P_l[e];
-                    const double G_pl = cfg.Gp_l[e], G_min = cfg.Gm_l[e];
-                    const double dt = cfg.dtau_l[e] + cfg.dtc_l[b];
-                    const double E = s.scat_corr ? E_parameter(w0, g0_low, s.i2s_transition) : 1.0;
-                    double pt_d, pt_u;
-                    if (dt < s.delta_tau_limit) {
-                        pt_d = planck_thin(Bint_lo, Blay, M, N, P);
-                        pt_u = pt_d;
-                    } else {
-                        const double pre = gradient_factor(s.epsi, w0, g0_low, E);
-                        const double pgrad = __ddiv_rn(__dsub_rn(Bint_lo, Blay), dt);
-                        pt_d = planck_grad_down(Bint_lo, Blay, M, N, P, pre, pgrad);
-                        pt_u = planck_grad_up(Blay, Bint_lo, M, N, P, pre, pgrad);
-                    }
-                    const Step st = make_step(M, N, P, source_factor(s.epsi, w0, E), pt_d, pt_u,
-                                              beam_source(Fdir_i, Fcdir, neg_mu, M, G_min, N, G_pl, P, G_min),
-                                              beam_source(Fcdir, Fdir_i, neg_mu, N, G_min, M, G_pl, P, G_pl));
-                    CF(4) = st.a; CF(5) = st.b; CF(6) = st.sd; CF(7) = st.su;
-                    w0_0 = i == 0 ? w0 : w0_0;
-                    E_0 = i == 0 ? E : E_0;
-                    Fdir0 = i == 0 ? Fdir_i : Fdir0;
-                }
-                Fu_reg[k] = F_up[e];
-                Fcu_reg[k] = Fc_up[e];
-            }
-        }
-        const double B_surf = BL[nlay + 1];
-
-        for (int pass = 0; pass < s.npass; pass++) {
-            const bool last = pass == s.npass - 1;
-            double ccu[CH], ccl[CH];
-            // ================= downward sweep: upper half, then lower half of every layer =================
-            {
-                double A = 1.0, Bm = 0.0;
-#pragma unroll
-                for (int k = CH - 1; k >= 0; k--) {
-                    const int i = lo + k;
-                    ccu[k] = ccl[k] = 0.0;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        double a = CF(0);
-                        ccu[k] = CF(2) - CF(1) * Fcu_reg[k];
-                        A = a * A;
-                        Bm = a * Bm + ccu[k];
-                        a = CF(4);
-                        ccl[k] = CF(6) - CF(5) * Fu_reg[k];
-                        A = a * A;
-                        Bm = a * Bm + ccl[k];
-                    }
-                }
-                S.mDA[w * COLS + c] = A;
-                S.mDB[w * COLS + c] = Bm;
-            }
-            __syncthreads();
-            {
-                double F = toa;
-                for (int v = nch - 1; v > w; v--) F = S.mDA[v * COLS + c] * F + S.mDB[v * COLS + c];
-                if (last && live && w == nch - 1) F_down[col + (size_t)ncol * nlay] = toa;
-#pragma unroll
-                for (int k = CH - 1; k >= 0; k--) {
-                    const int i = lo + k;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        F = tiny_to_abs(CF(0) * F + ccu[k]);
-                        Fcd_reg[k] = F;
-                        if (last && live) Fc_down[col + (size_t)ncol * i] = F;
-                        F = tiny_to_abs(CF(4) * F + ccl[k]);
-                        Fd_reg[k] = F;
-                        if (last && live) F_down[col + (size_t)ncol * i] = F;
-                    }
-                }
-                S.edgeD[w * COLS + c] = Fd_reg[0];
-            }
-            // ================= upward sweep: lower half, then upper half =================
-            if (w == 0) S.fu0[c] = boa_flux(A_s, Fdir0, Fd_reg[0], w0_0, E_0, B_surf);
-            __syncthreads();
-            const double Fd_hi = (w == nch - 1) ? toa : S.edgeD[(w + 1) * COLS + c];  // walked value (see iso)
-            {
-                double A = 1.0, Bm = 0.0;
-#pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    const int i = lo + k;
-                    ccu[k] = ccl[k] = 0.0;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        const double Fd_top = (k + 1 < CH && i + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                        double a = CF(4);
-                        ccl[k] = CF(7) - CF(5) * Fcd_reg[k];
-                        A = a * A;
-                        Bm = a * Bm + ccl[k];
-                        a = CF(0);
-                        ccu[k] = CF(3) - CF(1) * Fd_top;
-                        A = a * A;
-                        Bm = a * Bm + ccu[k];
-                    }
-                }
-                S.mUA[w * COLS + c] = A;
-                S.mUB[w * COLS + c] = Bm;
-            }
-            __syncthreads();
-            {
-                double F = S.fu0[c];
-                for (int v = 0; v < w; v++) F = S.mUA[v * COLS + c] * F + S.mUB[v * COLS + c];
-                if (last && live && w == 0) F_up[col] = F;
-#pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    const int i = lo + k;
-                    if (i < hi) {
-                        const size_t o = (size_t)i * COLS + c;
-                        Fu_reg[k] = F;
-                        // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
-                        F = CF(4) * F + ccl[k];
-                        Fcu_reg[k] = F;
-                        if (last && live) Fc_up[col + (size_t)ncol * i] = F;
-                        F = tiny_to_abs(CF(0) * F + ccu[k]);
-                        if (last && live) F_up[col + (size_t)ncol * (i + 1)] = F;
-                    }
-                }
-                S.edgeU[w * COLS + c] = F;
-            }
-            __syncthreads();
-            Fu_reg[0] = (w == 0) ? S.fu0[c] : S.edgeU[(w - 1) * COLS + c];
-        }
-        __syncthreads();
-    }
-}
-#undef CF
-
-// ------------------------------------------------------------------------------------------------
-// launch planning: pick (COLS, CH) so that the block fits (<= 32 chunks, <= 227 kB shared memory)
-// ------------------------------------------------------------------------------------------------
-struct CpPlan {
-    int cols, ch, nchunk, threads;
-    size_t smem;
-    int grid;
-};
-
-static bool cp_plan(helios_ctx* ctx, int nlay, int ncol, int planes, int cols, int ch, int minb, CpPlan* p) {
-    const int nchunk = (nlay + ch - 1) / ch;
-    const int threads = nchunk * cols;
-    const size_t smem = ((size_t)planes * nlay * cols + (size_t)6 * nchunk * cols + cols) * sizeof(double);
-    if (nchunk > 32 || threads > 1024 || smem > 227 * 1024) return false;
-    p->cols = cols;
-    p->ch = ch;
-    p->nchunk = nchunk;
-    p->threads = threads;
-    p->smem = smem;
-    const int ntile = (ncol + cols - 1) / cols;
+template <bool NONISO, int CH, int LPC, int NCOLS>
+static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                     const double* F_dir, const double* Fc_dir, const double* planck_lay, const double* planck_int,
+                     CpNonisoCoef c, const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s,
+                     int ncol) {
+    const int nlay = s.nint - 1;
+    const int nchunk = (nlay + CH - 1) / CH;
+    int pitch = nchunk * (CH + ((CH % 2 == 0) ? 1 : 0));
+    if (pitch % 2 == 0) pitch += 1;  // odd column pitch: the phase-A stores of 16 lanes hit distinct banks
+    s.nchunk = nchunk;
+    s.colpitch = pitch;
+    const size_t smem = ((size_t)(NONISO ? 10 : 5) * NCOLS * pitch + 4 * NCOLS) * sizeof(double);
+    if (nchunk > LPC || smem > 227 * 1024) return -1;
+    const int ntile = (ncol + NCOLS - 1) / NCOLS;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
-    const int by_threads = 2048 / ((threads + 31) / 32 * 32);
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm > minb) per_sm = minb;  // registers are budgeted for `minb` resident blocks
+    if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
     if (per_sm < 1) per_sm = 1;
-    const int cap = ctx->num_sms * per_sm;
-    p->grid = ntile < cap ? ntile : cap;
-    return true;
-}
-
-template <int COLS, int CH, int MINB>
-static int launch_iso(helios_ctx* ctx, const CpPlan& p, double* F_down, double* F_up, const double* F_dir,
-                      const double* planck, const double* w_0, const double* M, const double* N, const double* P,
-                      const double* Gp, const double* Gm, const double* albedo, const double* g0tot, CpScalars s) {
-    auto kern = k_fband_iso_cp<COLS, CH, MINB>;
-    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<p.grid, p.threads, p.smem, ctx->stream>>>(F_down, F_up, F_dir, planck, w_0, M, N, P, Gp, Gm, albedo,
-                                                      g0tot, s);
+    const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
+    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS>;
+    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NCOLS * LPC, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
+                                                   planck_int, c, albedo, g0_lay, g0_int, s);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
 
-template <int COLS, int CH, int MINB>
-static int launch_noniso(helios_ctx* ctx, const CpPlan& p, double* F_down, double* F_up, double* Fc_down,
-                         double* Fc_up, const double* F_dir, const double* Fc_dir, const double* planck_lay,
-                         const double* planck_int, CpNonisoCoef c, const double* albedo, const double* g0_lay,
-                         const double* g0_int, CpScalars s) {
-    auto kern = k_fband_noniso_cp<COLS, CH, MINB>;
-    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
-    kern<<<p.grid, p.threads, p.smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
-                                                      planck_int, c, albedo, g0_lay, g0_int, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+template <bool NONISO>
+static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                       const double* F_dir, const double* Fc_dir, const double* planck_lay,
+                       const double* planck_int, CpNonisoCoef c, const double* albedo, const double* g0_lay,
+                       const double* g0_int, CpScalars s, int ncol) {
+    const int nlay = s.nint - 1;
+#define WP_ARGS ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo, g0_lay, g0_int, s, ncol
+    if (NONISO) {
+        // twice the constants per layer: 32 lanes per column keep the per-lane register arrays short
+        if (nlay <= 32) return launch_wp<NONISO, 1, 32, 8>(WP_ARGS);
+        if (nlay <= 64) return launch_wp<NONISO, 2, 32, 8>(WP_ARGS);
+        if (nlay <= 96) return launch_wp<NONISO, 3, 32, 8>(WP_ARGS);
+        if (nlay <= 128) return launch_wp<NONISO, 4, 32, 8>(WP_ARGS);
+        if (nlay <= 256) return launch_wp<NONISO, 8, 32, 4>(WP_ARGS);
+    } else {
+        if (nlay <= 16) return launch_wp<NONISO, 1, 16, 16>(WP_ARGS);
+        if (nlay <= 32) return launch_wp<NONISO, 2, 16, 16>(WP_ARGS);
+        if (nlay <= 48) return launch_wp<NONISO, 3, 16, 16>(WP_ARGS);
+        if (nlay <= 80) return launch_wp<NONISO, 5, 16, 16>(WP_ARGS);
+        if (nlay <= 112) return launch_wp<NONISO, 7, 16, 16>(WP_ARGS);
+        if (nlay <= 128) return launch_wp<NONISO, 8, 16, 16>(WP_ARGS);
+        if (nlay <= 256) return launch_wp<NONISO, 8, 32, 8>(WP_ARGS);
+    }
+#undef WP_ARGS
+    return -1;
 }
 
-static int cp_variant() {
-    const char* v = getenv("HELIOS_CP_VARIANT");  // tuning hook (scratch/tune_fband.py); 0 = first that fits
-    return v ? atoi(v) : 0;
-}
-
-// returns HELIOS_OK when launched, -1 when the shape does not fit this scheme (caller falls back to the
-// one-thread-per-column kernel of fband.cu)
+// return HELIOS_OK when launched, -1 when the shape does not fit this scheme (the caller then falls back to
+// the one-thread-per-column kernel of fband.cu)
 int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double* F_dir, const double* planck,
                      const double* w_0, const double* M, const double* N, const double* P, const double* Gp,
                      const double* Gm, const double* albedo, const double* g0tot, double g_0, double Rstar,
                      double a, int nint, int nbin, double f_factor, double mu_star, int ny, double epsi,
                      int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
-    const int nlay = nint - 1, ncol = nbin * ny;
-    CpPlan p;
-    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0};
-    const int var = cp_variant();
-#define TRY_ISO(ID, COLS, CH, MINB)                                                                        \
-    if ((var == 0 || var == ID) && cp_plan(ctx, nlay, ncol, 4, COLS, CH, MINB, &p)) {                      \
-        s.nchunk = p.nchunk;                                                                               \
-        return launch_iso<COLS, CH, MINB>(ctx, p, F_down, F_up, F_dir, planck, w_0, M, N, P, Gp, Gm, albedo, g0tot, s); \
-    }
-    TRY_ISO(2, 16, 4, 2)
-    TRY_ISO(1, 16, 4, 3)
-    TRY_ISO(3, 16, 5, 3)
-    TRY_ISO(4, 8, 5, 4)
-    TRY_ISO(5, 16, 8, 2)
-    TRY_ISO(6, 8, 8, 2)
-    TRY_ISO(7, 8, 16, 2)
-#undef TRY_ISO
-    return -1;
+    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0};
+    CpNonisoCoef c{w_0, nullptr, nullptr, nullptr, nullptr, nullptr, M, nullptr, N, nullptr, P, nullptr, Gp, nullptr, Gm, nullptr};
+    return dispatch_wp<false>(ctx, F_down, F_up, nullptr, nullptr, F_dir, nullptr, planck, nullptr, c, albedo, g0tot,
+                              nullptr, s, nbin * ny);
 }
 
 int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
@@ -516,23 +448,8 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         const double* g0_int, double g_0, double Rstar, double a, int nint, int nbin,
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
-    const int nlay = nint - 1, ncol = nbin * ny;
-    CpPlan p;
-    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0};
-    const int var = cp_variant();
-#define TRY_NONISO(ID, COLS, CH, MINB)                                                                     \
-    if ((var == 0 || var == ID) && cp_plan(ctx, nlay, ncol, 8, COLS, CH, MINB, &p)) {                      \
-        s.nchunk = p.nchunk;                                                                               \
-        return launch_noniso<COLS, CH, MINB>(ctx, p, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, \
-                                             planck_int, c, albedo, g0_lay, g0_int, s);                    \
-    }
-    TRY_NONISO(2, 8, 4, 3)
-    TRY_NONISO(1, 8, 5, 3)
-    TRY_NONISO(3, 16, 4, 1)
-    TRY_NONISO(4, 8, 5, 2)
-    TRY_NONISO(5, 16, 5, 1)
-    TRY_NONISO(6, 8, 8, 2)
-    TRY_NONISO(7, 4, 8, 2)
-#undef TRY_NONISO
-    return -1;
+    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds,
+                scat_corr, npass, 0, 0};
+    return dispatch_wp<true>(ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo,
+                             g0_lay, g0_int, s, nbin * ny);
 }

@@ -70,4 +70,12 @@ __device__ __forceinline__ double boa_flux(double A_s, double Fdir0, double Fd0,
     return __fma_rn(A_s, __dadd_rn(Fdir0, Fd0), emis);
 }
 
+// the emission part of boa_flux alone: boa_flux(A, Fdir, Fd, ...) == fma(A, Fdir + Fd, boa_emission(A, ...))
+__device__ __forceinline__ double boa_emission(double A_s, double w0, double E, double B_surf) {
+    return __dmul_rn(
+        __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0)),
+                  __dsub_rn(E, w0)),
+        B_surf);
+}
+
 __device__ __forceinline__ double tiny_to_abs(double f) { return fabs(f) < 1e-100 ? fabs(f) : f; }
