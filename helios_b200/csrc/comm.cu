@@ -35,15 +35,18 @@ __device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long lon
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// vec_a[0..n) and (optionally) vec_b[0..n) are reduced in one exchange; `net` (optional) receives a - b.
 __global__ void __launch_bounds__(256)
-k_peer_allreduce(CommPeers peers, double* __restrict__ vec, int n, int rank, int world, int slot,
-                 size_t data_bytes, unsigned long long seq) {
+k_peer_allreduce(CommPeers peers, double* __restrict__ vec_a, double* __restrict__ vec_b,
+                 double* __restrict__ net, int n, int rank, int world, int slot, size_t data_bytes,
+                 unsigned long long seq) {
     const int bank = (int)(seq & 1ull);
+    const int nn = vec_b ? 2 * n : n;
     // 1. scatter my partials into slot `rank` of every mailbox (my own included)
-    for (int k = threadIdx.x; k < n * world; k += blockDim.x) {
-        const int r = k / n, t = k - r * n;
+    for (int k = threadIdx.x; k < nn * world; k += blockDim.x) {
+        const int r = k / nn, t = k - r * nn;
         double* data = reinterpret_cast<double*>(peers.p[r]);
-        data[((size_t)bank * world + rank) * slot + t] = vec[t];
+        data[((size_t)bank * world + rank) * slot + t] = t < n ? vec_a[t] : vec_b[t - n];
     }
     __threadfence_system();
     __syncthreads();
@@ -66,10 +69,39 @@ k_peer_allreduce(CommPeers peers, double* __restrict__ vec, int n, int rank, int
     // 4. add the world's slots in rank order
     const volatile double* mine = reinterpret_cast<const volatile double*>(peers.p[rank]);
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
-        double acc = 0.0;
-        for (int r = 0; r < world; r++) acc += mine[((size_t)bank * world + r) * slot + t];
-        vec[t] = acc;
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < world; r++) a += mine[((size_t)bank * world + r) * slot + t];
+        vec_a[t] = a;
+        if (vec_b) {
+            for (int r = 0; r < world; r++) b += mine[((size_t)bank * world + r) * slot + n + t];
+            vec_b[t] = b;
+            if (net) net[t] = a - b;
+        }
     }
+}
+
+static int comm_launch(helios_ctx* ctx, const char* who, double* a, double* b, double* net, int n) {
+    helios_comm_state* c = ctx->comm;
+    if (!c) {
+        helios_set_error("%s: no communicator", who);
+        return HELIOS_ERR_STATE;
+    }
+    if (a == nullptr || n <= 0 || (b ? 2 * n : n) > c->slot) {
+        helios_set_error("%s: invalid argument (n = %d, slot = %d doubles)", who, n, c->slot);
+        return HELIOS_ERR_ARG;
+    }
+    for (int r = 0; r < c->world; r++) {
+        if (c->peers[r] == nullptr) {
+            helios_set_error("%s: peer %d not connected", who, r);
+            return HELIOS_ERR_STATE;
+        }
+    }
+    CommPeers p;
+    for (int r = 0; r < COMM_MAX_WORLD; r++) p.p[r] = c->peers[r];
+    c->seq++;
+    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(p, a, b, net, n, c->rank, c->world, c->slot, c->data_bytes, c->seq);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
 }
 
 extern "C" {
@@ -130,24 +162,14 @@ int helios_comm_connect(helios_ctx* ctx, const unsigned char* handles) {
 
 int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n) {
     HCTX(ctx);
-    helios_comm_state* c = ctx->comm;
-    if (!c) {
-        helios_set_error("helios_comm_allreduce_sum: no communicator");
-        return HELIOS_ERR_STATE;
-    }
-    HARG(vec != nullptr && n > 0 && n <= c->slot);
-    for (int r = 0; r < c->world; r++) {
-        if (c->peers[r] == nullptr) {
-            helios_set_error("helios_comm_allreduce_sum: peer %d not connected", r);
-            return HELIOS_ERR_STATE;
-        }
-    }
-    CommPeers p;
-    for (int r = 0; r < COMM_MAX_WORLD; r++) p.p[r] = c->peers[r];
-    c->seq++;
-    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(p, vec, n, c->rank, c->world, c->slot, c->data_bytes, c->seq);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+    return comm_launch(ctx, "helios_comm_allreduce_sum", vec, nullptr, nullptr, n);
+}
+
+int helios_comm_allreduce_flux_totals(helios_ctx* ctx, double* F_up_tot, double* F_down_tot, double* F_net,
+                                      int numinterfaces) {
+    HCTX(ctx);
+    HARG(F_down_tot != nullptr && F_net != nullptr);
+    return comm_launch(ctx, "helios_comm_allreduce_flux_totals", F_up_tot, F_down_tot, F_net, numinterfaces);
 }
 
 int helios_comm_destroy(helios_ctx* ctx) {

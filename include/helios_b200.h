@@ -352,6 +352,12 @@ int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles,
 int helios_comm_connect(helios_ctx* ctx, const unsigned char* handles);
 /* vec[0..n) (device, n <= slot_doubles) <- sum over ranks, fixed rank order */
 int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n);
+/* the per-iteration exchange of a wavelength-sharded run, fused: F_up_tot and F_down_tot (the partial sums
+ * over this rank's bins, as written by helios_integrate_flux_double, K:2474-2495) become the sums over all
+ * ranks in ONE peer-memory round trip, and F_net = F_up_tot - F_down_tot is recomputed (K:2509).
+ * slot_doubles must be >= 2*numinterfaces. */
+int helios_comm_allreduce_flux_totals(helios_ctx* ctx, double* F_up_tot, double* F_down_tot, double* F_net,
+                                      int numinterfaces);
 int helios_comm_destroy(helios_ctx* ctx);
 
 #ifdef __cplusplus

@@ -229,6 +229,27 @@ class OracleCompute(object):
         q.dev_delta_t_prefactor, q.dev_F_net_diff = r["prefactor"], r["F_net_diff"]
         q.dev_F_smooth, q.dev_F_smooth_sum = r["F_smooth"], r["F_smooth_sum"]
 
+    # ---- kappa / c_p / entropy / phase number from file (C:199-292; K:703-919)
+    def _entr(self, q, temp, press, tab, n, log_t):
+        return O.scalar_interpol(temp, q.dev_entr_temp, press, q.dev_entr_press, tab, int(q.entr_npress),
+                                 int(q.entr_ntemp), int(n), log_t=log_t)
+
+    def interpolate_kappa_and_cp(self, q):
+        if not isinstance(q.input_kappa_value, str):
+            return
+        q.dev_kappa_lay = self._entr(q, q.dev_T_lay, q.dev_p_lay, q.dev_entr_kappa, q.nlayer, False)
+        q.dev_c_p_lay = self._entr(q, q.dev_T_lay, q.dev_p_lay, q.dev_entr_c_p, q.nlayer, True)
+        if q.iso == 0:
+            q.dev_kappa_int = self._entr(q, q.dev_T_int, q.dev_p_int, q.dev_entr_kappa, q.ninterface, False)
+
+    def interpolate_entropy(self, q):
+        if isinstance(q.input_kappa_value, str):
+            q.dev_entropy_lay = self._entr(q, q.dev_T_lay, q.dev_p_lay, q.dev_entr_entropy, q.nlayer, True)
+
+    def interpolate_phase_state(self, q):
+        if q.input_kappa_value == "water_atmo":
+            q.dev_phase_number_lay = self._entr(q, q.dev_T_lay, q.dev_p_lay, q.dev_entr_phase_number, q.nlayer, False)
+
     # ---- post-processing
     def integrate_optdepth_transmission(self, q):
         nb, nl, ny = int(q.nbin), int(q.nlayer), int(q.ny)

@@ -298,6 +298,86 @@ class RefCompute:
               q.dev_gauss_y, f64(mass_spec_g), i32(s), i32(ro_method), i32(q.ny), i32(q.nbin), i32(q.ninterface),
               block=(32, 32, 1), grid=((int(q.nbin) + 31) // 32, (int(q.ninterface) + 31) // 32, 1))
 
+    def calculate_H2O_Rayleigh_scattering(self, q, s):  # C:1390-1423
+        from helios_b200 import host
+        mass = f64(q.species_list[s].weight * host.AMU)
+        k = self._k("calc_h2o_scat")
+        k(q.dev_T_lay, q.dev_p_lay, q.dev_opac_wave, q.dev_scat_cross_spec_lay, q.dev_vmr_spec_lay, mass, i32(q.nbin),
+          i32(q.nlayer), block=(16, 16, 1), grid=((int(q.nbin) + 15) // 16, (int(q.nlayer) + 15) // 16, 1))
+        if q.iso == 0:
+            k(q.dev_T_int, q.dev_p_int, q.dev_opac_wave, q.dev_scat_cross_spec_int, q.dev_vmr_spec_int, mass,
+              i32(q.nbin), i32(q.ninterface), block=(16, 16, 1),
+              grid=((int(q.nbin) + 15) // 16, (int(q.ninterface) + 15) // 16, 1))
+
+    def add_to_mixed_scat_cross_sect(self, q):  # C:1425-1452
+        k = self._k("add_to_mixed_scat")
+        k(q.dev_vmr_spec_lay, q.dev_scat_cross_spec_lay, q.dev_scat_cross_lay, i32(q.nbin), i32(q.nlayer),
+          block=(16, 16, 1), grid=((int(q.nbin) + 15) // 16, (int(q.nlayer) + 15) // 16, 1))
+        if q.iso == 0:
+            k(q.dev_vmr_spec_int, q.dev_scat_cross_spec_int, q.dev_scat_cross_int, i32(q.nbin), i32(q.ninterface),
+              block=(16, 16, 1), grid=((int(q.nbin) + 15) // 16, (int(q.ninterface) + 15) // 16, 1))
+
+    # ---- kappa / c_p / entropy / phase (C:199-292): launched only when kappa comes from a file
+    def _entr(self, name, temp, press, out, tab, n, q):
+        self._k(name)(temp, q.dev_entr_temp, press, q.dev_entr_press, out, tab, i32(q.entr_npress), i32(q.entr_ntemp),
+                      i32(n), block=(16, 1, 1), grid=((int(n) + 15) // 16, 1, 1))
+
+    def interpolate_kappa_and_cp(self, q):
+        if not isinstance(q.input_kappa_value, str):
+            return
+        self._entr("kappa_interpol", q.dev_T_lay, q.dev_p_lay, q.dev_kappa_lay, q.dev_entr_kappa, q.nlayer, q)
+        self._entr("cp_interpol", q.dev_T_lay, q.dev_p_lay, q.dev_c_p_lay, q.dev_entr_c_p, q.nlayer, q)
+        if q.iso == 0:
+            self._entr("kappa_interpol", q.dev_T_int, q.dev_p_int, q.dev_kappa_int, q.dev_entr_kappa, q.ninterface, q)
+
+    def interpolate_entropy(self, q):
+        if isinstance(q.input_kappa_value, str):
+            self._entr("entropy_interpol", q.dev_T_lay, q.dev_p_lay, q.dev_entropy_lay, q.dev_entr_entropy, q.nlayer, q)
+
+    def interpolate_phase_state(self, q):
+        if q.input_kappa_value == "water_atmo":
+            self._entr("phase_number_interpol", q.dev_T_lay, q.dev_p_lay, q.dev_phase_number_lay,
+                       q.dev_entr_phase_number, q.nlayer, q)
+
+    # ---- post-processing (C:1176-1296)
+    def integrate_optdepth_transmission(self, q):
+        grid = ((int(q.nbin) + 15) // 16, (int(q.nlayer) + 15) // 16, 1)
+        if q.iso == 1:
+            self._k("integrate_optdepth_transmission_iso")(
+                q.dev_trans_wg, q.dev_trans_band, q.dev_delta_tau_wg, q.dev_delta_tau_band, q.dev_gauss_weight,
+                i32(q.nbin), i32(q.nlayer), i32(q.ny), block=(16, 16, 1), grid=grid)
+        else:
+            self._k("integrate_optdepth_transmission_noniso")(
+                q.dev_trans_wg_upper, q.dev_trans_wg_lower, q.dev_trans_band, q.dev_delta_tau_wg_upper,
+                q.dev_delta_tau_wg_lower, q.dev_delta_tau_band, q.dev_gauss_weight, q.dev_delta_tau_all_clouds,
+                q.dev_delta_tau_all_clouds_upper, q.dev_delta_tau_all_clouds_lower, i32(q.nbin), i32(q.nlayer),
+                i32(q.ny), block=(16, 16, 1), grid=grid)
+
+    def calculate_contribution_function(self, q):
+        grid = ((int(q.nbin) + 15) // 16, (int(q.nlayer) + 15) // 16, 1)
+        if q.iso == 1:
+            self._k("calc_contr_func_iso")(
+                q.dev_trans_wg, q.dev_trans_weight_band, q.dev_contr_func_band, q.dev_gauss_weight,
+                q.dev_planckband_lay, f64(q.epsi), i32(q.nbin), i32(q.nlayer), i32(q.ny), block=(16, 16, 1), grid=grid)
+        else:
+            self._k("calc_contr_func_noniso")(
+                q.dev_trans_wg_upper, q.dev_trans_wg_lower, q.dev_trans_weight_band, q.dev_contr_func_band,
+                q.dev_gauss_weight, q.dev_planckband_lay, f64(q.epsi), i32(q.nbin), i32(q.nlayer), i32(q.ny),
+                block=(16, 16, 1), grid=grid)
+
+    def calculate_mean_opacities(self, q):
+        self._k("calc_mean_opacities")(
+            q.dev_planck_opac_T_pl, q.dev_ross_opac_T_pl, q.dev_planck_opac_T_star, q.dev_ross_opac_T_star,
+            q.dev_opac_wg_lay, q.dev_abs_cross_all_clouds_lay, q.dev_meanmolmass_lay, q.dev_planckband_lay,
+            q.dev_opac_interwave, q.dev_opac_deltawave, q.dev_T_lay, q.dev_gauss_weight, q.dev_gauss_y,
+            q.dev_opac_band_lay, i32(q.nlayer), i32(q.nbin), i32(q.ny), f64(q.T_star), block=(16, 1, 1),
+            grid=((int(q.nlayer) + 15) // 16, 1, 1))
+
+    def integrate_beamflux(self, q):
+        self._k("integrate_beamflux")(q.dev_F_dir_tot, q.dev_F_dir_band, q.dev_opac_deltawave, q.dev_gauss_weight,
+                                      i32(q.nbin), i32(q.ninterface), block=(16, 1, 1),
+                                      grid=((int(q.ninterface) + 15) // 16, 1, 1))
+
     # generic access for the remaining (post-processing) kernels
     def launch(self, name, *args, block, grid):
         self._k(name)(*args, block=block, grid=grid)

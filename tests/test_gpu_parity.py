@@ -258,3 +258,35 @@ def test_layer_parallel_sweep_equals_column_sweep(ctx, variant):
         ctx.set_fband_mode(0)
     for n, a, b in zip(names, results[1], results[2]):
         assert_close(b, a, "layer-parallel vs column sweep: " + n, rtol=1e-12)
+
+
+@pytest.mark.parametrize("iso", [1, 0])
+def test_kappa_cp_entropy_phase_from_file(ctx, iso):
+    """K:703-919 (kappa_interpol, cp_interpol, entropy_interpol, phase_number_interpol; launch sites C:199-292):
+    only launched when `kappa value = file`; checked against NumPy and against the reference's kernels"""
+    q = synthetic.make_store("C1" if iso else "C2", ctx=ctx, **SMALL)
+    rng = np.random.default_rng(5)
+    nt, npr = 15, 12
+    q.input_kappa_value = "water_atmo"
+    q.entr_ntemp, q.entr_npress = np.int32(nt), np.int32(npr)
+    q.entr_temp = np.linspace(100.0, 4000.0, nt)
+    q.entr_press = 10.0 ** np.linspace(-1.0, 9.5, npr)
+    q.entr_kappa = rng.uniform(0.1, 0.4, nt * npr)
+    q.entr_c_p = rng.uniform(1e7, 4e8, nt * npr)
+    q.entr_entropy = rng.uniform(1e8, 1e9, nt * npr)
+    q.entr_phase_number = rng.integers(0, 3, nt * npr).astype(np.float64)
+    n = int(q.nlayer)
+    # includes temperatures outside the table on both sides (the kernels clamp to [0.001, n - 1.001])
+    q.T_lay = np.concatenate([np.linspace(4500.0, 60.0, n), [2400.0]])
+    synthetic.upload(q)
+    comp, oc = Compute(ctx, verbose=False), OracleCompute()
+    comp.interpolate_temperatures(q)
+    outs = {"interpolate_kappa_and_cp": ["kappa_lay", "c_p_lay"] + ([] if iso else ["kappa_int"]),
+            "interpolate_entropy": ["entropy_lay"], "interpolate_phase_state": ["phase_number_lay"]}
+    bad = Failures()
+    for method, names in outs.items():
+        stage_vs_oracle(q, comp, oc, method, names, soft=bad)
+        if ref_gpu.available():
+            stage_vs_ref(q, comp, ref_gpu.RefCompute(ctx.device), method, names, soft=bad)
+    bad.check()
+    assert np.all(q.dev_kappa_lay.get() > 0)
