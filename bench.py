@@ -47,6 +47,30 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _traffic_from_profile(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the flux-sweep kernel, from the committed
+    `ncu --set full` summary of this workload (profiles/); None if no capture of this workload is committed"""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_fband*%s*.csv" % workload.lower()))):
+        rows = list(csv.reader(open(path)))
+        h, units = rows[0], rows[1]
+        vals = []
+        for r in rows[2:]:
+            if "fband" not in r[0]:
+                continue
+            tot = 0.0
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = h.index(key)
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+                tot += float(r[i]) * scale
+            vals.append(tot)
+        if vals:
+            best = {"bytes_per_launch": sum(vals) / len(vals), "source": os.path.relpath(path, ROOT)}
+    return best
+
+
 class ClockSampler(object):
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -231,6 +255,7 @@ def run_ours(args):
     t_solve, t_fband, t_e2e = [float(v) for v in times.tolist()]
     if rank == 0:
         peak, peak_src = _peaks()
+        traffic = _traffic_from_profile(args.workload)
         bpc = _bytes_per_cell(q)
         t_k = t_fband / args.steps * 1e-3
         achieved = bpc * cells / t_k / 1e9
@@ -252,7 +277,9 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_fband_%s (all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_cell_per_solve": bpc,
+                         "traffic": (traffic or {}).get("bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                         "algorithmic_bytes_per_launch": bpc * cells,
+                         "peak_source": peak_src, "bytes_per_cell_per_solve": bpc,
                          "kernel_ms": t_k * 1e3,
                          "per_pass_equiv_GBs": achieved * npass},
             "clocks": clocks,

@@ -36,6 +36,9 @@ struct helios_ctx {
     double* scratch = nullptr;
     size_t scratch_bytes = 0;
     helios_comm_state* comm = nullptr;
+    // pow(epsi,-2), pow(mu_star,-2) of calc_trans_*, keyed on (epsi, mu_star): trans.cu
+    double trans_cache[4] = {0, 0, 0, 0};
+    bool trans_cache_valid = false;
     std::mutex mu;
 };
 

@@ -5,6 +5,7 @@
 struct TransScalars {
     double g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition;
     int scat, nbin, ny, nlayer, clouds, scat_corr, debug;
+    double inv_eps2, inv_mu2;  // pow(epsi, -2.0), pow(mu_star, -2.0): see trans_constants()
 };
 
 struct CellCoeffs {
@@ -39,13 +40,44 @@ __device__ __forceinline__ CellCoeffs cell_coeffs(double ray, double cloud_scat,
     c.P = ((zm * zm) - (zp * zp)) * c.trans;
     // G+ / G- (K:149-213)
     const double num = w0 * (E * one_m_wg + g0 * s.epsi / s.epsi2);
-    const double denom = E * pow(s.epsi, -2.0) * (E - w0) * one_m_wg - pow(s.mu_star, -2.0);
+    const double denom = E * s.inv_eps2 * (E - w0) * one_m_wg - s.inv_mu2;
     const double inv_eps = 1.0 / s.epsi;
     const double cross = 1.0 / (s.mu_star * E * one_m_wg);
     const double third = s.epsi * w0 * g0 * s.mu_star / (s.epsi2 * E * one_m_wg);
     c.Gp = g_limit(0.5 * (num / denom * (inv_eps + cross) + third));
     c.Gm = g_limit(0.5 * (num / denom * (inv_eps - cross) - third));
     return c;
+}
+
+// The G+/- denominator contains pow(epsi, -2.0) and pow(mu_star, -2.0) (K:168, K:202): loop-invariant
+// scalars that the reference re-evaluates with the generic libdevice pow in every cell (four calls per cell).
+// They are evaluated ONCE here -- on the device, with the same libdevice pow, because the denominator cancels
+// to O(w0) and a last-bit difference of a host pow would be amplified -- and cached in the context until epsi
+// or mu_star change.
+__global__ void k_trans_constants(double epsi, double mu_star, double* __restrict__ out) {
+    out[0] = pow(epsi, -2.0);
+    out[1] = pow(mu_star, -2.0);
+}
+
+static int trans_constants(helios_ctx* ctx, TransScalars& s) {
+    if (!(ctx->trans_cache_valid && ctx->trans_cache[0] == s.epsi && ctx->trans_cache[1] == s.mu_star)) {
+        double* d = nullptr;
+        int rc = helios_ctx_scratch(ctx, 2 * sizeof(double), &d);
+        if (rc != HELIOS_OK) return rc;
+        k_trans_constants<<<1, 1, 0, ctx->stream>>>(s.epsi, s.mu_star, d);
+        HLAUNCHED(ctx);
+        double h[2];
+        HCUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        HCUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->trans_cache[0] = s.epsi;
+        ctx->trans_cache[1] = s.mu_star;
+        ctx->trans_cache[2] = h[0];
+        ctx->trans_cache[3] = h[1];
+        ctx->trans_cache_valid = true;
+    }
+    s.inv_eps2 = ctx->trans_cache[2];
+    s.inv_mu2 = ctx->trans_cache[3];
+    return HELIOS_OK;
 }
 
 // one thread per cell of the [i][x][y] arrays, flat index -> fully coalesced 8-array store
@@ -215,6 +247,84 @@ k_fdir(double* __restrict__ F_dir, double* __restrict__ Fc_dir, const double* __
     }
 }
 
+// Layer-parallel form of the non-geometric branch above.  The attenuation factors exp(dtau/mu*) of a
+// column do not depend on each other, only their running product does: a block takes FD_COLS columns, all of
+// its threads evaluate the exponentials of every (layer, column) cell in parallel into shared memory, one warp
+// then forms the running products in the same top-down order as k_fdir (bit-identical results), and all
+// threads store the block's [layer][column] slab coalesced.  ~100 dependent multiplies per column instead of
+// ~100 dependent (load -> exp -> multiply) round trips.
+#define FD_COLS 32
+#define FD_THREADS 256
+template <bool NONISO>
+__global__ void __launch_bounds__(FD_THREADS)
+k_fdir_lp(double* __restrict__ F_dir, double* __restrict__ Fc_dir, const double* __restrict__ planck_lay,
+          const double* __restrict__ dtau_a, const double* __restrict__ dtau_b, double mu_star, double R_star,
+          double a, int dir_beam, int nint, int nbin, int ny) {
+    extern __shared__ double fd_sm[];
+    const int ncol = nbin * ny;
+    const int nlay = nint - 1;
+    double* s_full = fd_sm;                                   // [nlay][FD_COLS]: exp of the whole layer -> F_dir
+    double* s_half = fd_sm + (size_t)nlay * FD_COLS;          // NONISO: exp of the upper half -> Fc_dir
+    const int c = threadIdx.x % FD_COLS;
+    const int r = threadIdx.x / FD_COLS;
+    constexpr int ROWS = FD_THREADS / FD_COLS;
+    const int col = blockIdx.x * FD_COLS + c;
+    const bool live = col < ncol;
+    if (live) {
+        for (int i = r; i < nlay; i += ROWS) {
+            const size_t e = col + (size_t)ncol * i;
+            if (NONISO) {
+                const double du = dtau_a[e];
+                s_half[i * FD_COLS + c] = exp(du / mu_star);
+                s_full[i * FD_COLS + c] = exp((du + dtau_b[e]) / mu_star);
+            } else {
+                s_full[i * FD_COLS + c] = exp(dtau_a[e] / mu_star);
+            }
+        }
+    }
+    __syncthreads();
+    if (r == 0 && live) {
+        const int x = col / ny;
+        const double I_dir = ((R_star / a) * (R_star / a)) * hc::PI * planck_lay[nlay + (size_t)x * (nlay + 2)];
+        double F = -dir_beam * mu_star * I_dir;
+        F_dir[col + (size_t)ncol * nlay] = F;
+        for (int i = nlay - 1; i >= 0; i--) {
+            if (NONISO) s_half[i * FD_COLS + c] = F * s_half[i * FD_COLS + c];
+            F *= s_full[i * FD_COLS + c];
+            s_full[i * FD_COLS + c] = F;
+        }
+    }
+    __syncthreads();
+    if (live) {
+        for (int i = r; i < nlay; i += ROWS) {
+            const size_t e = col + (size_t)ncol * i;
+            F_dir[e] = s_full[i * FD_COLS + c];
+            if (NONISO) Fc_dir[e] = s_half[i * FD_COLS + c];
+        }
+    }
+}
+
+template <bool NONISO>
+static int launch_fdir(helios_ctx* ctx, double* F_dir, double* Fc_dir, const double* planck_lay,
+                       const double* dtau_a, const double* dtau_b, const double* z_lay, double mu_star,
+                       double R_planet, double R_star, double a, int dir_beam, int geom, int nint, int nbin,
+                       int ny) {
+    const int ncol = nbin * ny;
+    const size_t smem = (size_t)(nint - 1) * FD_COLS * sizeof(double) * (NONISO ? 2 : 1);
+    if (geom != 1 && smem <= 200 * 1024) {
+        auto kern = k_fdir_lp<NONISO>;
+        HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<ceil_div(ncol, FD_COLS), FD_THREADS, smem, ctx->stream>>>(F_dir, Fc_dir, planck_lay, dtau_a, dtau_b,
+                                                                        mu_star, R_star, a, dir_beam, nint, nbin, ny);
+    } else {
+        k_fdir<NONISO><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(F_dir, Fc_dir, planck_lay, dtau_a, dtau_b, z_lay,
+                                                                     mu_star, R_planet, R_star, a, dir_beam, geom,
+                                                                     nint, nbin, ny);
+    }
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
 extern "C" {
 
 int helios_calc_trans_iso(helios_ctx* ctx, double* trans_wg, double* delta_tau_wg, double* M_term,
@@ -233,7 +343,11 @@ int helios_calc_trans_iso(helios_ctx* ctx, double* trans_wg, double* delta_tau_w
     HARG(clouds == 0 || g_0_tot_lay != nullptr);
     HARG(nbin > 0 && ny > 0 && nlayer > 0);
     TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
-                   scat, nbin, ny, nlayer, clouds, scat_corr, debug};
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0};
+    {
+        const int rc = trans_constants(ctx, s);
+        if (rc != HELIOS_OK) return rc;
+    }
     const long long total = (long long)nbin * ny * nlayer;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ctx->num_sms * 32;
@@ -271,7 +385,11 @@ int helios_calc_trans_noniso(
     HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
     HARG(nbin > 0 && ny > 0 && nlayer > 0);
     TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
-                   scat, nbin, ny, nlayer, clouds, scat_corr, debug};
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0};
+    {
+        const int rc = trans_constants(ctx, s);
+        if (rc != HELIOS_OK) return rc;
+    }
     NonisoOut o{trans_wg_upper, trans_wg_lower, delta_tau_wg_upper, delta_tau_wg_lower, M_upper, M_lower,
                 N_upper, N_lower, P_upper, P_lower, G_plus_upper, G_plus_lower, G_minus_upper,
                 G_minus_lower, delta_tau_all_clouds_upper, delta_tau_all_clouds_lower, w_0_upper,
@@ -307,12 +425,8 @@ int helios_fdir_iso(helios_ctx* ctx, double* F_dir_wg, const double* planckband_
     HCTX(ctx);
     HARG(F_dir_wg && planckband_lay && delta_tau_wg && ninterface > 1 && nbin > 0 && ny > 0);
     HARG(geom_zenith_corr != 1 || z_lay != nullptr);
-    const int ncol = nbin * ny;
-    k_fdir<false><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(
-        F_dir_wg, nullptr, planckband_lay, delta_tau_wg, nullptr, z_lay, mu_star, R_planet, R_star, a,
-        dir_beam, geom_zenith_corr, ninterface, nbin, ny);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+    return launch_fdir<false>(ctx, F_dir_wg, nullptr, planckband_lay, delta_tau_wg, nullptr, z_lay, mu_star,
+                              R_planet, R_star, a, dir_beam, geom_zenith_corr, ninterface, nbin, ny);
 }
 
 int helios_fdir_noniso(helios_ctx* ctx, double* F_dir_wg, double* Fc_dir_wg, const double* planckband_lay,
@@ -323,12 +437,8 @@ int helios_fdir_noniso(helios_ctx* ctx, double* F_dir_wg, double* Fc_dir_wg, con
     HARG(F_dir_wg && Fc_dir_wg && planckband_lay && delta_tau_wg_upper && delta_tau_wg_lower &&
          ninterface > 1 && nbin > 0 && ny > 0);
     HARG(geom_zenith_corr != 1 || z_lay != nullptr);
-    const int ncol = nbin * ny;
-    k_fdir<true><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(
-        F_dir_wg, Fc_dir_wg, planckband_lay, delta_tau_wg_upper, delta_tau_wg_lower, z_lay, mu_star,
-        R_planet, R_star, a, dir_beam, geom_zenith_corr, ninterface, nbin, ny);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+    return launch_fdir<true>(ctx, F_dir_wg, Fc_dir_wg, planckband_lay, delta_tau_wg_upper, delta_tau_wg_lower,
+                             z_lay, mu_star, R_planet, R_star, a, dir_beam, geom_zenith_corr, ninterface, nbin, ny);
 }
 
 }  // extern "C"

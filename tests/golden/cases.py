@@ -109,6 +109,7 @@ def run_case(case, q, engine, io, after, ref_signature=False):
     """`ref_signature`: RefCompute.add_to_mixed_opacity takes (mass in grams, s, ro_method)"""
     config, opt = CASES[case]
     iso = int(q.iso) == 1
+    q.iter_value = np.int32(0)
 
     def site(method, names, *args):
         getattr(engine, method)(q, *args)
