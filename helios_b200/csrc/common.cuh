@@ -21,6 +21,25 @@ constexpr double AMU = 1.6605390666e-24;
 
 struct helios_comm_state;
 
+// Batched atmospheres (helios_ctx_set_batch): nbatch atmospheres of identical shape go through every
+// per-iteration kernel in ONE launch.  Per-atmosphere arrays hold nbatch consecutive single-atmosphere
+// arrays; their strides follow from the shape by the reference's allocation sizes (Q:400-409, 411-461,
+// 613-665), collected here once.
+struct BatchDesc {
+    int nbatch = 1;  // 1 = batch mode off
+    int nlayer = 0, nbin = 0, ny = 0;
+    const int* table_index = nullptr;     // device [nbatch]: which opacity table an atmosphere reads (null: 0)
+    size_t ktable_stride = 0, cross_stride = 0, mmass_stride = 0;  // doubles between consecutive tables
+    const double* g = nullptr;            // device [nbatch]: surface gravity (null: the scalar argument)
+    const double* planck_star = nullptr;  // device [nbatch][nbin]: stellar Planck row of each atmosphere
+    int* done = nullptr;                  // device [nbatch]: converged flags, owned by the context
+    __host__ __device__ int nint() const { return nlayer + 1; }
+    __host__ __device__ size_t wg() const { return (size_t)(nlayer + 1) * nbin * ny; }  // every [i][x][y] array (Q:407)
+    __host__ __device__ size_t band_lay() const { return (size_t)nlayer * nbin; }
+    __host__ __device__ size_t band_int() const { return (size_t)(nlayer + 1) * nbin; }
+    __host__ __device__ size_t planck_lay() const { return (size_t)(nlayer + 2) * nbin; }
+};
+
 struct helios_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -36,6 +55,7 @@ struct helios_ctx {
     double* scratch = nullptr;
     size_t scratch_bytes = 0;
     helios_comm_state* comm = nullptr;
+    BatchDesc batch;
     // pow(epsi,-2), pow(mu_star,-2) of calc_trans_*, keyed on (epsi, mu_star): trans.cu
     double trans_cache[4] = {0, 0, 0, 0};
     bool trans_cache_valid = false;
@@ -80,6 +100,24 @@ int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out);
     do {                                                                       \
         (ctx)->launches++;                                                     \
         HCUDA(cudaGetLastError());                                             \
+    } while (0)
+
+// entry points that have no batched form refuse to run in batch mode instead of silently doing one atmosphere
+#define HNOBATCH(ctx)                                                          \
+    do {                                                                       \
+        if ((ctx)->batch.nbatch > 1) {                                         \
+            helios_set_error("%s: not available in batch mode", __func__);     \
+            return HELIOS_ERR_STATE;                                           \
+        }                                                                      \
+    } while (0)
+
+// batch mode: the call's dimensions must be the ones the batch was declared with
+#define HBATCHDIMS(ctx, cond)                                                  \
+    do {                                                                       \
+        if ((ctx)->batch.nbatch > 1 && !(cond)) {                              \
+            helios_set_error("%s: dimensions differ from helios_ctx_set_batch: %s", __func__, #cond); \
+            return HELIOS_ERR_ARG;                                             \
+        }                                                                      \
     } while (0)
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -542,6 +542,7 @@ int helios_fband_iso(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const 
          G_plus && G_minus && surf_albedo);
     HARG(clouds == 0 || g_0_tot_lay != nullptr);
     HARG(numinterfaces > 1 && nbin > 0 && ny > 0 && npass > 0);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
     if (ctx->fband_mode != 1) {
         const int rc = fband_iso_cp_try(ctx, F_down_wg, F_up_wg, F_dir_wg, planckband_lay, w_0, M_term, N_term,
                                         P_term, G_plus, G_minus, surf_albedo, g_0_tot_lay, g_0, Rstar, a,
@@ -553,6 +554,7 @@ int helios_fband_iso(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const 
             return HELIOS_ERR_ARG;
         }
     }
+    HNOBATCH(ctx);  // only the layer-parallel kernel has a batched form
     FbandScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s_transition,
                    numinterfaces, nbin, ny, dir_beam, clouds, scat_corr, npass};
     const int grid = fband_grid(ctx, nbin * ny);
@@ -586,6 +588,7 @@ int helios_fband_noniso(
          surf_albedo);
     HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
     HARG(numinterfaces > 1 && nbin > 0 && ny > 0 && npass > 0);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
     FbandScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition,
                    numinterfaces, nbin, ny, dir_beam, clouds, scat_corr, npass};
     NonisoCoef c{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
@@ -606,6 +609,7 @@ int helios_fband_noniso(
             return HELIOS_ERR_ARG;
         }
     }
+    HNOBATCH(ctx);  // only the layer-parallel kernel has a batched form
     const int grid = fband_grid(ctx, nbin * ny);
     DISPATCH2(k_fband_noniso, clouds == 1, scat_corr == 1,
               <<<grid, FB_THREADS, 0, ctx->stream>>>(F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, F_dir_wg,
@@ -625,6 +629,7 @@ int helios_fband_matrix_iso(
     double mu_star, int ny, double epsi, int dir_beam, int clouds, int scat_corr, int debug,
     double i2s_transition) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     (void)singlewalk; (void)debug; (void)alpha; (void)beta; (void)source_term_down; (void)source_term_up;
     HARG(F_down_wg && F_up_wg && F_dir_wg && planckband_lay && w_0 && M_term && N_term && P_term &&
          G_plus && G_minus && c_prime && d_prime && scat_trigger && trans_wg && surf_albedo);
@@ -658,6 +663,7 @@ int helios_fband_matrix_noniso(
     int ny, double epsi, double delta_tau_limit, int dir_beam, int clouds, int scat_corr, int debug,
     double i2s_transition) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     (void)singlewalk; (void)debug; (void)alpha; (void)beta; (void)source_term_down; (void)source_term_up;
     HARG(F_down_wg && F_up_wg && Fc_down_wg && Fc_up_wg && F_dir_wg && Fc_dir_wg && planckband_lay &&
          planckband_int && w_0_upper && w_0_lower && delta_tau_wg_upper && delta_tau_wg_lower &&

@@ -31,6 +31,8 @@
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
+    int nbatch;       // atmospheres per launch (helios_ctx_set_batch), 1 otherwise
+    const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
 };
 
 struct CpNonisoCoef {
@@ -125,7 +127,15 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + NCOLS - 1) / NCOLS;
 
-    for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
+        // batch: tiles enumerate (atmosphere, column tile); per-atmosphere arrays are offset by the
+        // reference's allocation sizes (every [i][x][y] array holds ninterface rows, Q:407)
+        const int atm = gtile / ntile;
+        const int tile = gtile - atm * ntile;
+        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per block
+        const size_t wgo = (size_t)atm * ncol * nint;          // [i][x][y] arrays
+        const size_t blo = (size_t)atm * s.nbin * nlay;        // [layer][x] arrays
+        const size_t bio = (size_t)atm * s.nbin * nint;        // [interface][x] arrays
         // ================= phase A: coalesced streaming, lanes along columns =================
         // Every thread owns at most CH layer rows (nlay <= LPC*CH).
         {
@@ -133,14 +143,14 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
             const int r = threadIdx.x / NCOLS;  // 0 .. LPC-1
             const int col = min(tile * NCOLS + c, ncol - 1);
             const int x = col / s.ny;
-            const double* __restrict__ BL = planck_lay + (size_t)x * (nlay + 2);
-            const double* __restrict__ BI = NONISO ? planck_int + (size_t)x * nint : nullptr;
+            const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
+            const double* __restrict__ BI = NONISO ? planck_int + bio + (size_t)x * nint : nullptr;
             constexpr int NRAW = NONISO ? 24 : 11;
             double raw[1][NRAW];
             auto load_cell = [&](int m, double* q) {
                 const int i = r + LPC * m;
                 if (i < nlay) {
-                    const size_t e = col + (size_t)ncol * i;
+                    const size_t e = wgo + col + (size_t)ncol * i;
                     const size_t bb = (size_t)x + (size_t)s.nbin * i;
                     q[0] = F_dir[e];
                     q[1] = F_dir[e + ncol];
@@ -148,18 +158,18 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                     q[6] = cfg.Gp_u[e]; q[7] = cfg.Gm_u[e];
                     q[8] = BL[i];
                     q[9] = F_up[e];
-                    q[10] = s.clouds ? g0_lay[bb] : s.g_0;
+                    q[10] = s.clouds ? g0_lay[blo + bb] : s.g_0;
                     if (NONISO) {
                         q[11] = cfg.w0_l[e]; q[12] = cfg.M_l[e]; q[13] = cfg.N_l[e]; q[14] = cfg.P_l[e];
                         q[15] = cfg.Gp_l[e]; q[16] = cfg.Gm_l[e];
-                        q[17] = cfg.dtau_u[e] + cfg.dtc_u[bb];
-                        q[18] = cfg.dtau_l[e] + cfg.dtc_l[bb];
+                        q[17] = cfg.dtau_u[e] + cfg.dtc_u[blo + bb];
+                        q[18] = cfg.dtau_l[e] + cfg.dtc_l[blo + bb];
                         q[19] = Fc_dir[e];
                         q[20] = BI[i];
                         q[21] = BI[i + 1];
                         q[22] = Fc_up[e];
-                        q[23] = s.clouds ? g0_int[bb] : s.g_0;
-                        if (s.clouds) q[10] = (q[10] + g0_int[bb + s.nbin]) / 2.0;  // g0 of the upper half
+                        q[23] = s.clouds ? g0_int[bio + bb] : s.g_0;
+                        if (s.clouds) q[10] = (q[10] + g0_int[bio + bb + s.nbin]) / 2.0;  // g0 of the upper half
                     }
                 }
             };
@@ -198,7 +208,7 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                                 g0_up = q[10];
                                 // the layer value is recovered exactly: q[10] held (gl + gi_hi)/2 only for the upper
                                 // half, so the lower half re-reads gl (cheap, L1-resident)
-                                const double gl = g0_lay[(size_t)x + (size_t)s.nbin * i];
+                                const double gl = g0_lay[blo + (size_t)x + (size_t)s.nbin * i];
                                 g0_low = (q[23] + gl) / 2.0;
                             }
                             {   // ---- upper half: layer centre <-> interface i+1 (K:1640-1664, 1771-1795)
@@ -307,20 +317,20 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                 const double Fbot = sc.A * toa + sc.B;                       // flux leaving my chunk (interface lo)
                 double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);      // = flux entering it (interface hi)
                 if (sl >= nch - 1) F = toa;
-                if (wr && sl == nch - 1) F_down[colc + (size_t)ncol * nlay] = toa;
+                if (wr && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
                     if (act && lo + k < hi) {
                         if (NONISO) {
                             F = tiny_to_abs(a[0][k] * F + cc[0][k]);
                             Fcd_reg[k] = F;
-                            if (wr) Fc_down[colc + (size_t)ncol * (lo + k)] = F;
+                            if (wr) Fc_down[wgo + colc + (size_t)ncol * (lo + k)] = F;
                             F = tiny_to_abs(a[1][k] * F + cc[1][k]);
                         } else {
                             F = tiny_to_abs(a[0][k] * F + cc[0][k]);
                         }
                         Fd_reg[k] = F;
-                        if (wr) F_down[colc + (size_t)ncol * (lo + k)] = F;
+                        if (wr) F_down[wgo + colc + (size_t)ncol * (lo + k)] = F;
                     }
                 }
                 // the flux at my top interface as WALKED (and stored) by the lane above: every flux consumed
@@ -349,7 +359,7 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                 const double Ftop = sc.A * fu0 + sc.B;                       // flux leaving my chunk (interface hi)
                 F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);               // = flux entering it (interface lo)
                 if (sl == 0) F = fu0;
-                if (wr && sl == 0) F_up[colc] = fu0;
+                if (wr && sl == 0) F_up[wgo + colc] = fu0;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
                     if (act && lo + k < hi) {
@@ -358,10 +368,10 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                             // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
                             F = a[1][k] * F + cc[1][k];
                             Fcu_reg[k] = F;
-                            if (wr) Fc_up[colc + (size_t)ncol * (lo + k)] = F;
+                            if (wr) Fc_up[wgo + colc + (size_t)ncol * (lo + k)] = F;
                         }
                         F = tiny_to_abs(a[0][k] * F + cc[0][k]);
-                        if (wr) F_up[colc + (size_t)ncol * (lo + k + 1)] = F;
+                        if (wr) F_up[wgo + colc + (size_t)ncol * (lo + k + 1)] = F;
                     }
                 }
                 // next pass: the flux at my bottom interface as walked by the lane below
@@ -389,7 +399,9 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     s.colpitch = pitch;
     const size_t smem = ((size_t)(NONISO ? 10 : 5) * NCOLS * pitch + 4 * NCOLS) * sizeof(double);
     if (nchunk > LPC || smem > 227 * 1024) return -1;
-    const int ntile = (ncol + NCOLS - 1) / NCOLS;
+    const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
+    s.nbatch = ctx->batch.nbatch;
+    s.done = ctx->batch.nbatch > 1 ? ctx->batch.done : nullptr;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
     if (per_sm < 1) per_sm = 1;
@@ -436,7 +448,7 @@ int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double
                      const double* Gm, const double* albedo, const double* g0tot, double g_0, double Rstar,
                      double a, int nint, int nbin, double f_factor, double mu_star, int ny, double epsi,
                      int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
-    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0};
+    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0, 1, nullptr};
     CpNonisoCoef c{w_0, nullptr, nullptr, nullptr, nullptr, nullptr, M, nullptr, N, nullptr, P, nullptr, Gp, nullptr, Gm, nullptr};
     return dispatch_wp<false>(ctx, F_down, F_up, nullptr, nullptr, F_dir, nullptr, planck, nullptr, c, albedo, g0tot,
                               nullptr, s, nbin * ny);
@@ -449,7 +461,7 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
     CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds,
-                scat_corr, npass, 0, 0};
+                scat_corr, npass, 0, 0, 1, nullptr};
     return dispatch_wp<true>(ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo,
                              g0_lay, g0_int, s, nbin * ny);
 }

@@ -26,6 +26,11 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     const int i = blockIdx.y;
     const int x0 = blockIdx.x * xb;
     const int nx = min(xb, nbin - x0);
+    {   // batch (blockIdx.z = atmosphere): [i][x][y] and [i][x] arrays both hold gridDim.y = ninterface rows
+        const size_t wg = (size_t)blockIdx.z * gridDim.y * nbin * ny, bd = (size_t)blockIdx.z * gridDim.y * nbin;
+        F_down_wg += wg; F_up_wg += wg; F_dir_wg += wg;
+        F_down_band += bd; F_up_band += bd; F_dir_band += bd;
+    }
     const size_t base = ((size_t)i * nbin + x0) * ny;
     const int n = nx * ny;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
@@ -70,6 +75,11 @@ k_total_integrate(const double* __restrict__ deltalambda, const double* __restri
                   int nbin) {
     __shared__ double red[IF_THREADS];
     const int i = blockIdx.x;
+    {   // batch (blockIdx.y = atmosphere); gridDim.x = ninterface
+        const size_t bd = (size_t)blockIdx.y * gridDim.x * nbin, tt = (size_t)blockIdx.y * gridDim.x;
+        F_down_band += bd; F_up_band += bd; F_dir_band += bd;
+        F_down_tot += tt; F_up_tot += tt; F_net += tt;
+    }
     double up = 0.0, dn = 0.0;
     for (int x = threadIdx.x; x < nbin; x += blockDim.x) {
         const size_t o = (size_t)i * nbin + x;
@@ -93,6 +103,8 @@ k_total_integrate(const double* __restrict__ deltalambda, const double* __restri
 struct TempScalars {
     int itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, conv;
     double f_factor, g, physical_tstep, local_limit, F_intern;
+    const int* done;        // batch: atmospheres that have converged are left untouched
+    const double* g_batch;  // batch: per-atmosphere gravity
 };
 
 __global__ void __launch_bounds__(256)
@@ -104,6 +116,20 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
             double* __restrict__ F_smooth, double* __restrict__ F_smooth_sum,
             const double* __restrict__ c_p_lay, const double* __restrict__ mmm_lay, TempScalars s) {
     const int nl = s.numlayers;
+    if (gridDim.x > 1 || s.done != nullptr) {  // batch (blockIdx.x = atmosphere)
+        const size_t a = blockIdx.x;
+        if (s.done != nullptr && s.done[a] != 0) return;
+        if (s.g_batch != nullptr) s.g = s.g_batch[a];
+        const size_t v1 = a * (nl + 1), v0 = a * nl;  // vectors with nlayer + 1 / nlayer entries
+        if (F_down_tot) F_down_tot += v1;
+        F_net += v1; tlay += v1; pint += v1; T_store += v1; prefactor += v1;
+        if (abrt) abrt += v1;
+        if (marked_red) marked_red += v1;
+        F_net_diff += v0; play += v0; F_add_heat_lay += v0; F_smooth += v0; F_smooth_sum += v0;
+        if (F_add_heat_sum) F_add_heat_sum += v0;
+        if (c_p_lay) c_p_lay += v0;
+        if (mmm_lay) mmm_lay += v0;
+    }
     // phase 1: flux divergence and smoothing force, from the OLD temperatures
     for (int i = threadIdx.x; i < nl; i += blockDim.x) {
         F_net_diff[i] = F_net[i] - F_net[i + 1] + F_add_heat_lay[i];
@@ -196,8 +222,10 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
 // conv_temp_iter's smoothing branch differs slightly (no i > 0 guard in the reference, K:2808, which
 // reads tlay[-1]); the guarded form is used for both.
 
-__global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict__ out) {
+__global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict__ out, int* __restrict__ done) {
     __shared__ int red[256];
+    abrt += (size_t)blockIdx.x * n;  // batch (blockIdx.x = atmosphere)
+    out += blockIdx.x;
     int a = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) a += abrt[i];
     red[threadIdx.x] = a;
@@ -206,7 +234,10 @@ __global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict
         if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[0] = red[0];
+    if (threadIdx.x == 0) {
+        out[0] = red[0];
+        if (done != nullptr && red[0] == n) done[blockIdx.x] = 1;  // latched: see helios_ctx_set_batch
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -359,12 +390,13 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
         return HELIOS_ERR_ARG;
     }
     const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
-    dim3 grid(ceil_div(nbin, xb), numinterfaces);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
+    dim3 grid(ceil_div(nbin, xb), numinterfaces, ctx->batch.nbatch);
     k_band_integrate<<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band,
                                                               F_up_band, F_dir_band, gauss_weight, nbin,
                                                               ny, xb);
     HLAUNCHED(ctx);
-    k_total_integrate<<<numinterfaces, IF_THREADS, 0, ctx->stream>>>(
+    k_total_integrate<<<dim3(numinterfaces, ctx->batch.nbatch), IF_THREADS, 0, ctx->stream>>>(
         deltalambda, F_down_band, F_up_band, F_dir_band, F_down_tot, F_up_tot, F_net, nbin);
     HLAUNCHED(ctx);
     return HELIOS_OK;
@@ -385,9 +417,12 @@ int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double
          F_add_heat_lay && F_add_heat_sum && F_smooth && F_smooth_sum);
     HARG(physical_tstep == 0 || (c_p_lay != nullptr && meanmolmass_lay != nullptr));
     HARG(numlayers > 1 && adapt_interval > 0);
+    HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer);
+    const bool batched = ctx->batch.nbatch > 1;
     TempScalars s{itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, 0,
-                  f_factor, g, physical_tstep, local_limit, F_intern};
-    k_temp_iter<<<1, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
+                  f_factor, g, physical_tstep, local_limit, F_intern,
+                  batched ? ctx->batch.done : nullptr, batched ? ctx->batch.g : nullptr};
+    k_temp_iter<<<ctx->batch.nbatch, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
                                             deltat_prefactor, nullptr, F_add_heat_lay, F_add_heat_sum,
                                             F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay, s);
     HLAUNCHED(ctx);
@@ -405,7 +440,9 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
     HARG(F_net && F_net_diff && tlay && play && pint && T_store && deltat_prefactor && marked_red &&
          F_add_heat_lay && F_smooth && F_smooth_sum);
     HARG(numlayers > 1 && adapt_interval > 0);
-    TempScalars s{itervalue, 0, numlayers, adapt_interval, smooth, 0, 0, 0, 1, 0.0, 0.0, 0.0, 0.0, F_intern};
+    HNOBATCH(ctx);
+    TempScalars s{itervalue, 0, numlayers, adapt_interval, smooth, 0, 0, 0, 1, 0.0, 0.0, 0.0, 0.0, F_intern,
+                  nullptr, nullptr};
     k_temp_iter<<<1, 256, 0, ctx->stream>>>(nullptr, F_net, F_net_diff, tlay, play, pint, nullptr, T_store,
                                             deltat_prefactor, marked_red, F_add_heat_lay, nullptr, F_smooth,
                                             F_smooth_sum, nullptr, nullptr, s);
@@ -416,7 +453,9 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
 int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev) {
     HCTX(ctx);
     HARG(abrt && sum_dev && n > 0);
-    k_abort_sum<<<1, 256, 0, ctx->stream>>>(abrt, n, sum_dev);
+    HBATCHDIMS(ctx, n == ctx->batch.nlayer + 1);
+    k_abort_sum<<<ctx->batch.nbatch, 256, 0, ctx->stream>>>(abrt, n, sum_dev,
+                                                            ctx->batch.nbatch > 1 ? ctx->batch.done : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -426,6 +465,7 @@ int helios_integrate_optdepth_transmission_iso(helios_ctx* ctx, const double* tr
                                                double* delta_tau_band, const double* gauss_weight,
                                                int nbin, int nlayer, int ny) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(trans_wg && trans_band && delta_tau_wg && delta_tau_band && gauss_weight && nbin > 0 && nlayer > 0 && ny > 0);
     const long long n = (long long)nbin * nlayer;
     k_optdepth_trans<false><<<ceil_div(n, 128), 128, 0, ctx->stream>>>(
@@ -441,6 +481,7 @@ int helios_integrate_optdepth_transmission_noniso(
     const double* gauss_weight, double* delta_tau_all_clouds, const double* delta_tau_all_clouds_upper,
     const double* delta_tau_all_clouds_lower, int nbin, int nlayer, int ny) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(trans_wg_upper && trans_wg_lower && trans_band && delta_tau_wg_upper && delta_tau_wg_lower &&
          delta_tau_band && gauss_weight && delta_tau_all_clouds && delta_tau_all_clouds_upper &&
          delta_tau_all_clouds_lower && nbin > 0 && nlayer > 0 && ny > 0);
@@ -457,6 +498,7 @@ int helios_calc_contr_func_iso(helios_ctx* ctx, const double* trans_wg, double* 
                                double* contr_func_band, const double* gauss_weight,
                                const double* planckband_lay, double epsi, int nbin, int nlayer, int ny) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(trans_wg && trans_weight_band && contr_func_band && gauss_weight && planckband_lay && nbin > 0 &&
          nlayer > 0 && ny > 0);
     k_contr_func<false><<<ceil_div(nbin, 64), 64, 0, ctx->stream>>>(
@@ -471,6 +513,7 @@ int helios_calc_contr_func_noniso(helios_ctx* ctx, const double* trans_wg_upper,
                                   double* contr_func_band, const double* gauss_weight,
                                   const double* planckband_lay, double epsi, int nbin, int nlayer, int ny) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(trans_wg_upper && trans_wg_lower && trans_weight_band && contr_func_band && gauss_weight &&
          planckband_lay && nbin > 0 && nlayer > 0 && ny > 0);
     k_contr_func<true><<<ceil_div(nbin, 64), 64, 0, ctx->stream>>>(
@@ -488,6 +531,7 @@ int helios_calc_mean_opacities(helios_ctx* ctx, double* planck_opac_T_pl, double
                                const double* T_lay, const double* gauss_weight, const double* gauss_y,
                                double* opac_band_lay, int nlayer, int nbin, int ny, double T_star) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(planck_opac_T_pl && ross_opac_T_pl && planck_opac_T_star && ross_opac_T_star && opac_wg_lay &&
          abs_cross_all_clouds_lay && meanmolmass_lay && planckband_lay && opac_interwave && opac_deltawave &&
          T_lay && gauss_weight && gauss_y && opac_band_lay && nlayer > 0 && nbin > 0 && ny > 0);
@@ -503,6 +547,7 @@ int helios_integrate_beamflux(helios_ctx* ctx, double* F_dir_tot, const double* 
                               const double* deltalambda, const double* gauss_weight, int nbin,
                               int numinterfaces) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     (void)gauss_weight;
     HARG(F_dir_tot && F_dir_band && deltalambda && nbin > 0 && numinterfaces > 0);
     k_integrate_beamflux<<<numinterfaces, IF_THREADS, 0, ctx->stream>>>(F_dir_tot, F_dir_band, deltalambda,

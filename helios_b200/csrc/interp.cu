@@ -83,6 +83,8 @@ __global__ void k_inc_energy_scale(double* __restrict__ planck_grid, double* __r
 __global__ void k_temp_inter(const double* __restrict__ tlay, double* __restrict__ tint, int nint) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nint) return;
+    tlay += (size_t)blockIdx.y * nint;  // batch: T_lay has nlayer + 1 = nint entries per atmosphere
+    tint += (size_t)blockIdx.y * nint;
     if (i == 0) tint[i] = tlay[i] - 0.5 * (tlay[i + 1] - tlay[i]);
     else if (i == nint - 1) tint[i] = tlay[i - 1] + 0.5 * (tlay[i - 1] - tlay[i - 2]);
     else tint[i] = tlay[i - 1] + 0.5 * (tlay[i] - tlay[i - 1]);
@@ -97,8 +99,16 @@ __global__ void k_temp_inter(const double* __restrict__ tlay, double* __restrict
 __global__ void __launch_bounds__(256)
 k_planck_interpol(const double* __restrict__ temp, double* __restrict__ out,
                   const double* __restrict__ planck_grid, const double* __restrict__ starflux,
-                  int realstar, int mode, int nl, int nrows, int nwave, int dim, int step) {
+                  int realstar, int mode, int nl, int nrows, int nwave, int dim, int step,
+                  const double* __restrict__ planck_star) {
     __shared__ double tile[32][33];
+    {   // batch (blockIdx.z = atmosphere): T_lay holds nl + 1 values, T_int nrows
+        const size_t b = blockIdx.z;
+        temp += b * (size_t)(mode == 0 ? nl + 1 : nrows);
+        out += b * (size_t)nrows * nwave;
+        if (starflux) starflux += b * (size_t)nwave;
+        if (planck_star) planck_star += b * (size_t)nwave;
+    }
     const int x0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     for (int r = ty; r < 32; r += 8) {
@@ -106,7 +116,8 @@ k_planck_interpol(const double* __restrict__ temp, double* __restrict__ out,
         double v = 0.0;
         if (i < nrows && x < nwave) {
             if (mode == 0 && i == nl) {
-                v = realstar == 1 ? starflux[x] / hc::PI : planck_grid[x + (size_t)dim * nwave];
+                v = realstar == 1 ? starflux[x] / hc::PI
+                                  : (planck_star ? planck_star[x] : planck_grid[x + (size_t)dim * nwave]);
             } else {
                 const double Ti = (mode == 0 && i == nl + 1) ? temp[nl] : temp[i];
                 double t = (Ti - 1.0) / step;
@@ -142,9 +153,13 @@ struct PTBox {
 // clamp_mode 0: [0.001, n-1.001] (K:549, 556);  1: [0, n-1] (K:3233, 3238)
 __global__ void k_pt_prep(const double* __restrict__ temp, const double* __restrict__ press,
                           const double* __restrict__ gtemp, const double* __restrict__ gpress, int ntemp,
-                          int npress, int n, int clamp_mode, int log_t, PTBox* __restrict__ box) {
+                          int npress, int n, int clamp_mode, int log_t, PTBox* __restrict__ box, int tstride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // batch (blockIdx.y = atmosphere): temperatures are tstride apart (T_lay: nlayer + 1), pressures n
+    temp += (size_t)blockIdx.y * tstride;
+    press += (size_t)blockIdx.y * n;
+    box += (size_t)blockIdx.y * n;
     double t;
     if (log_t) {
         const double dT = (log10(gtemp[ntemp - 1]) - log10(gtemp[0])) / (ntemp - 1.0);
@@ -187,8 +202,20 @@ __device__ __forceinline__ double bilin4(double dd, double ud, double du, double
 __global__ void __launch_bounds__(256)
 k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, double* __restrict__ out,
             int rowlen, const double* __restrict__ table2, double* __restrict__ out2, int rowlen2,
-            int npress) {
+            int npress, int n, const int* __restrict__ table_index, size_t tstride, size_t tstride2,
+            size_t ostride, size_t ostride2) {
     const int i = blockIdx.y;
+    {   // batch (blockIdx.z = atmosphere)
+        const size_t a = blockIdx.z;
+        const size_t which = table_index ? (size_t)table_index[a] : 0;
+        box += a * (size_t)n;
+        table += which * tstride;
+        out += a * ostride;
+        if (table2 != nullptr) {
+            table2 += which * tstride2;
+            out2 += a * ostride2;
+        }
+    }
     const PTBox b = box[i];
     const size_t r_dd = (size_t)b.pdown + (size_t)npress * b.tdown;
     const size_t r_ud = (size_t)b.pup + (size_t)npress * b.tdown;
@@ -218,9 +245,14 @@ k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, dou
 __global__ void k_pt_scalar(const double* __restrict__ temp, const double* __restrict__ press,
                             const double* __restrict__ gtemp, const double* __restrict__ gpress, int ntemp,
                             int npress, int n, int log_t, const double* __restrict__ tab,
-                            double* __restrict__ out) {
+                            double* __restrict__ out, int tstride, const int* __restrict__ table_index,
+                            size_t tabstride) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    temp += (size_t)blockIdx.y * tstride;  // batch (blockIdx.y = atmosphere)
+    press += (size_t)blockIdx.y * n;
+    out += (size_t)blockIdx.y * n;
+    if (table_index) tab += (size_t)table_index[blockIdx.y] * tabstride;
     double t;
     if (log_t) {
         const double dT = (log10(gtemp[ntemp - 1]) - log10(gtemp[0])) / (ntemp - 1.0);
@@ -248,7 +280,8 @@ extern "C" {
 int helios_plancktable(helios_ctx* ctx, double* planck_grid, const double* lambda_edge,
                        const double* deltalambda, int nwave, double Tstar, int dim, int step) {
     HCTX(ctx);
-    HARG(planck_grid && lambda_edge && deltalambda && nwave > 0 && dim > 0 && step > 0);
+    HARG(planck_grid && lambda_edge && deltalambda && nwave > 0 && dim >= 0 && step > 0);
+    HNOBATCH(ctx);
     const long long total = (long long)(dim + 1) * nwave;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ctx->num_sms * 64;
@@ -263,8 +296,9 @@ int helios_corr_inc_energy(helios_ctx* ctx, double* planck_grid, double* starflu
                            const double* deltalambda, int realstar, int nwave, double Tstar, int dim,
                            double* corr_factor_host) {
     HCTX(ctx);
-    HARG(planck_grid && deltalambda && nwave > 0 && dim > 0);
+    HARG(planck_grid && deltalambda && nwave > 0 && dim >= 0);
     HARG(realstar == 0 || starflux != nullptr);
+    HNOBATCH(ctx);
     double* scratch = nullptr;
     int rc = helios_ctx_scratch(ctx, sizeof(double), &scratch);
     if (rc) return rc;
@@ -285,7 +319,9 @@ int helios_corr_inc_energy(helios_ctx* ctx, double* planck_grid, double* starflu
 int helios_temp_inter(helios_ctx* ctx, const double* tlay, double* tint, int numinterfaces) {
     HCTX(ctx);
     HARG(tlay && tint && numinterfaces >= 3);
-    k_temp_inter<<<ceil_div(numinterfaces, 128), 128, 0, ctx->stream>>>(tlay, tint, numinterfaces);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint());
+    k_temp_inter<<<dim3(ceil_div(numinterfaces, 128), ctx->batch.nbatch), 128, 0, ctx->stream>>>(tlay, tint,
+                                                                                                  numinterfaces);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -297,9 +333,11 @@ int helios_planck_interpol_layer(helios_ctx* ctx, const double* temp, double* pl
     HARG(temp && planckband_lay && planck_grid && numlayers > 0 && nwave > 0 && dim > 1 && step > 0);
     HARG(realstar == 0 || starflux != nullptr);
     const int nrows = numlayers + 2;
-    dim3 grid(ceil_div(nwave, 32), ceil_div(nrows, 32));
+    HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer && nwave == ctx->batch.nbin);
+    dim3 grid(ceil_div(nwave, 32), ceil_div(nrows, 32), ctx->batch.nbatch);
     k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_lay, planck_grid, starflux,
-                                                     realstar, 0, numlayers, nrows, nwave, dim, step);
+                                                     realstar, 0, numlayers, nrows, nwave, dim, step,
+                                                     ctx->batch.nbatch > 1 ? ctx->batch.planck_star : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -309,9 +347,10 @@ int helios_planck_interpol_interface(helios_ctx* ctx, const double* temp, double
                                      int step) {
     HCTX(ctx);
     HARG(temp && planckband_int && planck_grid && numinterfaces > 0 && nwave > 0 && dim > 1 && step > 0);
-    dim3 grid(ceil_div(nwave, 32), ceil_div(numinterfaces, 32));
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nwave == ctx->batch.nbin);
+    dim3 grid(ceil_div(nwave, 32), ceil_div(numinterfaces, 32), ctx->batch.nbatch);
     k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_int, planck_grid, nullptr, 0, 1, 0,
-                                                     numinterfaces, nwave, dim, step);
+                                                     numinterfaces, nwave, dim, step, nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -320,19 +359,27 @@ static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gt
                            const double* gpress, const double* table, double* out, int rowlen,
                            const double* table2, double* out2, int rowlen2, int npress, int ntemp, int n,
                            int clamp_mode) {
+    const BatchDesc& bd = ctx->batch;
+    const int nb = bd.nbatch;
     double* scratch = nullptr;
-    int rc = helios_ctx_scratch(ctx, sizeof(PTBox) * (size_t)n + 64, &scratch);
+    int rc = helios_ctx_scratch(ctx, sizeof(PTBox) * (size_t)n * nb + 64, &scratch);
     if (rc) return rc;
     // keep clear of the first 64 bytes, which small reductions use
     PTBox* box = reinterpret_cast<PTBox*>(reinterpret_cast<char*>(scratch) + 64);
-    k_pt_prep<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
-                                                         clamp_mode, 0, box);
+    // batch: T_lay carries the surface value behind the nlayer layer values, T_int has exactly n entries
+    const int tstride = (nb > 1 && n == bd.nlayer) ? n + 1 : n;
+    k_pt_prep<<<dim3(ceil_div(n, 128), nb), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
+                                                                   clamp_mode, 0, box, tstride);
     HLAUNCHED(ctx);
     int bx = ceil_div(rowlen, 256);
-    const int cap = (ctx->num_sms * 8 + n - 1) / n;
+    const int cap = (ctx->num_sms * 8 + n * nb - 1) / (n * nb);
     if (bx > cap) bx = cap > 0 ? cap : 1;
-    dim3 grid(bx, n);
-    k_pt_gather<<<grid, 256, 0, ctx->stream>>>(box, table, out, rowlen, table2, out2, rowlen2, npress);
+    dim3 grid(bx, n, nb);
+    // per-atmosphere output strides: every [i][x][y] array is allocated with ninterface rows (Q:407), the
+    // [i][x] cross-section arrays with exactly n rows
+    k_pt_gather<<<grid, 256, 0, ctx->stream>>>(box, table, out, rowlen, table2, out2, rowlen2, npress, n,
+                                               nb > 1 ? bd.table_index : nullptr, bd.ktable_stride, bd.cross_stride,
+                                               nb > 1 ? bd.wg() : 0, (size_t)n * rowlen2);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -344,6 +391,8 @@ int helios_opac_interpol(helios_ctx* ctx, const double* temp, const double* opac
     HCTX(ctx);
     HARG(temp && opactemp && press && opacpress && ktable && opac && crosstable && scat_cross);
     HARG(npress > 1 && ntemp > 1 && ny > 0 && nbin > 0 && nlay_or_nint > 0);
+    HBATCHDIMS(ctx, ny == ctx->batch.ny && nbin == ctx->batch.nbin &&
+                    (nlay_or_nint == ctx->batch.nlayer || nlay_or_nint == ctx->batch.nint()));
     return pt_table_interp(ctx, temp, opactemp, press, opacpress, ktable, opac, ny * nbin, crosstable,
                            scat_cross, nbin, npress, ntemp, nlay_or_nint, 0);
 }
@@ -355,15 +404,22 @@ int helios_opac_species_interpol(helios_ctx* ctx, const double* temp, const doub
     HCTX(ctx);
     HARG(temp && opactemp && press && opacpress && opac_opacity_pretab && opac_spec_wg);
     HARG(npress > 1 && ntemp > 1 && ny > 0 && nbin > 0 && nlay_or_nint > 0);
+    HNOBATCH(ctx);
     return pt_table_interp(ctx, temp, opactemp, press, opacpress, opac_opacity_pretab, opac_spec_wg,
                            ny * nbin, nullptr, nullptr, 0, npress, ntemp, nlay_or_nint, 1);
 }
 
 static int pt_scalar(helios_ctx* ctx, const double* temp, const double* gtemp, const double* press,
                      const double* gpress, double* out, const double* tab, int npress, int ntemp, int n,
-                     int log_t) {
-    k_pt_scalar<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
-                                                           log_t, tab, out);
+                     int log_t, bool batched = false) {
+    const BatchDesc& bd = ctx->batch;
+    if (!batched) HNOBATCH(ctx);
+    const int nb = bd.nbatch;
+    const int tstride = (nb > 1 && n == bd.nlayer) ? n + 1 : n;
+    k_pt_scalar<<<dim3(ceil_div(n, 128), nb), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
+                                                                     log_t, tab, out, tstride,
+                                                                     nb > 1 ? bd.table_index : nullptr,
+                                                                     bd.mmass_stride);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -376,8 +432,9 @@ int helios_meanmolmass_interpol(helios_ctx* ctx, const double* temp, const doubl
                                 const double* opacpress, int npress, int ntemp, int ninterface) {
     HCTX(ctx);
     SCALAR_ARGS_OK(temp, opactemp, press, opacpress, meanmolmass, opac_meanmass, npress, ntemp, ninterface);
+    HBATCHDIMS(ctx, ninterface == ctx->batch.nlayer || ninterface == ctx->batch.nint());
     return pt_scalar(ctx, temp, opactemp, press, opacpress, meanmolmass, opac_meanmass, npress, ntemp,
-                     ninterface, 0);
+                     ninterface, 0, true);
 }
 
 int helios_kappa_interpol(helios_ctx* ctx, const double* temp, const double* entr_temp,

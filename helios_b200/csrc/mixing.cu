@@ -230,6 +230,7 @@ int helios_add_to_mixed_opac(helios_ctx* ctx, const double* vmr, const double* o
                              const double* gauss_y, double mass_spec, int s, int ro_method, int ny,
                              int nbin, int nlay_or_nint) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(vmr && opac_spec && opac_wg && meanmolmass && gauss_weight && gauss_y);
     HARG(ny > 0 && nbin > 0 && nlay_or_nint > 0 && s >= 0);
     if (ro_method != 0 && s != 0 && ny != 1 && ny != RO_NY) {
@@ -249,6 +250,7 @@ int helios_calc_h2o_scat(helios_ctx* ctx, const double* temp, const double* pres
                          double* scat_cross, const double* vmr, double mass_h2o, int nbin,
                          int nlay_or_nint) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(temp && press && wave && scat_cross && vmr && nbin > 0 && nlay_or_nint > 0);
     const long long n = (long long)nbin * nlay_or_nint;
     k_calc_h2o_scat<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(temp, press, wave, scat_cross, vmr,
@@ -260,6 +262,7 @@ int helios_calc_h2o_scat(helios_ctx* ctx, const double* temp, const double* pres
 int helios_add_to_mixed_scat(helios_ctx* ctx, const double* vmr, const double* scat_cross_spec,
                              double* scat_cross, int nbin, int nlay_or_nint) {
     HCTX(ctx);
+    HNOBATCH(ctx);
     HARG(vmr && scat_cross_spec && scat_cross && nbin > 0 && nlay_or_nint > 0);
     const long long n = (long long)nbin * nlay_or_nint;
     k_add_to_mixed_scat<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(vmr, scat_cross_spec, scat_cross, nbin,
@@ -274,7 +277,9 @@ int helios_calc_total_g_0_of_gas_and_clouds(helios_ctx* ctx, const double* scat_
                                             double g_0, int nbin, int nlay_or_nint) {
     HCTX(ctx);
     HARG(scat_cross && g_0_all_clouds && scat_cross_all_clouds && g_0_tot && nbin > 0 && nlay_or_nint > 0);
-    const long long n = (long long)nbin * nlay_or_nint;
+    // element-wise over [i][x] arrays that all have exactly nlay_or_nint rows per atmosphere: a batch is
+    // simply nbatch times as many elements
+    const long long n = (long long)nbin * nlay_or_nint * ctx->batch.nbatch;
     k_total_g0<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(scat_cross, g_0_all_clouds,
                                                           scat_cross_all_clouds, g_0_tot, g_0, n);
     HLAUNCHED(ctx);

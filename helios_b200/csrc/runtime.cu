@@ -73,6 +73,7 @@ int helios_ctx_destroy(helios_ctx* ctx) {
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     ctx->allocs.clear();
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->batch.done) cudaFree(ctx->batch.done);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return HELIOS_OK;
@@ -110,6 +111,51 @@ int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count) {
     HCTX(ctx);
     HARG(count != nullptr);
     *count = ctx->launches;
+    return HELIOS_OK;
+}
+
+int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int ny, const int* table_index,
+                         size_t ktable_stride, size_t crosstable_stride, size_t meanmass_stride, const double* g,
+                         const double* planck_star) {
+    HCTX(ctx);
+    HARG(nbatch >= 1);
+    HCUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->batch.done) {
+        cudaFree(ctx->batch.done);
+        ctx->batch.done = nullptr;
+    }
+    ctx->batch = BatchDesc();
+    if (nbatch == 1) return HELIOS_OK;
+    HARG(nlayer > 1 && nbin > 0 && ny > 0);
+    BatchDesc b;
+    b.nbatch = nbatch;
+    b.nlayer = nlayer;
+    b.nbin = nbin;
+    b.ny = ny;
+    b.table_index = table_index;
+    b.ktable_stride = ktable_stride;
+    b.cross_stride = crosstable_stride;
+    b.mmass_stride = meanmass_stride;
+    b.g = g;
+    b.planck_star = planck_star;
+    HCUDA(cudaMalloc((void**)&b.done, sizeof(int) * (size_t)nbatch));
+    HCUDA(cudaMemset(b.done, 0, sizeof(int) * (size_t)nbatch));
+    ctx->batch = b;
+    return HELIOS_OK;
+}
+
+int helios_ctx_batch_done(helios_ctx* ctx, int* done_host, int reset) {
+    HCTX(ctx);
+    if (ctx->batch.nbatch <= 1) {
+        helios_set_error("helios_ctx_batch_done: not in batch mode");
+        return HELIOS_ERR_STATE;
+    }
+    if (reset) HCUDA(cudaMemsetAsync(ctx->batch.done, 0, sizeof(int) * (size_t)ctx->batch.nbatch, ctx->stream));
+    if (done_host) {
+        HCUDA(cudaMemcpyAsync(done_host, ctx->batch.done, sizeof(int) * (size_t)ctx->batch.nbatch,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+        HCUDA(cudaStreamSynchronize(ctx->stream));
+    }
     return HELIOS_OK;
 }
 

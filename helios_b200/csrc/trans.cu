@@ -6,6 +6,7 @@ struct TransScalars {
     double g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition;
     int scat, nbin, ny, nlayer, clouds, scat_corr, debug;
     double inv_eps2, inv_mu2;  // pow(epsi, -2.0), pow(mu_star, -2.0): see trans_constants()
+    int nbatch;                // atmospheres per launch (helios_ctx_set_batch), 1 otherwise
 };
 
 struct CellCoeffs {
@@ -91,20 +92,25 @@ k_calc_trans_iso(double* __restrict__ trans_wg, double* __restrict__ delta_tau_w
                  double* __restrict__ w_0, const double* __restrict__ g_0_tot_lay,
                  int* __restrict__ scat_trigger, TransScalars s) {
     const int ncol = s.nbin * s.ny;
-    const long long total = (long long)ncol * s.nlayer;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e / ncol);
-        const int col = (int)(e - (long long)i * ncol);
+    const long long per_atm = (long long)ncol * s.nlayer;
+    const long long total = per_atm * s.nbatch;
+    for (long long ee = blockIdx.x * (long long)blockDim.x + threadIdx.x; ee < total;
+         ee += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(ee / per_atm);                       // atmosphere (0 outside batch mode)
+        const long long el = ee - (long long)a * per_atm;
+        const int i = (int)(el / ncol);
+        const int col = (int)(el - (long long)i * ncol);
         const int x = col / s.ny;
         const int y = col - x * s.ny;
-        const size_t b = (size_t)x + (size_t)s.nbin * i;
+        const size_t e = (size_t)a * ncol * (s.nlayer + 1) + el;  // [i][x][y] arrays hold ninterface rows (Q:407)
+        const size_t b = (size_t)a * s.nbin * s.nlayer + (size_t)x + (size_t)s.nbin * i;
+        const size_t li = (size_t)a * s.nlayer + i;
         const double g0 = s.clouds == 1 ? g_0_tot_lay[b] : s.g_0;
         const double ray = s.scat == 1 ? scat_cross_lay[b] : 0.0;
         const double csc = s.scat == 1 ? scat_cross_cl[b] : 0.0;
         const double cab = abs_cross_cl[b];
-        const double mmm = meanmolmass_lay[i];
-        const double dcol = delta_colmass[i];
+        const double mmm = meanmolmass_lay[li];
+        const double dcol = delta_colmass[li];
         const double dtc = dcol * (cab + csc) / mmm;
         if (y == 0) delta_tau_all_clouds[b] = dtc;
         const CellCoeffs c = cell_coeffs(ray, csc, cab, opac_wg_lay[e], mmm, dcol, dtc, g0, s);
@@ -116,7 +122,7 @@ k_calc_trans_iso(double* __restrict__ trans_wg, double* __restrict__ delta_tau_w
         P_term[e] = c.P;
         G_plus[e] = c.Gp;
         G_minus[e] = c.Gm;
-        if (c.w0 > s.w_0_scat_limit) scat_trigger[col] = 1;  // benign race, as K:1102
+        if (c.w0 > s.w_0_scat_limit) scat_trigger[(size_t)a * ncol + col] = 1;  // benign race, as K:1102
     }
 }
 
@@ -132,42 +138,48 @@ struct NonisoIn {
 __global__ void __launch_bounds__(256)
 k_calc_trans_noniso(NonisoOut o, NonisoIn in, int* __restrict__ scat_trigger, TransScalars s) {
     const int ncol = s.nbin * s.ny;
-    const long long total = (long long)ncol * s.nlayer;
-    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
-         e += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(e / ncol);
-        const int col = (int)(e - (long long)i * ncol);
+    const long long per_atm = (long long)ncol * s.nlayer;
+    const long long total = per_atm * s.nbatch;
+    for (long long ee = blockIdx.x * (long long)blockDim.x + threadIdx.x; ee < total;
+         ee += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(ee / per_atm);                       // atmosphere (0 outside batch mode)
+        const long long el = ee - (long long)a * per_atm;
+        const int i = (int)(el / ncol);
+        const int col = (int)(el - (long long)i * ncol);
         const int x = col / s.ny;
         const int y = col - x * s.ny;
-        const size_t b = (size_t)x + (size_t)s.nbin * i;   // layer i / interface i
-        const size_t bu = b + s.nbin;                       // interface i+1
+        const size_t e = (size_t)a * ncol * (s.nlayer + 1) + el;                         // [i][x][y] arrays
+        const size_t b = (size_t)a * s.nbin * s.nlayer + (size_t)x + (size_t)s.nbin * i;        // [layer][x]
+        const size_t bi = (size_t)a * s.nbin * (s.nlayer + 1) + (size_t)x + (size_t)s.nbin * i;  // [interface][x]
+        const size_t bu = bi + s.nbin;                                                           // interface i+1
+        const size_t li = (size_t)a * s.nlayer + i, ii = (size_t)a * (s.nlayer + 1) + i;
         double g0_up = s.g_0, g0_low = s.g_0;
         if (s.clouds == 1) {
             g0_up = (in.g0_lay[b] + in.g0_int[bu]) / 2.0;
-            g0_low = (in.g0_int[b] + in.g0_lay[b]) / 2.0;
+            g0_low = (in.g0_int[bi] + in.g0_lay[b]) / 2.0;
         }
         double ray_up = 0.0, ray_low = 0.0, csc_up = 0.0, csc_low = 0.0;
         if (s.scat == 1) {
             ray_up = (in.scat_lay[b] + in.scat_int[bu]) / 2.0;
-            ray_low = (in.scat_int[b] + in.scat_lay[b]) / 2.0;
+            ray_low = (in.scat_int[bi] + in.scat_lay[b]) / 2.0;
             csc_up = (in.csc_lay[b] + in.csc_int[bu]) / 2.0;
-            csc_low = (in.csc_int[b] + in.csc_lay[b]) / 2.0;
+            csc_low = (in.csc_int[bi] + in.csc_lay[b]) / 2.0;
         }
         const double cab_up = (in.cab_lay[b] + in.cab_int[bu]) / 2.0;
-        const double cab_low = (in.cab_int[b] + in.cab_lay[b]) / 2.0;
+        const double cab_low = (in.cab_int[bi] + in.cab_lay[b]) / 2.0;
         const double k_lay = in.opac_lay[e];
         const double opac_up = (k_lay + in.opac_int[e + ncol]) / 2.0;
         const double opac_low = (in.opac_int[e] + k_lay) / 2.0;
-        const double mmm_up = (in.mmm_lay[i] + in.mmm_int[i + 1]) / 2.0;
-        const double mmm_low = (in.mmm_int[i] + in.mmm_lay[i]) / 2.0;
-        const double dtc_up = in.dcol_u[i] * (cab_up + csc_up) / mmm_up;
-        const double dtc_low = in.dcol_l[i] * (cab_low + csc_low) / mmm_low;
+        const double mmm_up = (in.mmm_lay[li] + in.mmm_int[ii + 1]) / 2.0;
+        const double mmm_low = (in.mmm_int[ii] + in.mmm_lay[li]) / 2.0;
+        const double dtc_up = in.dcol_u[li] * (cab_up + csc_up) / mmm_up;
+        const double dtc_low = in.dcol_l[li] * (cab_low + csc_low) / mmm_low;
         if (y == 0) {
             o.dtc_u[b] = dtc_up;
             o.dtc_l[b] = dtc_low;
         }
-        const CellCoeffs u = cell_coeffs(ray_up, csc_up, cab_up, opac_up, mmm_up, in.dcol_u[i], dtc_up, g0_up, s);
-        const CellCoeffs l = cell_coeffs(ray_low, csc_low, cab_low, opac_low, mmm_low, in.dcol_l[i], dtc_low, g0_low, s);
+        const CellCoeffs u = cell_coeffs(ray_up, csc_up, cab_up, opac_up, mmm_up, in.dcol_u[li], dtc_up, g0_up, s);
+        const CellCoeffs l = cell_coeffs(ray_low, csc_low, cab_low, opac_low, mmm_low, in.dcol_l[li], dtc_low, g0_low, s);
         o.w0_u[e] = u.w0;      o.w0_l[e] = l.w0;
         o.dtau_u[e] = u.dtau;  o.dtau_l[e] = l.dtau;
         o.trans_u[e] = u.trans; o.trans_l[e] = l.trans;
@@ -176,14 +188,21 @@ k_calc_trans_noniso(NonisoOut o, NonisoIn in, int* __restrict__ scat_trigger, Tr
         o.P_u[e] = u.P;  o.P_l[e] = l.P;
         o.Gp_u[e] = u.Gp; o.Gp_l[e] = l.Gp;
         o.Gm_u[e] = u.Gm; o.Gm_l[e] = l.Gm;
-        if (u.w0 > s.w_0_scat_limit || l.w0 > s.w_0_scat_limit) scat_trigger[col] = 1;
+        if (u.w0 > s.w_0_scat_limit || l.w0 > s.w_0_scat_limit) scat_trigger[(size_t)a * ncol + col] = 1;
     }
 }
 
 // K:1247-1261
 __global__ void k_calc_delta_z(const double* __restrict__ tlay, const double* __restrict__ pint,
-                               const double* __restrict__ mmm, double* __restrict__ dz, double g, int nlayer) {
+                               const double* __restrict__ mmm, double* __restrict__ dz, double g, int nlayer,
+                               const double* __restrict__ g_batch) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t a = blockIdx.y;  // batch: T_lay and p_int hold nlayer + 1 values per atmosphere
+    if (g_batch) g = g_batch[a];
+    tlay += a * (nlayer + 1);
+    pint += a * (nlayer + 1);
+    mmm += a * nlayer;
+    dz += a * nlayer;
     if (i < nlayer) dz[i] = hc::KBOLTZMANN * tlay[i] / (mmm[i] * g) * log(pint[i] / pint[i + 1]);
 }
 
@@ -270,6 +289,17 @@ k_fdir_lp(double* __restrict__ F_dir, double* __restrict__ Fc_dir, const double*
     constexpr int ROWS = FD_THREADS / FD_COLS;
     const int col = blockIdx.x * FD_COLS + c;
     const bool live = col < ncol;
+    {   // batch (blockIdx.y = atmosphere)
+        const size_t a = blockIdx.y;
+        const size_t wg = (size_t)ncol * nint;
+        F_dir += a * wg;
+        dtau_a += a * wg;
+        if (NONISO) {
+            Fc_dir += a * wg;
+            dtau_b += a * wg;
+        }
+        planck_lay += a * (size_t)(nlay + 2) * nbin;
+    }
     if (live) {
         for (int i = r; i < nlay; i += ROWS) {
             const size_t e = col + (size_t)ncol * i;
@@ -311,12 +341,14 @@ static int launch_fdir(helios_ctx* ctx, double* F_dir, double* Fc_dir, const dou
                        int ny) {
     const int ncol = nbin * ny;
     const size_t smem = (size_t)(nint - 1) * FD_COLS * sizeof(double) * (NONISO ? 2 : 1);
+    HBATCHDIMS(ctx, nint == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
     if (geom != 1 && smem <= 200 * 1024) {
         auto kern = k_fdir_lp<NONISO>;
         HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<ceil_div(ncol, FD_COLS), FD_THREADS, smem, ctx->stream>>>(F_dir, Fc_dir, planck_lay, dtau_a, dtau_b,
-                                                                        mu_star, R_star, a, dir_beam, nint, nbin, ny);
+        kern<<<dim3(ceil_div(ncol, FD_COLS), ctx->batch.nbatch), FD_THREADS, smem, ctx->stream>>>(
+            F_dir, Fc_dir, planck_lay, dtau_a, dtau_b, mu_star, R_star, a, dir_beam, nint, nbin, ny);
     } else {
+        HNOBATCH(ctx);
         k_fdir<NONISO><<<ceil_div(ncol, 128), 128, 0, ctx->stream>>>(F_dir, Fc_dir, planck_lay, dtau_a, dtau_b, z_lay,
                                                                      mu_star, R_planet, R_star, a, dir_beam, geom,
                                                                      nint, nbin, ny);
@@ -343,12 +375,13 @@ int helios_calc_trans_iso(helios_ctx* ctx, double* trans_wg, double* delta_tau_w
     HARG(clouds == 0 || g_0_tot_lay != nullptr);
     HARG(nbin > 0 && ny > 0 && nlayer > 0);
     TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
-                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0};
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0, ctx->batch.nbatch};
+    HBATCHDIMS(ctx, nbin == ctx->batch.nbin && ny == ctx->batch.ny && nlayer == ctx->batch.nlayer);
     {
         const int rc = trans_constants(ctx, s);
         if (rc != HELIOS_OK) return rc;
     }
-    const long long total = (long long)nbin * ny * nlayer;
+    const long long total = (long long)nbin * ny * nlayer * ctx->batch.nbatch;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
@@ -385,7 +418,8 @@ int helios_calc_trans_noniso(
     HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
     HARG(nbin > 0 && ny > 0 && nlayer > 0);
     TransScalars s{g_0, epsi, epsi2, mu_star, w_0_limit, w_0_scat_limit, i2s_transition,
-                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0};
+                   scat, nbin, ny, nlayer, clouds, scat_corr, debug, 0.0, 0.0, ctx->batch.nbatch};
+    HBATCHDIMS(ctx, nbin == ctx->batch.nbin && ny == ctx->batch.ny && nlayer == ctx->batch.nlayer);
     {
         const int rc = trans_constants(ctx, s);
         if (rc != HELIOS_OK) return rc;
@@ -398,7 +432,7 @@ int helios_calc_trans_noniso(
                 meanmolmass_int, scat_cross_lay, scat_cross_int, abs_cross_all_clouds_lay,
                 abs_cross_all_clouds_int, scat_cross_all_clouds_lay, scat_cross_all_clouds_int,
                 g_0_tot_lay, g_0_tot_int};
-    const long long total = (long long)nbin * ny * nlayer;
+    const long long total = (long long)nbin * ny * nlayer * ctx->batch.nbatch;
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)ctx->num_sms * 32;
     if (blocks > cap) blocks = cap;
@@ -412,8 +446,9 @@ int helios_calc_delta_z(helios_ctx* ctx, const double* tlay, const double* pint,
     HCTX(ctx);
     (void)play;
     HARG(tlay && pint && meanmolmass_lay && delta_z_lay && nlayer > 0);
-    k_calc_delta_z<<<ceil_div(nlayer, 128), 128, 0, ctx->stream>>>(tlay, pint, meanmolmass_lay,
-                                                                   delta_z_lay, g, nlayer);
+    HBATCHDIMS(ctx, nlayer == ctx->batch.nlayer);
+    k_calc_delta_z<<<dim3(ceil_div(nlayer, 128), ctx->batch.nbatch), 128, 0, ctx->stream>>>(
+        tlay, pint, meanmolmass_lay, delta_z_lay, g, nlayer, ctx->batch.nbatch > 1 ? ctx->batch.g : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }

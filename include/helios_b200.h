@@ -64,6 +64,30 @@ int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes);
  * 1 = one thread per column (fband.cu), 2 = layer-parallel only (error if the shape does not fit) */
 int helios_ctx_set_fband_mode(helios_ctx* ctx, int mode);
 
+/* Batched atmospheres (BASELINE.json configs[4]; no reference counterpart -- the reference runs one atmosphere
+ * per process).  After helios_ctx_set_batch(ctx, nbatch > 1, ...) the per-iteration entry points
+ *   temp_inter, planck_interpol_layer/interface, opac_interpol, meanmolmass_interpol,
+ *   calc_total_g_0_of_gas_and_clouds, calc_trans_iso/noniso, calc_delta_z, fdir_iso/noniso (no geometric zenith
+ *   correction), fband_iso/noniso, integrate_flux_double, rad_temp_iter, abort_sum
+ * process nbatch atmospheres of identical shape (nlayer, nbin, ny) in ONE launch each.  Conventions:
+ *   - every per-atmosphere array argument holds nbatch consecutive single-atmosphere arrays, each of the size the
+ *     reference allocates for it (Q:400-461, 613-665; e.g. all [i][x][y] arrays are ninterface*ny*nbin, Q:407);
+ *   - shared arguments are passed once: the (P,T) grids, the opacity / Rayleigh / mean-molecular-mass tables
+ *     (several tables may be stacked: atmosphere b reads table table_index[b], the strides give the distance
+ *     between consecutive tables in doubles), the Planck table, wavelength grids, Gauss weights, surf_albedo;
+ *   - g[b] replaces the scalar gravity argument; planck_star[b][x] replaces row `dim` of the Planck table
+ *     (the stellar slot of planckband_lay, K:940) so that atmospheres with different T_star share one table;
+ *   - scalar arguments (dimensions, flags, mu_star, epsi, ...) apply to all atmospheres;
+ *   - abort_sum writes one sum per atmosphere and latches done[b] once all nlayer+1 flags of b are set;
+ *     rad_temp_iter and fband_* skip atmospheres whose done flag is set, so a converged atmosphere keeps exactly
+ *     the state a single-atmosphere run ends with while the others iterate on.
+ * All other entry points return HELIOS_ERR_STATE in batch mode.  nbatch = 1 leaves batch mode. */
+int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int ny, const int* table_index,
+                         size_t ktable_stride, size_t crosstable_stride, size_t meanmass_stride, const double* g,
+                         const double* planck_star);
+/* copy the done flags to done_host[nbatch] (may be NULL) and/or clear them */
+int helios_ctx_batch_done(helios_ctx* ctx, int* done_host, int reset);
+
 /* buffers: replace gpuarray.to_gpu / cuda.mem_alloc / .get() (Q:463-665) */
 int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr);
 int helios_buf_free(helios_ctx* ctx, void* dptr);
