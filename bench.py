@@ -164,6 +164,196 @@ def _bytes_per_cell(q):
     return 14 * 8 + 16 + 16 + 32 + (2 * 8 + 2 * 8 + (2 * 8 if q.clouds == 1 else 0)) / ny
 
 
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations, measured with the same rules (CUDA events on the launching stream,
+# L2 flushed between steps, >= 3 warm-up steps).  They ride along in the default line under "workloads".
+# ------------------------------------------------------------------------------------------------------------
+def _timed(ctx, step, steps, warmup, flush, split=None):
+    """average ms per step; `split` (optional) is called between the two halves of a step and returns nothing --
+    when given, the time of the first half is returned as well"""
+    for _ in range(max(warmup, 3)):
+        flush.fill_zero()
+        step(None)
+    ctx.synchronize()
+    ev = [[ctx.event() for _ in range(3)] for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_zero()
+        step(ev[k])
+    ctx.synchronize()
+    total = sum(e[0].time_till(e[2]) for e in ev) / steps
+    first = sum(e[0].time_till(e[1]) for e in ev) / steps
+    return total, first
+
+
+def bench_batch(ctx, rank, world, nbatch, steps, warmup, flush, config="C1"):
+    """C5: a grid of independent atmospheres, `nbatch` per GPU, one launch per kernel (helios_b200/batch.py)"""
+    from helios_b200 import synthetic, sharding
+    from helios_b200.batch import make_batch
+    params = sharding.partition_atmospheres(synthetic.grid_parameters(), rank, world)[:nbatch]
+    while len(params) < nbatch:  # fewer ranks than the grid was cut for: recycle parameter sets
+        params = (params + params)[:nbatch]
+    stores = synthetic.make_grid_stores(params, config=config, ctx=ctx)
+    n = int(stores[0].nlayer)
+    for k, q in enumerate(stores):
+        q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]]) + 3.0 * (k % 16)
+    qb, comp = make_batch(stores, ctx)
+    del stores
+    comp.construct_planck_table(qb)
+    comp.correct_incident_energy(qb)
+    qb.enter()
+    qb.iter_value = np.int32(0)
+    comp.interpolate_temperatures(qb)
+    comp.interpolate_planck(qb)
+    comp._refresh_atmosphere(qb)
+    ctx.synchronize()
+    npass = comp.n_scat_passes(qb)
+    cells = int(qb.nlayer) * int(qb.nbin) * int(qb.ny) * nbatch
+
+    def step(ev):
+        if ev:
+            ev[0].record()
+        comp.populate_spectral_flux_iteratively(qb)
+        if ev:
+            ev[1].record()
+        comp.integrate_flux(qb)
+        if ev:
+            ev[2].record()
+
+    t_solve, t_fband = _timed(ctx, step, steps, warmup, flush)
+
+    # one full batched RT iteration through the public API with host buffers
+    nl1 = int(qb.nlayer) + 1
+    T_host = backend_mod().PinnedArray(nbatch * nl1)
+    T_host.array[:] = qb.dev_T_lay.get()
+    res_host = backend_mod().PinnedArray(nbatch * nl1)
+    sums_host = backend_mod().PinnedArray(nbatch, np.int32)
+    e0, e1 = ctx.event(), ctx.event()
+
+    def iteration():
+        T_host.h2d_async(ctx, qb.dev_T_lay)
+        comp.interpolate_temperatures(qb)
+        comp.interpolate_planck(qb)
+        comp._refresh_atmosphere(qb)
+        step(None)
+        comp.rad_temp_iteration(qb)
+        ctx.call("abort_sum", qb.dev_abort, nl1, qb.dev_abort_sums)
+        res_host.d2h_async(ctx, qb.dev_T_lay)
+        sums_host.d2h_async(ctx, qb.dev_abort_sums)
+        ctx.synchronize()
+
+    for _ in range(2):
+        iteration()
+    t_e2e = 0.0
+    n_e2e = max(3, steps // 2)
+    for _ in range(n_e2e):
+        flush.fill_zero()
+        e0.record()
+        iteration()
+        e1.record()
+        e1.synchronize()
+        t_e2e += e0.time_till(e1)
+    t_e2e /= n_e2e
+    qb.leave()
+    bpc = _bytes_per_cell(qb)
+    return dict(qb=qb, comp=comp, npass=npass, cells=cells, points=cells * npass, t_solve=t_solve, t_fband=t_fband,
+                t_e2e=t_e2e, bpc=bpc, h2d=T_host.nbytes, d2h=res_host.nbytes + sums_host.nbytes,
+                workload="C5: %d independent atmospheres per GPU (T_star x log g x opacity scaling grid), each %d layers x "
+                         "%d bins x %d gauss points, %s layers, %d fused flux passes; one launch per kernel for the "
+                         "whole batch, %d opacity tables shared" % (nbatch, qb.nlayer, qb.nbin, qb.ny,
+                                                                    "isothermal" if qb.iso == 1 else "non-isothermal",
+                                                                    npass, qb.ntables))
+
+
+def backend_mod():
+    from helios_b200 import backend
+    return backend
+
+
+def bench_c4(ctx, rank, world, steps, warmup, flush, nbin=100000, scat=1, dim=8000, step_k=2, reuse=None):
+    """C4: post-processing of a high-resolution opacity-sampling spectrum (1e5 bins x 1 point), wavelength-sharded
+    across the ranks with the fused NVLink all-reduce of the flux totals (helios_b200/sharding.py)"""
+    from helios_b200 import synthetic, sharding
+    from helios_b200.computation import Compute
+    if reuse is not None:
+        q, comp = reuse["q"], reuse["comp"]
+        q.scat = np.int32(scat)
+    else:
+        q = synthetic.make_store("C4", ctx=ctx, nbin=nbin, plancktable_dim=dim, plancktable_step=step_k)
+        q.scat = np.int32(scat)
+        n = int(q.nlayer)
+        q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+        if world > 1:
+            sharding.shard_store(q, rank, world)
+        synthetic.upload(q)
+        if world > 1:
+            sharding.attach_flux_allreduce(q, ctx, rank, world)
+        comp = Compute(ctx, verbose=False)
+        comp.construct_planck_table(q)
+    q.iter_value = np.int32(0)
+    refresh(comp, q)
+    ctx.synchronize()
+    npass = comp.n_scat_passes(q)
+    cells = int(q.nlayer) * int(q.nbin) * int(q.ny)
+
+    def step(ev):
+        if ev:
+            ev[0].record()
+        comp.populate_spectral_flux_iteratively(q)
+        if ev:
+            ev[1].record()
+        comp.integrate_flux(q)
+        if ev:
+            ev[2].record()
+
+    t_solve, t_fband = _timed(ctx, step, steps, warmup, flush)
+    return dict(q=q, comp=comp, npass=npass, cells=cells, points=cells * npass, t_solve=t_solve, t_fband=t_fband,
+                bpc=_bytes_per_cell(q),
+                workload="C4: post-processing spectrum, %d layers x %d bins x 1 point (this rank: %d bins), %d fused "
+                         "flux passes (scat=%d), wavelength-sharded over %d GPU(s)" %
+                         (q.nlayer, nbin, q.nbin, npass, scat, world))
+
+
+def rce_leg(ctx, workload, seed_offset=0):
+    """converged RCE atmospheres per hour: the radiation loop (+ convection loop) of one atmosphere from the
+    standard isothermal start to the reference's own convergence criterion, wall clock, host logic included"""
+    from helios_b200 import synthetic
+    from helios_b200.computation import Compute
+    q = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    status = "converged"
+    try:
+        comp.radiation_loop(q, None, None, None)
+        rad_iters = int(q.iter_value)
+        conv_iters = 0
+        if q.convection == 1:
+            comp.convection_loop(q, None, None, None)
+            conv_iters = int(q.iter_value)
+    except SystemExit:
+        status = "iteration limit"
+        rad_iters, conv_iters = int(q.iter_value), 0
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    return {"seconds": dt, "radiation_iterations": rad_iters, "convection_iterations": conv_iters, "status": status,
+            "ms_per_iteration": 1e3 * dt / max(1, rad_iters + conv_iters)}
+
+
+def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload):
+    peak, peak_src = _peaks()
+    traffic = _traffic_from_profile(workload)
+    t_k = t_kernel_ms * 1e-3
+    achieved = bpc * cells / t_k / 1e9
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": (traffic or {}).get("bytes_per_launch"),
+            "traffic_source": (traffic or {}).get("source"), "algorithmic_bytes_per_launch": bpc * cells,
+            "peak_source": peak_src, "bytes_per_cell_per_solve": bpc, "kernel_ms": t_kernel_ms,
+            "per_pass_equiv_GBs": achieved * npass}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -173,11 +363,100 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = runtime.set_default_context(backend.Context(local))
+    flush = ctx.zeros(256 * 1024 * 1024 // 8)
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_max(values):
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    base = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    l2 = "flushed between timed steps (256 MiB memset outside the event bracket)"
+
+    if args.workload == "C5":
+        barrier()
+        r = bench_batch(ctx, rank, world, args.batch, steps, warmup, flush)
+        barrier()
+        t_solve, t_fband, t_e2e = reduce_max([r["t_solve"], r["t_fband"], r["t_e2e"]])
+        line = dict(base, value=world * r["points"] / (t_solve * 1e-3), ms_per_step=t_solve, scaling="weak",
+                    config={"workload": r["workload"], "l2": l2, "sharding": "atmospheres dealt round-robin to the ranks, no collective"},
+                    e2e={"value": world * r["points"] / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": r["h2d"],
+                         "d2h_bytes_per_step": r["d2h"], "ms_per_step": t_e2e,
+                         "what": "one full batched RT iteration via BatchCompute.* (T profiles from pinned host, rebuild, "
+                                 "flux solve, temperature step, profiles + convergence sums to host)"},
+                    gpu_launches=None,
+                    roofline=_roofline("k_fband_wp (iso, all %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
+                                       r["bpc"], r["cells"], t_fband, r["npass"], "C5"))
+    elif args.workload == "C4":
+        barrier()
+        r = bench_c4(ctx, rank, world, steps, warmup, flush, scat=args.c4_scat)
+        barrier()
+        t_solve, t_fband = reduce_max([r["t_solve"], r["t_fband"]])
+        pts = reduce_max([float(r["points"])])  # ranks hold nbin/world +- 1 bins
+        total_points = 100 * 100000 * r["npass"]
+        line = dict(base, value=total_points / (t_solve * 1e-3), ms_per_step=t_solve, scaling="strong",
+                    config={"workload": r["workload"], "l2": l2,
+                            "sharding": "contiguous wavelength ranges per rank; one fused NVLink peer-memory all-reduce of "
+                                        "the per-interface flux totals per step"},
+                    e2e=None, gpu_launches=None,
+                    roofline=_roofline("k_fband_wp (iso, %d passes fused)" % r["npass"], r["bpc"], r["cells"], t_fband,
+                                       r["npass"], "C4"))
+        del pts
+    else:
+        line = _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max)
+        if rank == 0 and world == 1 and not args.only_main:
+            extra = {}
+            try:
+                t0 = time.perf_counter()
+                r = bench_batch(ctx, 0, 8, args.batch, max(5, steps // 5), 3, flush)
+                extra["C5_batched_grid"] = {
+                    "workload": r["workload"], "value": r["points"] / (r["t_solve"] * 1e-3), "unit": UNIT,
+                    "ms_per_step": r["t_solve"],
+                    "e2e": {"value": r["points"] / (r["t_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": r["t_e2e"],
+                            "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                    "roofline": _roofline("k_fband_wp (iso, %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
+                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5"),
+                    "setup_s": time.perf_counter() - t0}
+                del r
+            except Exception as e:  # noqa: BLE001 -- the main line must survive a failing extra
+                extra["C5_batched_grid"] = {"error": repr(e)}
+            r = None
+            for scat in (0, 1):
+                key = "C4_spectrum_1e5_bins_scat%d" % scat
+                try:
+                    r = bench_c4(ctx, 0, 1, max(3, steps // 10), 3, flush, scat=scat, reuse=r)
+                    extra[key] = {"workload": r["workload"], "value": r["points"] / (r["t_solve"] * 1e-3), "unit": UNIT,
+                                  "ms_per_step": r["t_solve"],
+                                  "roofline": _roofline("k_fband_wp (iso, %d passes fused)" % r["npass"], r["bpc"], r["cells"],
+                                                        r["t_fband"], r["npass"], "C4")}
+                except Exception as e:  # noqa: BLE001
+                    extra[key] = {"error": repr(e)}
+            line["workloads"] = extra
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        line["clocks"] = clocks
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
+    """C1 / C2: one atmosphere per rank (weak scaling, no collective)"""
+    from helios_b200 import backend
     q, comp = _prepare(args.workload, ctx, seed_offset=rank)
     npass = comp.n_scat_passes(q)
     cells = int(q.nlayer) * int(q.nbin) * int(q.ny)
     points = cells * npass
-    flush = ctx.zeros(256 * 1024 * 1024 // 8)
 
     def flux_solve(events=None):
         if events:
@@ -189,17 +468,10 @@ def run_ours(args):
         if events:
             events[2].record()
 
-    def barrier():
-        ctx.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         flush.fill_zero()
         flux_solve()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [[ctx.event() for _ in range(3)] for _ in range(args.steps)]
     launches0 = ctx.launch_count()
     barrier()
@@ -207,7 +479,7 @@ def run_ours(args):
         flush.fill_zero()  # L2 flush between timed steps (not inside the event bracket)
         flux_solve(ev[k])
     barrier()
-    launches = ctx.launch_count() - launches0 - args.steps * 0  # memsets are not kernel launches of ours
+    launches = ctx.launch_count() - launches0
     t_solve = sum(e[0].time_till(e[2]) for e in ev)
     t_fband = sum(e[0].time_till(e[1]) for e in ev)
 
@@ -247,48 +519,33 @@ def run_ours(args):
         e1.synchronize()
         t_e2e += e0.time_till(e1)
     barrier()
-    clocks = sampler.stop() if sampler else None
-
-    times = torch.tensor([t_solve, t_fband, t_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_solve, t_fband, t_e2e = [float(v) for v in times.tolist()]
-    if rank == 0:
-        peak, peak_src = _peaks()
-        traffic = _traffic_from_profile(args.workload)
-        bpc = _bytes_per_cell(q)
-        t_k = t_fband / args.steps * 1e-3
-        achieved = bpc * cells / t_k / 1e9
-        line = {
-            "metric": METRIC, "value": world * points * args.steps / (t_solve * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": t_solve / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s: %d layers x %d bins x %d gauss points, %s layers, %d fused flux passes, "
-                                   "clouds=%d, dir_beam=%d; one atmosphere per GPU" %
-                                   (args.workload, q.nlayer, q.nbin, q.ny, "isothermal" if q.iso == 1 else "non-isothermal",
-                                    npass, q.clouds, q.dir_beam),
-                       "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
-                       "sharding": "one atmosphere per rank, no collective"},
-            "e2e": {"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
-                    "what": "one full RT iteration via Compute.* (T profile from pinned host, rebuild, flux solve, "
-                            "temperature step, results to host)"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_fband_%s (all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (traffic or {}).get("bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                         "algorithmic_bytes_per_launch": bpc * cells,
-                         "peak_source": peak_src, "bytes_per_cell_per_solve": bpc,
-                         "kernel_ms": t_k * 1e3,
-                         "per_pass_equiv_GBs": achieved * npass},
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(q, args.workload)
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    rce = None
+    if not args.no_rce:
+        rce = rce_leg(ctx, args.workload, seed_offset=rank)
+        barrier()
+        rce_s = reduce_max([rce["seconds"]])[0]
+        rce = dict(rce, atmospheres_per_hour=world * 3600.0 / rce_s, seconds_max_over_ranks=rce_s,
+                   what="radiation_loop + convection_loop of one %s atmosphere per GPU from the isothermal start to the "
+                        "reference's convergence criterion (rad_convergence_limit 1e-8), wall clock incl. host logic" % args.workload)
+    t_solve, t_fband, t_e2e = reduce_max([t_solve, t_fband, t_e2e])
+    line = dict(base, value=world * points * args.steps / (t_solve * 1e-3), ms_per_step=t_solve / args.steps,
+                scaling="weak",
+                config={"workload": "%s: %d layers x %d bins x %d gauss points, %s layers, %d fused flux passes, "
+                                    "clouds=%d, dir_beam=%d; one atmosphere per GPU" %
+                                    (args.workload, q.nlayer, q.nbin, q.ny, "isothermal" if q.iso == 1 else "non-isothermal",
+                                     npass, q.clouds, q.dir_beam),
+                        "l2": l2, "sharding": "one atmosphere per rank, no collective"},
+                e2e={"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
+                     "what": "one full RT iteration via Compute.* (T profile from pinned host, rebuild, flux solve, "
+                             "temperature step, results to host)"},
+                gpu_launches=int(launches),
+                roofline=_roofline("k_fband_wp (%s, all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
+                                   _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload),
+                rce=rce)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(q, args.workload)
+    return line
 
 
 def cpu_baseline(q_dev, workload):
@@ -364,8 +621,13 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4", "C5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-rce", action="store_true", help="skip the converged-atmospheres-per-hour leg")
+    ap.add_argument("--only-main", action="store_true", help="skip the extra workloads (C5 batch, C4 spectrum)")
+    ap.add_argument("--batch", type=int, default=128, help="atmospheres per GPU of the C5 workload")
+    ap.add_argument("--c4-scat", type=int, default=0, help="C4: 1 = 1001 scattering passes as the reference's "
+                                                            "post-processing does, 0 = single pass")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

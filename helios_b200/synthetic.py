@@ -73,7 +73,9 @@ def rayleigh_table(ktemp, kpress, lam_c):
 
 def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=28, plancktable_dim=8000,
                plancktable_step=2, kcoeff_mixing="RO", n_species=10, table_scale=1.0, T_star=6117.0, g=930.0,
-               T_lay=None, seed=SEED):
+               T_lay=None, seed=SEED, tables=None):
+    """`tables`: optional dict scale -> (opac_k, opac_scat_cross, opac_meanmass) shared between the stores of a
+    grid, filled on first use (the stores then reference ONE host copy per scaling)"""
     rng = np.random.default_rng(seed)
     q = Store(ctx)
     q.name = "synthetic_" + config
@@ -150,8 +152,12 @@ def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=2
         q.gauss_y = 0.5 * leggauss(20)[0] + 0.5
     q.ny = np.int32(q.gauss_y.size)
     host.set_up_numerical_parameters(q)  # gauss_weight and the numerical limits
-    q.opac_scat_cross = rayleigh_table(q.ktemp, q.kpress, q.opac_wave)
-    q.opac_meanmass = np.full(ntemp * npress, 2.3 * host.AMU)
+    shared = tables.get(table_scale) if tables is not None else None
+    if shared is not None:
+        q.opac_scat_cross, q.opac_meanmass = shared[1], shared[2]
+    else:
+        q.opac_scat_cross = rayleigh_table(q.ktemp, q.kpress, q.opac_wave)
+        q.opac_meanmass = np.full(ntemp * npress, 2.3 * host.AMU)
     if config == "C3":
         q.opac_k = np.zeros(1)
         names = [("H2", 2.01588), ("He", 4.0026), ("H2O", 18.0153), ("CO", 28.01), ("CO2", 44.01), ("CH4", 16.04),
@@ -167,8 +173,12 @@ def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=2
                 sp.scat_cross_sect_layer = np.tile(sig, nlayer)
                 sp.scat_cross_sect_interface = np.tile(sig, nlayer + 1)
             q.species_list.append(sp)
+    elif shared is not None:
+        q.opac_k = shared[0]
     else:
         q.opac_k = k_table(rng, q.ktemp, q.kpress, q.opac_wave, q.gauss_y, spread=(config != "C4"), scale=table_scale)
+        if tables is not None:
+            tables[table_scale] = (q.opac_k, q.opac_scat_cross, q.opac_meanmass)
     # ---- kappa / c_p (read.py:1172-1193) and empty entropy tables
     q.kappa_lay = np.ones(nlayer) * float(q.input_kappa_value) if q.convection == 1 else np.zeros(nlayer)
     q.c_p_lay = np.ones(nlayer) * (host.R_UNIV / float(q.input_kappa_value)) if q.convection == 1 else np.zeros(nlayer)
@@ -183,6 +193,11 @@ def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=2
     q.starflux = np.zeros(int(q.nbin))
     q.dimensions()
     host.construct_grid(q)
+    if q.singlewalk == 1:
+        # post-processing starts from a given T-P profile (read.py:1274-1322 -> T_restart: surface first, then
+        # the layers bottom-up); stand-in: a smooth hot-Jupiter profile
+        nl_ = int(q.nlayer)
+        q.T_restart = [2350.0] + list(2300.0 - 1200.0 * (np.arange(nl_) / (nl_ - 1.0)) ** 1.5)
     host.initial_temp(q)
     if T_lay is not None:
         q.T_lay = np.array(T_lay, np.float64)
@@ -216,6 +231,12 @@ def upload(q):
     q.copy_host_to_device()
     q.allocate_on_device()
     return q
+
+
+def make_grid_stores(params, config="C1", ctx=None, **kw):
+    """the stores of a grid of atmospheres (C5), sharing one table set per opacity scaling"""
+    tables = {}
+    return [make_store(config, ctx=ctx, tables=tables, **dict(kw, **p)) for p in params]
 
 
 def grid_parameters(n_tstar=16, n_logg=16, n_scale=4):

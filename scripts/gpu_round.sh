@@ -14,13 +14,13 @@ timeout 600 python bench.py --workload C1 --no-cpu > gpurun_out/bench_c1_$tag.js
 cat gpurun_out/bench_$tag.json
 # launch list of the same command (cold-cache, serialised: shares only)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-    --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu_$tag.log 2>&1
+    --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-rce --only-main > gpurun_out/bench_under_ncu_$tag.log 2>&1
 echo "ncu list rc=$?"
 # full capture of the flux-sweep kernel and the transmission kernel
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fband -s 4 -c 2 \
-    -o gpurun_out/prof_fband_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_fband_$tag.log 2>&1
+    -o gpurun_out/prof_fband_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu --no-rce --only-main > gpurun_out/ncu_fband_$tag.log 2>&1
 echo "ncu fband rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_calc_trans|k_pt_gather|k_fdir|k_band_integrate|k_planck_interpol" -c 10 \
-    -o gpurun_out/prof_rebuild_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_rebuild_$tag.log 2>&1
+    -o gpurun_out/prof_rebuild_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu --no-rce --only-main > gpurun_out/ncu_rebuild_$tag.log 2>&1
 echo "ncu rebuild rc=$?"
 ls -la gpurun_out | tail -30
