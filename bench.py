@@ -10,7 +10,7 @@ offline).  A "step" is one flux solve of the RT iteration: `populate_spectral_fl
 passes) + `integrate_flux` (computation.py:881-888).
 
   value   layer*lambda*g-points/s = nlayer*nbin*ny*n_pass / t, inputs resident in HBM, CUDA-event timed per
-          step on the launching stream, L2 flushed (256 MiB memset) between steps, max over ranks
+          step on the launching stream, L2 flushed between steps (helios_l2_flush: 2x L2 overwritten, then read back), max over ranks
   e2e     the same metric for one full RT iteration through the public API (`Compute.*`): the step's
           temperature profile comes from pinned host memory (H2D), every temperature-dependent quantity is
           rebuilt (interpolation, transmission, direct beam), the flux solve runs, the temperature step is
@@ -172,12 +172,12 @@ def _timed(ctx, step, steps, warmup, flush, split=None):
     """average ms per step; `split` (optional) is called between the two halves of a step and returns nothing --
     when given, the time of the first half is returned as well"""
     for _ in range(max(warmup, 3)):
-        flush.fill_zero()
+        flush()
         step(None)
     ctx.synchronize()
     ev = [[ctx.event() for _ in range(3)] for _ in range(steps)]
     for k in range(steps):
-        flush.fill_zero()
+        flush()
         step(ev[k])
     ctx.synchronize()
     total = sum(e[0].time_till(e[2]) for e in ev) / steps
@@ -246,7 +246,7 @@ def bench_batch(ctx, rank, world, nbatch, steps, warmup, flush, config="C1"):
     t_e2e = 0.0
     n_e2e = max(3, steps // 2)
     for _ in range(n_e2e):
-        flush.fill_zero()
+        flush()
         e0.record()
         iteration()
         e1.record()
@@ -361,9 +361,13 @@ def run_ours(args):
     world, rank, local = _dist()
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL writes its version / debug lines to stdout by default; stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = runtime.set_default_context(backend.Context(local))
-    flush = ctx.zeros(256 * 1024 * 1024 // 8)
+    def flush():
+        ctx.call("l2_flush", 1)
+
     steps, warmup = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -381,7 +385,8 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     base = {"metric": METRIC, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
-    l2 = "flushed between timed steps (256 MiB memset outside the event bracket)"
+    l2 = ("flushed between timed steps, outside the event bracket: a 256 MiB buffer (2x L2) is overwritten and then "
+          "read back, so the timed kernels start on a cold L2 that holds no dirty lines of the flusher")
 
     if args.workload == "C5":
         barrier()
@@ -445,7 +450,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         line["clocks"] = clocks
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -469,14 +474,14 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
             events[2].record()
 
     for _ in range(max(args.warmup, 3)):
-        flush.fill_zero()
+        flush()
         flux_solve()
     barrier()
     ev = [[ctx.event() for _ in range(3)] for _ in range(args.steps)]
     launches0 = ctx.launch_count()
     barrier()
     for k in range(args.steps):
-        flush.fill_zero()  # L2 flush between timed steps (not inside the event bracket)
+        flush()  # L2 flush between timed steps (not inside the event bracket)
         flux_solve(ev[k])
     barrier()
     launches = ctx.launch_count() - launches0
@@ -512,7 +517,7 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     e2e_steps = args.steps
     t_e2e = 0.0
     for _ in range(e2e_steps):
-        flush.fill_zero()
+        flush()
         e0.record()
         iteration()
         e1.record()
@@ -574,7 +579,7 @@ def run_reference(args):
         return
     from oracle import ref_gpu
     if not ref_gpu.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/helios_ref.cubin was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/helios_ref.cubin was not built (needs /root/reference at build time)"})
         return
     from helios_b200 import backend, runtime
     ctx = runtime.set_default_context(backend.Context(local))
@@ -582,7 +587,9 @@ def run_reference(args):
     ref = ref_gpu.RefCompute(local)
     npass = comp.n_scat_passes(q)
     points = int(q.nlayer) * int(q.nbin) * int(q.ny) * npass
-    flush = ctx.zeros(256 * 1024 * 1024 // 8)
+    def flush():
+        ctx.call("l2_flush", 1)
+
     sampler = ClockSampler(local)
 
     def flux_solve():
@@ -594,14 +601,14 @@ def run_reference(args):
     t = 0.0
     n0 = ref.mod.launches
     for _ in range(args.steps):
-        flush.fill_zero()
+        flush()
         ctx.synchronize()
         t0 = time.perf_counter()  # the reference syncs the device after every launch, so wall clock == device time
         flux_solve()
         t += time.perf_counter() - t0
     clocks = sampler.stop()
     value = points * args.steps / t
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -612,7 +619,26 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
                          "sample": "reference kernels.cu (verbatim cubin) on GPU 0; %d launches per step" % ((ref.mod.launches - n0) // args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": int(ref.mod.launches - n0), "clocks": clocks}))
+        "gpu_launches": int(ref.mod.launches - n0), "clocks": clocks})
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL prints its version line) write to fd 1; the contract is ONE JSON line on stdout.  Point
+    fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -629,6 +655,7 @@ def main():
     ap.add_argument("--c4-scat", type=int, default=0, help="C4: 1 = 1001 scattering passes as the reference's "
                                                             "post-processing does, 0 = single pass")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -56,6 +56,8 @@ struct helios_ctx {
     size_t scratch_bytes = 0;
     helios_comm_state* comm = nullptr;
     BatchDesc batch;
+    void* flush_buf = nullptr;  // helios_l2_flush
+    size_t flush_bytes = 0;
     // pow(epsi,-2), pow(mu_star,-2) of calc_trans_*, keyed on (epsi, mu_star): trans.cu
     double trans_cache[4] = {0, 0, 0, 0};
     bool trans_cache_valid = false;

@@ -126,7 +126,6 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
     double* c_emis = c_fdir0 + NCOLS;
     const double neg_mu = -s.mu_star;
     const int ntile = (ncol + NCOLS - 1) / NCOLS;
-
     for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
         // batch: tiles enumerate (atmosphere, column tile); per-atmosphere arrays are offset by the
         // reference's allocation sizes (every [i][x][y] array holds ninterface rows, Q:407)

@@ -95,6 +95,49 @@ k_total_integrate(const double* __restrict__ deltalambda, const double* __restri
     }
 }
 
+// Wide spectra (1e5 sampling bins): one block per interface would leave the chip idle, so the sum over x is
+// split into TI_CHUNK-bin pieces (fixed tree inside a piece) whose partial sums a second kernel adds in chunk
+// order -- still a fixed summation order, bitwise reproducible run to run.
+#define TI_CHUNK 2048
+__global__ void __launch_bounds__(IF_THREADS)
+k_total_partial(const double* __restrict__ deltalambda, const double* __restrict__ F_down_band,
+                const double* __restrict__ F_up_band, const double* __restrict__ F_dir_band,
+                double* __restrict__ partial, int nbin) {
+    __shared__ double red[IF_THREADS];
+    const int i = blockIdx.y, nint = gridDim.y, nchunk = gridDim.x;
+    const size_t bd = (size_t)blockIdx.z * nint * nbin;  // batch (blockIdx.z = atmosphere)
+    const int x0 = blockIdx.x * TI_CHUNK, x1 = min(nbin, x0 + TI_CHUNK);
+    double up = 0.0, dn = 0.0;
+    for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x) {
+        const size_t o = bd + (size_t)i * nbin + x;
+        up += F_up_band[o] * deltalambda[x];
+        dn += (F_dir_band[o] + F_down_band[o]) * deltalambda[x];
+    }
+    up = block_sum(up, red);
+    dn = block_sum(dn, red);
+    if (threadIdx.x == 0) {
+        double* p = partial + (((size_t)blockIdx.z * nint + i) * nchunk + blockIdx.x) * 2;
+        p[0] = up;
+        p[1] = dn;
+    }
+}
+
+__global__ void k_total_final(const double* __restrict__ partial, double* __restrict__ F_down_tot,
+                              double* __restrict__ F_up_tot, double* __restrict__ F_net, int nint, int nchunk,
+                              int nbatch) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // (atmosphere, interface)
+    if (t >= nint * nbatch) return;
+    const double* p = partial + (size_t)t * nchunk * 2;
+    double up = 0.0, dn = 0.0;
+    for (int c = 0; c < nchunk; c++) {
+        up += p[2 * c];
+        dn += p[2 * c + 1];
+    }
+    F_up_tot[t] = up;
+    F_down_tot[t] = dn;
+    F_net[t] = up - dn;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Temperature stepping (K:2606-2884).  One block; the reads of neighbouring temperatures, the
 // smoothing prefix sums and the temperature update are separated by block barriers (the reference
@@ -396,9 +439,25 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
                                                               F_up_band, F_dir_band, gauss_weight, nbin,
                                                               ny, xb);
     HLAUNCHED(ctx);
-    k_total_integrate<<<dim3(numinterfaces, ctx->batch.nbatch), IF_THREADS, 0, ctx->stream>>>(
-        deltalambda, F_down_band, F_up_band, F_dir_band, F_down_tot, F_up_tot, F_net, nbin);
-    HLAUNCHED(ctx);
+    if (nbin <= 2 * TI_CHUNK) {
+        k_total_integrate<<<dim3(numinterfaces, ctx->batch.nbatch), IF_THREADS, 0, ctx->stream>>>(
+            deltalambda, F_down_band, F_up_band, F_dir_band, F_down_tot, F_up_tot, F_net, nbin);
+        HLAUNCHED(ctx);
+    } else {
+        const int nchunk = ceil_div(nbin, TI_CHUNK);
+        const int nb = ctx->batch.nbatch;
+        double* scratch = nullptr;
+        const size_t bytes = (size_t)nb * numinterfaces * nchunk * 2 * sizeof(double);
+        int rc = helios_ctx_scratch(ctx, bytes + 64, &scratch);
+        if (rc) return rc;
+        double* partial = scratch + 8;  // clear of the first 64 bytes (small reductions)
+        k_total_partial<<<dim3(nchunk, numinterfaces, nb), IF_THREADS, 0, ctx->stream>>>(
+            deltalambda, F_down_band, F_up_band, F_dir_band, partial, nbin);
+        HLAUNCHED(ctx);
+        k_total_final<<<ceil_div(numinterfaces * nb, 128), 128, 0, ctx->stream>>>(partial, F_down_tot, F_up_tot,
+                                                                              F_net, numinterfaces, nchunk, nb);
+        HLAUNCHED(ctx);
+    }
     return HELIOS_OK;
 }
 

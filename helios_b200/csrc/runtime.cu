@@ -20,6 +20,16 @@ int helios_fail_cuda(cudaError_t e, const char* what, const char* file, int line
     return e == cudaErrorMemoryAllocation ? HELIOS_ERR_NOMEM : HELIOS_ERR_CUDA;
 }
 
+// read sweep used by helios_l2_flush
+__global__ void k_read_sweep(const double4* __restrict__ src, size_t n4, double* __restrict__ sink) {
+    double acc = 0.0;
+    for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n4; k += (size_t)gridDim.x * blockDim.x) {
+        const double4 v = src[k];
+        acc += v.x + v.y + v.z + v.w;
+    }
+    if (acc == 1.2345e300) sink[0] = acc;  // never true for the zero-filled buffer; keeps the loads alive
+}
+
 extern "C" {
 
 int helios_abi_version(void) { return HELIOS_ABI_VERSION; }
@@ -74,6 +84,7 @@ int helios_ctx_destroy(helios_ctx* ctx) {
     ctx->allocs.clear();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->batch.done) cudaFree(ctx->batch.done);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return HELIOS_OK;
@@ -155,6 +166,26 @@ int helios_ctx_batch_done(helios_ctx* ctx, int* done_host, int reset) {
         HCUDA(cudaMemcpyAsync(done_host, ctx->batch.done, sizeof(int) * (size_t)ctx->batch.nbatch,
                               cudaMemcpyDeviceToHost, ctx->stream));
         HCUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return HELIOS_OK;
+}
+
+int helios_l2_flush(helios_ctx* ctx, int mode) {
+    HCTX(ctx);
+    HARG(mode == 0 || mode == 1);
+    const size_t bytes = ctx->l2_bytes * 2 > ((size_t)256 << 20) ? ctx->l2_bytes * 2 : ((size_t)256 << 20);
+    if (ctx->flush_buf == nullptr) {
+        HCUDA(cudaMalloc(&ctx->flush_buf, bytes + 64));
+        ctx->flush_bytes = bytes;
+    }
+    HCUDA(cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    if (mode == 1) {
+        // the memset leaves L2 full of DIRTY lines, whose write-back would be charged to whatever runs next;
+        // a read sweep over the same buffer replaces them with clean lines (cold for every other address)
+        double* sink = reinterpret_cast<double*>(reinterpret_cast<char*>(ctx->flush_buf) + ctx->flush_bytes);
+        k_read_sweep<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(reinterpret_cast<const double4*>(ctx->flush_buf),
+                                                               ctx->flush_bytes / sizeof(double4), sink);
+        HCUDA(cudaGetLastError());
     }
     return HELIOS_OK;
 }

@@ -100,10 +100,10 @@ def attach_flux_allreduce(q, ctx, rank, world, pg=None):
     import ctypes
     n = int(q.ninterface)
     handle = (ctypes.c_ubyte * 64)()
-    backend._check(backend.lib().helios_comm_create(ctx.handle(), int(rank), int(world), 2 * n, handle), "comm_create")
+    backend._check(backend.lib().helios_comm_create(ctx.handle, int(rank), int(world), 2 * n, handle), "comm_create")
     handles = exchange_handles(handle, rank, world, pg)
     buf = (ctypes.c_ubyte * (64 * world)).from_buffer_copy(handles)
-    backend._check(backend.lib().helios_comm_connect(ctx.handle(), buf), "comm_connect")
+    backend._check(backend.lib().helios_comm_connect(ctx.handle, buf), "comm_connect")
 
     def flux_allreduce(quant):
         ctx.call("comm_allreduce_flux_totals", quant.dev_F_up_tot, quant.dev_F_down_tot, quant.dev_F_net, n)

@@ -60,6 +60,13 @@ int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count);
 /* bytes currently allocated through helios_buf_alloc */
 int helios_ctx_bytes_allocated(helios_ctx* ctx, size_t* nbytes);
 
+/* Benchmark hygiene, no reference counterpart: evict the L2 cache between timed steps (stream-ordered).
+ * mode 0: overwrite a context-owned buffer of 2x the L2 size (L2 is left full of dirty lines, whose write-back
+ *         overlaps whatever runs next);
+ * mode 1: the same followed by a read sweep over that buffer, so that L2 ends up full of CLEAN foreign lines:
+ *         everything is cold for the next kernel and no write-back traffic is charged to it. */
+int helios_l2_flush(helios_ctx* ctx, int mode);
+
 /* flux-sweep algorithm: 0 = automatic (layer-parallel kernel whenever the shape fits, default),
  * 1 = one thread per column (fband.cu), 2 = layer-parallel only (error if the shape does not fit) */
 int helios_ctx_set_fband_mode(helios_ctx* ctx, int mode);

@@ -82,7 +82,7 @@ def _worker(rank, world, port, config, out):
         dist.all_gather(rows, mine)
         assert all(torch.equal(r, mine) for r in rows), "ranks disagree bitwise"
         ctx.synchronize()
-        backend.lib().helios_comm_destroy(ctx.handle())
+        backend.lib().helios_comm_destroy(ctx.handle)
         out.put((rank, "ok", worst))
         dist.destroy_process_group()
     except Exception:  # noqa: BLE001

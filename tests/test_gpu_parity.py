@@ -295,3 +295,22 @@ def test_kappa_cp_entropy_phase_from_file(ctx, iso):
             stage_vs_ref(q, comp, ref_gpu.RefCompute(ctx.device), method, names, soft=bad)
     bad.check()
     assert np.all(q.dev_kappa_lay.get() > 0)
+
+
+def test_wide_spectrum_flux_integration(ctx):
+    """nbin > 4096 takes the two-stage sum over wavelength (flux.cu: k_total_partial / k_total_final)"""
+    from oracle import helios_oracle as O
+    rng = np.random.default_rng(3)
+    nbin, nint, ny = 9001, 7, 1
+    gw = np.array([2.0])
+    dl = rng.uniform(1e-7, 1e-5, nbin)
+    Fd, Fu, Fr = (rng.uniform(0, 1e9, nint * nbin * ny) for _ in range(3))
+    d = {k: ctx.to_device(v) for k, v in dict(dl=dl, Fd=Fd, Fu=Fu, Fr=Fr, gw=gw).items()}
+    out = {k: ctx.zeros(n) for k, n in dict(dt=nint, ut=nint, net=nint, db=nint * nbin, ub=nint * nbin, rb=nint * nbin).items()}
+    ctx.call("integrate_flux_double", d["dl"], out["dt"], out["ut"], out["net"], d["Fd"], d["Fu"], d["Fr"], out["db"],
+             out["ub"], out["rb"], d["gw"], nbin, nint, ny)
+    r = O.integrate_flux(dl, Fd, Fu, Fr, gw, nbin, nint, ny)
+    for name, got in (("F_down_band", out["db"]), ("F_up_band", out["ub"]), ("F_dir_band", out["rb"]),
+                      ("F_down_tot", out["dt"]), ("F_up_tot", out["ut"])):
+        assert_close(got.get(), r[name], "wide integrate: " + name, rtol=1e-12)
+    assert np.array_equal(out["net"].get(), out["ut"].get() - out["dt"].get())
