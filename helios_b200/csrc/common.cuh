@@ -56,6 +56,11 @@ struct helios_ctx {
     size_t scratch_bytes = 0;
     helios_comm_state* comm = nullptr;
     BatchDesc batch;
+    // Direct-beam arrays known to hold only (signed) zeros: written by fdir_* with dir_beam == 0 and not
+    // touched since (every write to device memory goes through this library).  fband_* then skips loading
+    // them and the G+/- coefficient arrays that only multiply them.  [0] = F_dir_wg, [1] = Fc_dir_wg.
+    const void* zero_beam[2] = {nullptr, nullptr};
+    size_t zero_beam_bytes = 0;
     void* flush_buf = nullptr;  // helios_l2_flush
     size_t flush_bytes = 0;
     // pow(epsi,-2), pow(mu_star,-2) of calc_trans_*, keyed on (epsi, mu_star): trans.cu
@@ -121,6 +126,15 @@ int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out);
             return HELIOS_ERR_ARG;                                             \
         }                                                                      \
     } while (0)
+
+// a buffer range is about to be overwritten from outside the kernels: forget what was known about it
+static inline void helios_note_write(helios_ctx* ctx, const void* p, size_t nbytes) {
+    const char* lo = static_cast<const char*>(p);
+    for (int k = 0; k < 2; k++) {
+        const char* z = static_cast<const char*>(ctx->zero_beam[k]);
+        if (z != nullptr && lo < z + ctx->zero_beam_bytes && z < lo + nbytes) ctx->zero_beam[k] = nullptr;
+    }
+}
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 

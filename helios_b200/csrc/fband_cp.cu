@@ -31,6 +31,7 @@
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
+    int no_beam;      // F_dir / Fc_dir are known to be all -0.0: do not load them, nor G+/-
     int nbatch;       // atmospheres per launch (helios_ctx_set_batch), 1 otherwise
     const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
 };
@@ -145,25 +146,38 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
             const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
             const double* __restrict__ BI = NONISO ? planck_int + bio + (size_t)x * nint : nullptr;
             constexpr int NRAW = NONISO ? 24 : 11;
-            double raw[1][NRAW];
+            // cells whose loads are in flight together per thread (2 or 4 were measured SLOWER for the isothermal
+            // kernel on B200: register spills outweigh the extra memory-level parallelism)
+            constexpr int UA = 1;
+            double raw[UA][NRAW];
             auto load_cell = [&](int m, double* q) {
                 const int i = r + LPC * m;
                 if (i < nlay) {
                     const size_t e = wgo + col + (size_t)ncol * i;
                     const size_t bb = (size_t)x + (size_t)s.nbin * i;
-                    q[0] = F_dir[e];
-                    q[1] = F_dir[e + ncol];
+                    if (s.no_beam) {
+                        q[0] = q[1] = -0.0;  // what fdir_* wrote (trans.cu); G+/- only ever multiply the beam
+                        q[6] = q[7] = 0.0;
+                    } else {
+                        q[0] = F_dir[e];
+                        q[1] = F_dir[e + ncol];
+                        q[6] = cfg.Gp_u[e]; q[7] = cfg.Gm_u[e];
+                    }
                     q[2] = cfg.w0_u[e]; q[3] = cfg.M_u[e]; q[4] = cfg.N_u[e]; q[5] = cfg.P_u[e];
-                    q[6] = cfg.Gp_u[e]; q[7] = cfg.Gm_u[e];
                     q[8] = BL[i];
                     q[9] = F_up[e];
                     q[10] = s.clouds ? g0_lay[blo + bb] : s.g_0;
                     if (NONISO) {
                         q[11] = cfg.w0_l[e]; q[12] = cfg.M_l[e]; q[13] = cfg.N_l[e]; q[14] = cfg.P_l[e];
-                        q[15] = cfg.Gp_l[e]; q[16] = cfg.Gm_l[e];
+                        if (s.no_beam) {
+                            q[15] = q[16] = 0.0;
+                            q[19] = -0.0;
+                        } else {
+                            q[15] = cfg.Gp_l[e]; q[16] = cfg.Gm_l[e];
+                            q[19] = Fc_dir[e];
+                        }
                         q[17] = cfg.dtau_u[e] + cfg.dtc_u[blo + bb];
                         q[18] = cfg.dtau_l[e] + cfg.dtc_l[blo + bb];
-                        q[19] = Fc_dir[e];
                         q[20] = BI[i];
                         q[21] = BI[i + 1];
                         q[22] = Fc_up[e];
@@ -172,13 +186,10 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                     }
                 }
             };
-#pragma unroll
-            for (int m = 0; m < CH; m++) {
-                load_cell(m, raw[0]);  // all loads of the cell are issued back to back, then consumed
+            auto emit_cell = [&](int m, const double* q) {
                 {
                     const int i = r + LPC * m;
                     if (i < nlay) {
-                        const double* q = raw[0];
                         const int o = c * pitch + (i / CH) * STRIDE + (i % CH);
                         const double Fdir_i = q[0], Fdir_ip1 = q[1];
                         if (!NONISO) {
@@ -264,6 +275,15 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                         }
                     }
                 }
+            };
+#pragma unroll
+            for (int m0 = 0; m0 < CH; m0 += UA) {
+#pragma unroll
+                for (int u = 0; u < UA; u++)  // all loads of UA cells are issued back to back, then consumed
+                    if (m0 + u < CH) load_cell(m0 + u, raw[u]);
+#pragma unroll
+                for (int u = 0; u < UA; u++)
+                    if (m0 + u < CH) emit_cell(m0 + u, raw[u]);
             }
         }
         __syncthreads();
@@ -447,7 +467,8 @@ int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double
                      const double* Gm, const double* albedo, const double* g0tot, double g_0, double Rstar,
                      double a, int nint, int nbin, double f_factor, double mu_star, int ny, double epsi,
                      int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
-    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0, 1, nullptr};
+    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0,
+                (dir_beam == 0 && ctx->zero_beam[0] == F_dir) ? 1 : 0, 1, nullptr};
     CpNonisoCoef c{w_0, nullptr, nullptr, nullptr, nullptr, nullptr, M, nullptr, N, nullptr, P, nullptr, Gp, nullptr, Gm, nullptr};
     return dispatch_wp<false>(ctx, F_down, F_up, nullptr, nullptr, F_dir, nullptr, planck, nullptr, c, albedo, g0tot,
                               nullptr, s, nbin * ny);
@@ -460,7 +481,8 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
     CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds,
-                scat_corr, npass, 0, 0, 1, nullptr};
+                scat_corr, npass, 0, 0,
+                (dir_beam == 0 && ctx->zero_beam[0] == F_dir && ctx->zero_beam[1] == Fc_dir) ? 1 : 0, 1, nullptr};
     return dispatch_wp<true>(ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo,
                              g0_lay, g0_int, s, nbin * ny);
 }

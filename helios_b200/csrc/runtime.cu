@@ -220,6 +220,7 @@ int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr) {
 
 int helios_buf_free(helios_ctx* ctx, void* dptr) {
     HCTX(ctx);
+    helios_note_write(ctx, dptr, 1);
     if (dptr == nullptr) return HELIOS_OK;
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
@@ -241,6 +242,7 @@ int helios_buf_h2d(helios_ctx* ctx, void* dst_dev, const void* src_host, size_t 
     HCTX(ctx);
     if (nbytes == 0) return HELIOS_OK;
     HARG(dst_dev != nullptr && src_host != nullptr);
+    helios_note_write(ctx, dst_dev, nbytes);
     HCUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     // the caller may reuse/free the (pageable) host array right away, as with gpuarray.to_gpu
     HCUDA(cudaStreamSynchronize(ctx->stream));
@@ -260,6 +262,7 @@ int helios_buf_h2d_async(helios_ctx* ctx, void* dst_dev, const void* src_host, s
     HCTX(ctx);
     if (nbytes == 0) return HELIOS_OK;
     HARG(dst_dev != nullptr && src_host != nullptr);
+    helios_note_write(ctx, dst_dev, nbytes);
     HCUDA(cudaMemcpyAsync(dst_dev, src_host, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     return HELIOS_OK;
 }
@@ -276,6 +279,7 @@ int helios_buf_d2d(helios_ctx* ctx, void* dst_dev, const void* src_dev, size_t n
     HCTX(ctx);
     if (nbytes == 0) return HELIOS_OK;
     HARG(dst_dev != nullptr && src_dev != nullptr);
+    helios_note_write(ctx, dst_dev, nbytes);
     HCUDA(cudaMemcpyAsync(dst_dev, src_dev, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return HELIOS_OK;
 }
@@ -284,6 +288,7 @@ int helios_buf_zero(helios_ctx* ctx, void* dptr, size_t nbytes) {
     HCTX(ctx);
     if (nbytes == 0) return HELIOS_OK;
     HARG(dptr != nullptr);
+    helios_note_write(ctx, dptr, nbytes);
     HCUDA(cudaMemsetAsync(dptr, 0, nbytes, ctx->stream));
     return HELIOS_OK;
 }

@@ -354,6 +354,10 @@ static int launch_fdir(helios_ctx* ctx, double* F_dir, double* Fc_dir, const dou
                                                                      nint, nbin, ny);
     }
     HLAUNCHED(ctx);
+    // with dir_beam == 0 every entry written above is -0.0 (F_toa = -0 * mu* * I): remember that (common.cuh)
+    ctx->zero_beam[0] = dir_beam == 0 ? F_dir : nullptr;
+    ctx->zero_beam[1] = (dir_beam == 0 && NONISO) ? Fc_dir : nullptr;
+    ctx->zero_beam_bytes = (size_t)ncol * nint * sizeof(double) * ctx->batch.nbatch;
     return HELIOS_OK;
 }
 

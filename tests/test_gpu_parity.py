@@ -314,3 +314,37 @@ def test_wide_spectrum_flux_integration(ctx):
                       ("F_down_tot", out["dt"]), ("F_up_tot", out["ut"])):
         assert_close(got.get(), r[name], "wide integrate: " + name, rtol=1e-12)
     assert np.array_equal(out["net"].get(), out["ut"].get() - out["dt"].get())
+
+
+@pytest.mark.parametrize("config", ["C1", "C2"])
+def test_known_zero_beam_fast_path_is_bit_identical(ctx, config):
+    """With dir_beam = 0 fdir_* writes -0.0 everywhere; the library remembers that and fband_* then skips loading
+    the beam arrays and G+/- (fband_cp.cu: no_beam).  Re-uploading the same F_dir makes the library forget, so
+    the generic path runs: both must give the same bits."""
+    q = synthetic.make_store(config, ctx=ctx, **SMALL)
+    q.dir_beam = np.int32(0)
+    n = int(q.nlayer)
+    q.T_lay = np.concatenate([np.linspace(2300.0, 900.0, n), [2400.0]])
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    steps = ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+             "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass"]
+    if q.clouds == 1:
+        steps.append("calc_total_g_0_of_gas_and_clouds")
+    steps += ["calculate_transmission", "calculate_direct_beamflux"]
+    for m in steps:
+        getattr(comp, m)(q)
+    assert not np.any(q.dev_F_dir_wg.get() != 0.0)
+    names = ["F_down_wg", "F_up_wg"] + ([] if q.iso == 1 else ["Fc_down_wg", "Fc_up_wg"])
+    results = []
+    for forget in (False, True):
+        comp.calculate_direct_beamflux(q)          # (re-)establishes the known-zero state
+        if forget:
+            q.dev_F_dir_wg.set(q.dev_F_dir_wg.get())  # any write from outside clears it
+        for name in names:
+            getattr(q, "dev_" + name).fill_zero()
+        for _ in range(2):
+            comp.populate_spectral_flux_iteratively(q)
+        results.append([getattr(q, "dev_" + name).get() for name in names])
+    for name, a, b in zip(names, *results):
+        assert np.array_equal(a, b), name

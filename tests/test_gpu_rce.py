@@ -98,33 +98,39 @@ def test_converged_profile_and_spectrum_match_reference_kernels(ctx, config):
     convergence basin |dF| / F < rad_convergence_limit.  Where the profile is well determined by that
     criterion (C1) the two agree to ~1e-6 K.  In C2 the deep, optically thick layers are only weakly
     constrained by it (dF/dT is ~1e-4 of the optically thin value), so the honest yardstick is the reference's
-    own spread: the same loop driven by the reference's kernels from a start profile perturbed by 1e-9 K.
-    Bars (BASELINE.json): T-P within 0.01 K and TOA spectrum within 1e-8 -- or within 3x the reference's own
-    spread where that spread exceeds them."""
+    own spread: the same loop driven by the reference's kernels from three start profiles 1e-9 K apart (the
+    reference's trajectory is not even reproducible run to run; its iteration count varies by tens of percent).
+    Bars (BASELINE.json): T-P within 0.01 K and TOA spectrum within 1e-8 of the nearest reference run -- or
+    within 2x the reference's own run-to-run spread where that spread exceeds them."""
     if not ref_gpu.available():
         pytest.skip("reference cubin not built")
     lock = _lockstep(ctx, config)
     ours = _run(ctx, config, backed=False)
-    ref = _run(ctx, config, backed=True)
-    ref2 = _run(ctx, config, backed=True, perturb=1e-9)
+    refs = [_run(ctx, config, backed=True, perturb=p) for p in (0.0, 1e-9, -1e-9)]
 
     def spec_diff(a, b):
         return float(np.max(np.abs(a["toa"] - b["toa"]) / np.maximum(np.abs(b["toa"]), 1e-6 * np.max(np.abs(b["toa"])))))
 
-    dT = float(np.max(np.abs(ours["T"] - ref["T"])))
-    dT_rad = float(np.max(np.abs(ours["T_rad"] - ref["T_rad"])))
-    spread_T = float(np.max(np.abs(ref2["T"] - ref["T"])))
-    spec, spread_spec = spec_diff(ours, ref), spec_diff(ref2, ref)
-    print("\n[rce] %s: lock-step 25 iterations max rel dT %.1e; radiation loop %d (ours) / %d (kernels.cu) / %d "
-          "(kernels.cu, start + 1e-9 K) iterations, convection loop %d / %d; max |dT| ours-vs-ref %.2e K "
-          "(after the radiation loop %.2e K), ref-vs-ref spread %.2e K; TOA spectrum rel. diff %.2e (ref-vs-ref %.2e)" %
-          (config, lock, ours["rad_iters"], ref["rad_iters"], ref2["rad_iters"], ours["conv_iters"],
-           ref["conv_iters"], dT, dT_rad, spread_T, spec, spread_spec))
+    def t_diff(a, b, key="T"):
+        return float(np.max(np.abs(a[key] - b[key])))
+
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    spread_T = max(t_diff(refs[i], refs[j]) for i, j in pairs)
+    spread_spec = max(spec_diff(refs[i], refs[j]) for i, j in pairs)
+    # ours is as close to SOME run of the reference as the reference's runs are to each other
+    dT = min(t_diff(ours, r) for r in refs)
+    dT_rad = min(t_diff(ours, r, "T_rad") for r in refs)
+    spec = min(spec_diff(ours, r) for r in refs)
+    print("\n[rce] %s: lock-step 25 iterations max rel dT %.1e; radiation loop %d (ours) / %s (kernels.cu, three starts "
+          "1e-9 K apart) iterations, convection loop %d / %d; max |dT| ours-vs-nearest-ref %.2e K (after the radiation "
+          "loop %.2e K), ref-vs-ref spread %.2e K; TOA spectrum rel. diff %.2e (ref-vs-ref %.2e)" %
+          (config, lock, ours["rad_iters"], [r["rad_iters"] for r in refs], ours["conv_iters"], refs[0]["conv_iters"],
+           dT, dT_rad, spread_T, spec, spread_spec))
     assert lock < 1e-9, lock
     assert ours["rad_iters"] > 50, "the loop did not iterate"
-    assert dT <= max(0.01, 3 * spread_T), (dT, spread_T)
-    assert dT_rad <= max(0.01, 3 * spread_T), (dT_rad, spread_T)
-    assert spec <= max(1e-8, 3 * spread_spec), (spec, spread_spec)
+    assert dT <= max(0.01, 2 * spread_T), (dT, spread_T)
+    assert dT_rad <= max(0.01, 2 * spread_T), (dT_rad, spread_T)
+    assert spec <= max(1e-8, 2 * spread_spec), (spec, spread_spec)
     # radiative equilibrium: F_net == F_intern at every interface of the radiative zone (K:2751, known-answer iii)
     if ours["conv"] == 0:
         scale = ours["Fdn_top"] + ours["F_intern"]
