@@ -314,32 +314,83 @@ def bench_c4(ctx, rank, world, steps, warmup, flush, nbin=100000, scat=1, dim=80
 
 
 def rce_leg(ctx, workload, seed_offset=0):
-    """converged RCE atmospheres per hour: the radiation loop (+ convection loop) of one atmosphere from the
-    standard isothermal start to the reference's own convergence criterion, wall clock, host logic included"""
+    """converged RCE atmospheres per hour: one atmosphere from the standard isothermal start to the reference's own
+    convergence criterion, wall clock with all host logic included.  Two drivers of the same kernels:
+      host_loop    Compute.radiation_loop + convection_loop: the reference's loop structure (one poll per iteration)
+      device_loop  BatchCompute.radiation_loop with nbatch = 1: iteration counter and convergence latch on the
+                   device, blocks of 10 iterations replayed as one CUDA graph; bit-identical result
+                   (tests/test_gpu_batch.py); the convection loop then runs on the host loop as in the reference"""
     from helios_b200 import synthetic
+    from helios_b200.batch import make_batch
     from helios_b200.computation import Compute
-    q = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)
-    synthetic.upload(q)
-    comp = Compute(ctx, verbose=False)
-    comp.construct_planck_table(q)
-    comp.correct_incident_energy(q)
+    out = {}
+    for mode in ("host_loop", "device_loop"):
+        q = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)
+        status = "converged"
+        conv_iters = 0
+        if mode == "host_loop":
+            synthetic.upload(q)
+            comp = Compute(ctx, verbose=False)
+            comp.construct_planck_table(q)
+            comp.correct_incident_energy(q)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            try:
+                comp.radiation_loop(q, None, None, None)
+                rad_iters = int(q.iter_value)
+                if q.convection == 1:
+                    comp.convection_loop(q, None, None, None)
+                    conv_iters = int(q.iter_value)
+            except SystemExit:
+                status, rad_iters = "iteration limit", int(q.iter_value)
+        else:
+            single = synthetic.upload(q)
+            qb, bcomp = make_batch([synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)], ctx)
+            comp = Compute(ctx, verbose=False)
+            bcomp.construct_planck_table(qb)
+            bcomp.correct_incident_energy(qb)
+            comp.construct_planck_table(single)
+            comp.correct_incident_energy(single)
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            try:
+                bcomp.radiation_loop(qb)
+                rad_iters = int(qb.converged_at[0])
+                if q.convection == 1:
+                    # hand the converged state over to the host-driven convection loop (C:992-1174)
+                    for name in ("T_lay", "F_net", "F_up_tot", "F_down_tot", "abort", "T_store", "delta_t_prefactor"):
+                        getattr(single, "dev_" + name).copy_from(getattr(qb, "dev_" + name))
+                    single.marked_red = (single.dev_abort.get() == 0).astype(np.float64)
+                    comp.convection_loop(single, None, None, None)
+                    conv_iters = int(single.iter_value)
+            except SystemExit:
+                status, rad_iters = "iteration limit", int(qb.iter_value)
+            del qb, bcomp
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        out[mode] = {"seconds": dt, "radiation_iterations": rad_iters, "convection_iterations": conv_iters,
+                     "status": status, "ms_per_iteration": 1e3 * dt / max(1, rad_iters + conv_iters)}
+    return out
+
+
+def rce_batch(ctx, nbatch=32):
+    """the same for a grid of C1 atmospheres advanced together (one launch per kernel for the whole batch)"""
+    from helios_b200 import synthetic, sharding
+    from helios_b200.batch import make_batch
+    params = sharding.partition_atmospheres(synthetic.grid_parameters(), 0, 1024 // nbatch)
+    qb, comp = make_batch(synthetic.make_grid_stores(params, config="C1", ctx=ctx), ctx)
+    comp.construct_planck_table(qb)
+    comp.correct_incident_energy(qb)
     ctx.synchronize()
     t0 = time.perf_counter()
-    status = "converged"
-    try:
-        comp.radiation_loop(q, None, None, None)
-        rad_iters = int(q.iter_value)
-        conv_iters = 0
-        if q.convection == 1:
-            comp.convection_loop(q, None, None, None)
-            conv_iters = int(q.iter_value)
-    except SystemExit:
-        status = "iteration limit"
-        rad_iters, conv_iters = int(q.iter_value), 0
+    comp.radiation_loop(qb)
     ctx.synchronize()
     dt = time.perf_counter() - t0
-    return {"seconds": dt, "radiation_iterations": rad_iters, "convection_iterations": conv_iters, "status": status,
-            "ms_per_iteration": 1e3 * dt / max(1, rad_iters + conv_iters)}
+    at = [int(v) for v in qb.converged_at]
+    return {"atmospheres": nbatch, "seconds": dt, "atmospheres_per_hour": nbatch * 3600.0 / dt,
+            "iterations_to_convergence_min_max": [min(at), max(at)], "iterations_run": int(qb.iter_value),
+            "what": "BatchCompute.radiation_loop: %d C1 atmospheres of the T_star x log g x opacity grid advanced together "
+                    "to the reference's convergence criterion, converged ones frozen by the on-device latch" % nbatch}
 
 
 def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload):
@@ -433,6 +484,7 @@ def run_ours(args):
                                           r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5"),
                     "setup_s": time.perf_counter() - t0}
                 del r
+                extra["C5_batched_grid"]["rce"] = rce_batch(ctx, 32)
             except Exception as e:  # noqa: BLE001 -- the main line must survive a failing extra
                 extra["C5_batched_grid"] = {"error": repr(e)}
             r = None
@@ -526,12 +578,13 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     barrier()
     rce = None
     if not args.no_rce:
-        rce = rce_leg(ctx, args.workload, seed_offset=rank)
+        legs = rce_leg(ctx, args.workload, seed_offset=rank)
         barrier()
-        rce_s = reduce_max([rce["seconds"]])[0]
-        rce = dict(rce, atmospheres_per_hour=world * 3600.0 / rce_s, seconds_max_over_ranks=rce_s,
-                   what="radiation_loop + convection_loop of one %s atmosphere per GPU from the isothermal start to the "
-                        "reference's convergence criterion (rad_convergence_limit 1e-8), wall clock incl. host logic" % args.workload)
+        rce_s = reduce_max([legs["device_loop"]["seconds"]])[0]
+        rce = dict(legs, atmospheres_per_hour=world * 3600.0 / rce_s, seconds_max_over_ranks=rce_s,
+                   what="one %s atmosphere per GPU from the isothermal start to the reference's convergence criterion "
+                        "(rad_convergence_limit 1e-8): radiation loop on the device (CUDA-graph blocks of 10 iterations) + "
+                        "convection loop, wall clock incl. host logic; host_loop = the reference's loop structure" % args.workload)
     t_solve, t_fband, t_e2e = reduce_max([t_solve, t_fband, t_e2e])
     line = dict(base, value=world * points * args.steps / (t_solve * 1e-3), ms_per_step=t_solve / args.steps,
                 scaling="weak",

@@ -133,6 +133,36 @@ def _as_arg(a):
     return a
 
 
+# ----------------------------------------------------------------------------- CUDA graphs
+class Graph:
+    """a recorded launch sequence (helios_graph_*): `with ctx.capture() as g: ...launches...`, then g.launch()"""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+        self._g = ctypes.c_void_p()
+
+    def __enter__(self):
+        _check(lib().helios_graph_begin(self._ctx.handle), "helios_graph_begin")
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        rc = lib().helios_graph_end(self._ctx.handle, ctypes.byref(self._g))
+        if exc_type is None:
+            _check(rc, "helios_graph_end")
+        return False
+
+    def launch(self):
+        _check(lib().helios_graph_launch(self._ctx.handle, self._g), "helios_graph_launch")
+
+    def __del__(self):
+        try:
+            if self._g.value:
+                lib().helios_graph_destroy(self._g)
+                self._g = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
 # ----------------------------------------------------------------------------- context
 class Context:
     """One device + one stream.  Replaces `import pycuda.autoinit` (computation.py:24)."""
@@ -207,6 +237,9 @@ class Context:
         a = DeviceArray(self, h.shape, h.dtype)
         a.set(h)
         return a
+
+    def capture(self) -> "Graph":
+        return Graph(self)
 
     # -- events
     def event(self) -> "Event":

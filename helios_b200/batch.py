@@ -110,10 +110,22 @@ class BatchStore(Store):
             self.ctx.handle, self.nbatch, int(self.nlayer), nb, ny, ctypes.c_void_p(self.dev_table_index.ptr),
             ntp * nb * ny, ntp * nb, ntp, ctypes.c_void_p(self.dev_g_batch.ptr), ctypes.c_void_p(self.dev_planck_star.ptr)),
             "helios_ctx_set_batch")
+        self._entered = True
 
     def leave(self):
-        backend._check(backend.lib().helios_ctx_set_batch(self.ctx.handle, 1, 0, 0, 0, None, 0, 0, 0, None, None),
+        backend._check(backend.lib().helios_ctx_set_batch(self.ctx.handle, 0, 0, 0, 0, None, 0, 0, 0, None, None),
                        "helios_ctx_set_batch")
+        self._entered = False
+
+    def state(self, reset=False):
+        """(done flags, iteration counts at which they latched, device iteration counter)"""
+        done = np.zeros(self.nbatch, np.int32)
+        at = np.zeros(self.nbatch, np.int32)
+        it = np.zeros(1, np.int32)
+        backend._check(backend.lib().helios_ctx_batch_state(
+            self.ctx.handle, done.ctypes.data_as(ctypes.c_void_p), at.ctypes.data_as(ctypes.c_void_p),
+            it.ctypes.data_as(ctypes.c_void_p), 1 if reset else 0), "helios_ctx_batch_state")
+        return done, at, int(it[0])
 
     def atmosphere(self, name, b):
         """host copy of atmosphere b's block of a per-atmosphere device array"""
@@ -129,25 +141,29 @@ class BatchCompute(Compute):
         """shared rows T = 1 + t*step once; one stellar row per atmosphere (K:362-416 with dim = 0 computes
         exactly the row T = T_star)"""
         q = quant
-        q.leave()
+        was_entered = getattr(q, "_entered", False)
+        q.leave()  # the set-up kernels are single-atmosphere launches
         self.ctx.call("plancktable", q.dev_planckband_grid, q.dev_opac_interwave, q.dev_opac_deltawave, q.nbin,
                       float(q.T_star_batch[0]), q.plancktable_dim, q.plancktable_step)
         nb = int(q.nbin)
         for b in range(q.nbatch):
             self.ctx.call("plancktable", q.dev_planck_star.view(b * nb, nb), q.dev_opac_interwave, q.dev_opac_deltawave,
                           q.nbin, float(q.T_star_batch[b]), 0, q.plancktable_step)
-        q.enter()
+        if was_entered:
+            q.enter()
 
     def correct_incident_energy(self, quant):
         q = quant
         nb = int(q.nbin)
+        was_entered = getattr(q, "_entered", False)
         q.leave()
         for b in range(q.nbatch):
             if q.energy_correction == 1 and q.T_star_batch[b] > 10:
                 star = q.dev_starflux.view(b * nb, nb) if q.real_star == 1 else None
                 self.ctx.call("corr_inc_energy", q.dev_planck_star.view(b * nb, nb), star, q.dev_opac_deltawave,
                               q.real_star, q.nbin, float(q.T_star_batch[b]), 0, None)
-        q.enter()
+        if was_entered:
+            q.enter()
 
     def _heights(self, quant):
         """H:673-698 per atmosphere (host side, every 10th iteration)"""
@@ -175,54 +191,84 @@ class BatchCompute(Compute):
         self._heights(quant)
         self.calculate_direct_beamflux(quant)
 
-    def _abort_sums(self, quant):
-        self.ctx.call("abort_sum", quant.dev_abort, int(quant.nlayer) + 1, quant.dev_abort_sums)
-        return quant.dev_abort_sums.get()
-
-    def radiation_loop(self, quant, write=None, read=None, rt_plot=None, poll_every=1):
-        """C:851-984 for nbatch atmospheres at once.  `converged_at[b]` is the iteration count at which
-        atmosphere b met the criterion (identical to `iter_value` of its single-atmosphere run)."""
+    def _iteration(self, quant, refresh, heights=True):
+        """one RT iteration of C:851-984 on the device (the temperature step reads the device iteration counter)"""
         q = quant
+        self.interpolate_temperatures(q)
+        self.interpolate_planck(q)
+        if refresh:
+            self.interpolate_opacities_and_scattering_cross_sections(q)
+            self.interpolate_meanmolmass(q)
+            if q.clouds == 1:
+                self.calc_total_g_0_of_gas_and_clouds(q)
+            self.calculate_transmission(q)
+            self.calculate_delta_z(q)
+            if heights:
+                self._heights(q)
+            self.calculate_direct_beamflux(q)
+        self.populate_spectral_flux_iteratively(q)
+        self.integrate_flux(q)
+        self.rad_temp_iteration(q)
+        self.ctx.call("abort_sum", q.dev_abort, int(q.nlayer) + 1, q.dev_abort_sums)
+        self.ctx.call("batch_iter_advance")
+
+    def radiation_loop(self, quant, write=None, read=None, rt_plot=None, graph=True):
+        """C:851-984 for nbatch atmospheres at once, bookkeeping on the device.
+
+        The iteration counter, the per-atmosphere convergence latch and the iteration count at which each
+        atmosphere converged live on the device, so a block of 10 iterations (one opacity refresh + 10 flux
+        solves and temperature steps, the reference's schedule C:860) is replayed as ONE CUDA graph and the host
+        looks at the state once per block.  Converged atmospheres are frozen by the latch, so the (up to 9)
+        iterations a block runs past an atmosphere's convergence do not touch it: `converged_at[b]` and the final
+        state equal `iter_value` and the state of its single-atmosphere run.  The altitude grid (host side,
+        H:673) feeds no kernel without the geometric zenith correction and is evaluated once at the end."""
+        q = quant
+        if int(q.foreplay) != 0 or q.physical_tstep != 0 or q.singlewalk == 1:
+            raise ValueError("the batched loop covers the default iterative run (foreplay = 0, no physical timestep)")
         q.enter()
-        backend._check(backend.lib().helios_ctx_batch_done(self.ctx.handle, None, 1), "helios_ctx_batch_done")
-        full = int(q.nlayer) + 1
-        q.iter_value = np.int32(0)
-        q.converged_at = np.zeros(q.nbatch, np.int64)
+        q.iter_value = np.int32(0)  # the kernels read the device counter; the argument is ignored
+        lib = backend.lib()
+        backend._check(lib.helios_ctx_batch_device_iteration(self.ctx.handle, 1), "helios_ctx_batch_device_iteration")
+        q.state(reset=True)
         ev = (self.ctx.event(), self.ctx.event())
         ev[0].record()
+        block = 10
+        graphs = {}
         try:
-            while True:
-                it = int(q.iter_value)
-                self.interpolate_temperatures(q)
-                self.interpolate_planck(q)
-                if it % 10 == 0:
-                    self._refresh_atmosphere(q)
-                self.populate_spectral_flux_iteratively(q)
-                self.integrate_flux(q)
-                if q.singlewalk == 1:
-                    break
-                if it >= q.foreplay:
-                    self.rad_temp_iteration(q)
-                    if it % poll_every == 0:
-                        sums = self._abort_sums(q)
-                        newly = (sums == full) & (q.converged_at == 0)
-                        q.converged_at[newly] = it + 1
-                q.iter_value = np.int32(it + 1)
-                it += 1
+            # the first block runs eagerly: it sizes the library's scratch buffers, which must not grow while capturing
+            for k in range(block):
+                self._iteration(q, refresh=(k == 0), heights=False)
+            done, at, it = q.state()
+            while not done.all():
+                limit = float(q.rad_convergence_limit)
+                if graph:
+                    if limit not in graphs:
+                        with self.ctx.capture() as g:
+                            for k in range(block):
+                                self._iteration(q, refresh=(k == 0), heights=False)
+                        graphs[limit] = g
+                    graphs[limit].launch()
+                else:
+                    for k in range(block):
+                        self._iteration(q, refresh=(k == 0), heights=False)
+                done, at, it = q.state()
                 if self.verbose and it % 100 == 0:
-                    print("batch iteration %d: %d of %d atmospheres converged" % (it, int((q.converged_at > 0).sum()), q.nbatch))
-                if np.all(q.converged_at > 0):
-                    break
-                if q.crit_relaxation_numbers is not None and it in q.crit_relaxation_numbers:
-                    self.hsfunc.relax_radiative_convergence_criterion(q)
+                    print("batch iteration %d: %d of %d atmospheres converged" % (it, int(done.sum()), q.nbatch))
+                for n_relax in (q.crit_relaxation_numbers or []):
+                    if it - block < n_relax <= it:
+                        self.hsfunc.relax_radiative_convergence_criterion(q)
                 if it > q.max_nr_iterations:
                     print("\nRun exceeds allowed maximum allowed number of iteration steps. Aborting...")
                     raise SystemExit()
+            q.converged_at = at.astype(np.int64)
+            q.iter_value = np.int32(it)
+            self._heights(q)
         finally:
             ev[1].record()
             ev[1].synchronize()
             self.stats["radiation_loop_ms"] = ev[0].time_till(ev[1])
             self.stats["radiation_iterations"] = int(q.iter_value)
+            backend._check(lib.helios_ctx_batch_device_iteration(self.ctx.handle, 0), "helios_ctx_batch_device_iteration")
             q.leave()
 
     def convection_loop(self, quant, write=None, read=None, rt_plot=None):

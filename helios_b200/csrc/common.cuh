@@ -26,13 +26,17 @@ struct helios_comm_state;
 // arrays; their strides follow from the shape by the reference's allocation sizes (Q:400-409, 411-461,
 // 613-665), collected here once.
 struct BatchDesc {
-    int nbatch = 1;  // 1 = batch mode off
+    bool active = false;  // batch mode on (nbatch may be 1: a single atmosphere with the on-device bookkeeping)
+    int nbatch = 1;
     int nlayer = 0, nbin = 0, ny = 0;
     const int* table_index = nullptr;     // device [nbatch]: which opacity table an atmosphere reads (null: 0)
     size_t ktable_stride = 0, cross_stride = 0, mmass_stride = 0;  // doubles between consecutive tables
     const double* g = nullptr;            // device [nbatch]: surface gravity (null: the scalar argument)
     const double* planck_star = nullptr;  // device [nbatch][nbin]: stellar Planck row of each atmosphere
     int* done = nullptr;                  // device [nbatch]: converged flags, owned by the context
+    int* converged_at = nullptr;          // device [nbatch]: iteration count at which done[b] latched
+    int* iter_dev = nullptr;              // device [1]: iteration counter (rad_temp_iter reads it when `use_iter_dev`)
+    bool use_iter_dev = false;
     __host__ __device__ int nint() const { return nlayer + 1; }
     __host__ __device__ size_t wg() const { return (size_t)(nlayer + 1) * nbin * ny; }  // every [i][x][y] array (Q:407)
     __host__ __device__ size_t band_lay() const { return (size_t)nlayer * nbin; }
@@ -56,6 +60,8 @@ struct helios_ctx {
     size_t scratch_bytes = 0;
     helios_comm_state* comm = nullptr;
     BatchDesc batch;
+    bool capturing = false;  // helios_graph_begin .. helios_graph_end
+    unsigned long long capture_launches0 = 0;
     // Direct-beam arrays known to hold only (signed) zeros: written by fdir_* with dir_beam == 0 and not
     // touched since (every write to device memory goes through this library).  fband_* then skips loading
     // them and the G+/- coefficient arrays that only multiply them.  [0] = F_dir_wg, [1] = Fc_dir_wg.
@@ -112,7 +118,7 @@ int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out);
 // entry points that have no batched form refuse to run in batch mode instead of silently doing one atmosphere
 #define HNOBATCH(ctx)                                                          \
     do {                                                                       \
-        if ((ctx)->batch.nbatch > 1) {                                         \
+        if ((ctx)->batch.active) {                                         \
             helios_set_error("%s: not available in batch mode", __func__);     \
             return HELIOS_ERR_STATE;                                           \
         }                                                                      \
@@ -121,7 +127,7 @@ int helios_ctx_scratch(helios_ctx* ctx, size_t nbytes, double** out);
 // batch mode: the call's dimensions must be the ones the batch was declared with
 #define HBATCHDIMS(ctx, cond)                                                  \
     do {                                                                       \
-        if ((ctx)->batch.nbatch > 1 && !(cond)) {                              \
+        if ((ctx)->batch.active && !(cond)) {                              \
             helios_set_error("%s: dimensions differ from helios_ctx_set_batch: %s", __func__, #cond); \
             return HELIOS_ERR_ARG;                                             \
         }                                                                      \

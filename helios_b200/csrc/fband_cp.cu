@@ -420,7 +420,7 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (nchunk > LPC || smem > 227 * 1024) return -1;
     const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
     s.nbatch = ctx->batch.nbatch;
-    s.done = ctx->batch.nbatch > 1 ? ctx->batch.done : nullptr;
+    s.done = ctx->batch.active ? ctx->batch.done : nullptr;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
     if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
     if (per_sm < 1) per_sm = 1;

@@ -148,6 +148,7 @@ struct TempScalars {
     double f_factor, g, physical_tstep, local_limit, F_intern;
     const int* done;        // batch: atmospheres that have converged are left untouched
     const double* g_batch;  // batch: per-atmosphere gravity
+    const int* iter_dev;    // batch with the on-device iteration counter: overrides itervalue
 };
 
 __global__ void __launch_bounds__(256)
@@ -159,6 +160,7 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
             double* __restrict__ F_smooth, double* __restrict__ F_smooth_sum,
             const double* __restrict__ c_p_lay, const double* __restrict__ mmm_lay, TempScalars s) {
     const int nl = s.numlayers;
+    if (s.iter_dev != nullptr) s.itervalue = *s.iter_dev;
     if (gridDim.x > 1 || s.done != nullptr) {  // batch (blockIdx.x = atmosphere)
         const size_t a = blockIdx.x;
         if (s.done != nullptr && s.done[a] != 0) return;
@@ -265,7 +267,8 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
 // conv_temp_iter's smoothing branch differs slightly (no i > 0 guard in the reference, K:2808, which
 // reads tlay[-1]); the guarded form is used for both.
 
-__global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict__ out, int* __restrict__ done) {
+__global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict__ out, int* __restrict__ done,
+                            int* __restrict__ converged_at, const int* __restrict__ iter_dev) {
     __shared__ int red[256];
     abrt += (size_t)blockIdx.x * n;  // batch (blockIdx.x = atmosphere)
     out += blockIdx.x;
@@ -279,7 +282,10 @@ __global__ void k_abort_sum(const int* __restrict__ abrt, int n, int* __restrict
     }
     if (threadIdx.x == 0) {
         out[0] = red[0];
-        if (done != nullptr && red[0] == n) done[blockIdx.x] = 1;  // latched: see helios_ctx_set_batch
+        if (done != nullptr && red[0] == n && done[blockIdx.x] == 0) {  // latched: see helios_ctx_set_batch
+            done[blockIdx.x] = 1;
+            if (iter_dev != nullptr) converged_at[blockIdx.x] = *iter_dev + 1;  // iterations completed
+        }
     }
 }
 
@@ -477,10 +483,11 @@ int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double
     HARG(physical_tstep == 0 || (c_p_lay != nullptr && meanmolmass_lay != nullptr));
     HARG(numlayers > 1 && adapt_interval > 0);
     HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer);
-    const bool batched = ctx->batch.nbatch > 1;
+    const bool batched = ctx->batch.active;
     TempScalars s{itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, 0,
                   f_factor, g, physical_tstep, local_limit, F_intern,
-                  batched ? ctx->batch.done : nullptr, batched ? ctx->batch.g : nullptr};
+                  batched ? ctx->batch.done : nullptr, batched ? ctx->batch.g : nullptr,
+                  (batched && ctx->batch.use_iter_dev) ? ctx->batch.iter_dev : nullptr};
     k_temp_iter<<<ctx->batch.nbatch, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
                                             deltat_prefactor, nullptr, F_add_heat_lay, F_add_heat_sum,
                                             F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay, s);
@@ -501,7 +508,7 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
     HARG(numlayers > 1 && adapt_interval > 0);
     HNOBATCH(ctx);
     TempScalars s{itervalue, 0, numlayers, adapt_interval, smooth, 0, 0, 0, 1, 0.0, 0.0, 0.0, 0.0, F_intern,
-                  nullptr, nullptr};
+                  nullptr, nullptr, nullptr};
     k_temp_iter<<<1, 256, 0, ctx->stream>>>(nullptr, F_net, F_net_diff, tlay, play, pint, nullptr, T_store,
                                             deltat_prefactor, marked_red, F_add_heat_lay, nullptr, F_smooth,
                                             F_smooth_sum, nullptr, nullptr, s);
@@ -513,8 +520,22 @@ int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev) {
     HCTX(ctx);
     HARG(abrt && sum_dev && n > 0);
     HBATCHDIMS(ctx, n == ctx->batch.nlayer + 1);
-    k_abort_sum<<<ctx->batch.nbatch, 256, 0, ctx->stream>>>(abrt, n, sum_dev,
-                                                            ctx->batch.nbatch > 1 ? ctx->batch.done : nullptr);
+    const BatchDesc& bd = ctx->batch;
+    k_abort_sum<<<bd.nbatch, 256, 0, ctx->stream>>>(abrt, n, sum_dev, bd.active ? bd.done : nullptr, bd.converged_at,
+                                                    (bd.active && bd.use_iter_dev) ? bd.iter_dev : nullptr);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+__global__ void k_iter_advance(int* iter_dev) { iter_dev[0] += 1; }
+
+int helios_batch_iter_advance(helios_ctx* ctx) {
+    HCTX(ctx);
+    if (!ctx->batch.active) {
+        helios_set_error("helios_batch_iter_advance: not in batch mode");
+        return HELIOS_ERR_STATE;
+    }
+    k_iter_advance<<<1, 1, 0, ctx->stream>>>(ctx->batch.iter_dev);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }

@@ -337,7 +337,7 @@ int helios_planck_interpol_layer(helios_ctx* ctx, const double* temp, double* pl
     dim3 grid(ceil_div(nwave, 32), ceil_div(nrows, 32), ctx->batch.nbatch);
     k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_lay, planck_grid, starflux,
                                                      realstar, 0, numlayers, nrows, nwave, dim, step,
-                                                     ctx->batch.nbatch > 1 ? ctx->batch.planck_star : nullptr);
+                                                     ctx->batch.active ? ctx->batch.planck_star : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -367,7 +367,7 @@ static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gt
     // keep clear of the first 64 bytes, which small reductions use
     PTBox* box = reinterpret_cast<PTBox*>(reinterpret_cast<char*>(scratch) + 64);
     // batch: T_lay carries the surface value behind the nlayer layer values, T_int has exactly n entries
-    const int tstride = (nb > 1 && n == bd.nlayer) ? n + 1 : n;
+    const int tstride = (bd.active && n == bd.nlayer) ? n + 1 : n;
     k_pt_prep<<<dim3(ceil_div(n, 128), nb), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
                                                                    clamp_mode, 0, box, tstride);
     HLAUNCHED(ctx);
@@ -378,8 +378,8 @@ static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gt
     // per-atmosphere output strides: every [i][x][y] array is allocated with ninterface rows (Q:407), the
     // [i][x] cross-section arrays with exactly n rows
     k_pt_gather<<<grid, 256, 0, ctx->stream>>>(box, table, out, rowlen, table2, out2, rowlen2, npress, n,
-                                               nb > 1 ? bd.table_index : nullptr, bd.ktable_stride, bd.cross_stride,
-                                               nb > 1 ? bd.wg() : 0, (size_t)n * rowlen2);
+                                               bd.active ? bd.table_index : nullptr, bd.ktable_stride, bd.cross_stride,
+                                               bd.active ? bd.wg() : 0, (size_t)n * rowlen2);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -415,10 +415,10 @@ static int pt_scalar(helios_ctx* ctx, const double* temp, const double* gtemp, c
     const BatchDesc& bd = ctx->batch;
     if (!batched) HNOBATCH(ctx);
     const int nb = bd.nbatch;
-    const int tstride = (nb > 1 && n == bd.nlayer) ? n + 1 : n;
+    const int tstride = (bd.active && n == bd.nlayer) ? n + 1 : n;
     k_pt_scalar<<<dim3(ceil_div(n, 128), nb), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
                                                                      log_t, tab, out, tstride,
-                                                                     nb > 1 ? bd.table_index : nullptr,
+                                                                     bd.active ? bd.table_index : nullptr,
                                                                      bd.mmass_stride);
     HLAUNCHED(ctx);
     return HELIOS_OK;

@@ -74,6 +74,7 @@ int helios_ctx_create(int device, helios_ctx** out) {
 }
 
 int helios_comm_destroy(helios_ctx* ctx);
+static void batch_release(helios_ctx* ctx);
 
 int helios_ctx_destroy(helios_ctx* ctx) {
     if (ctx == nullptr) return HELIOS_OK;
@@ -83,7 +84,7 @@ int helios_ctx_destroy(helios_ctx* ctx) {
     for (auto& kv : ctx->allocs) cudaFree(kv.first);
     ctx->allocs.clear();
     if (ctx->scratch) cudaFree(ctx->scratch);
-    if (ctx->batch.done) cudaFree(ctx->batch.done);
+    batch_release(ctx);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -125,20 +126,22 @@ int helios_ctx_launch_count(helios_ctx* ctx, unsigned long long* count) {
     return HELIOS_OK;
 }
 
+static void batch_release(helios_ctx* ctx) {
+    if (ctx->batch.done) cudaFree(ctx->batch.done);
+    ctx->batch = BatchDesc();
+}
+
 int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int ny, const int* table_index,
                          size_t ktable_stride, size_t crosstable_stride, size_t meanmass_stride, const double* g,
                          const double* planck_star) {
     HCTX(ctx);
-    HARG(nbatch >= 1);
+    HARG(nbatch >= 0);
     HCUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->batch.done) {
-        cudaFree(ctx->batch.done);
-        ctx->batch.done = nullptr;
-    }
-    ctx->batch = BatchDesc();
-    if (nbatch == 1) return HELIOS_OK;
+    batch_release(ctx);
+    if (nbatch == 0) return HELIOS_OK;
     HARG(nlayer > 1 && nbin > 0 && ny > 0);
     BatchDesc b;
+    b.active = true;
     b.nbatch = nbatch;
     b.nlayer = nlayer;
     b.nbin = nbin;
@@ -149,24 +152,102 @@ int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int 
     b.mmass_stride = meanmass_stride;
     b.g = g;
     b.planck_star = planck_star;
-    HCUDA(cudaMalloc((void**)&b.done, sizeof(int) * (size_t)nbatch));
-    HCUDA(cudaMemset(b.done, 0, sizeof(int) * (size_t)nbatch));
+    // done[nbatch] | converged_at[nbatch] | iteration counter
+    const size_t n = 2 * (size_t)nbatch + 1;
+    HCUDA(cudaMalloc((void**)&b.done, sizeof(int) * n));
+    HCUDA(cudaMemset(b.done, 0, sizeof(int) * n));
+    b.converged_at = b.done + nbatch;
+    b.iter_dev = b.done + 2 * nbatch;
     ctx->batch = b;
     return HELIOS_OK;
 }
 
-int helios_ctx_batch_done(helios_ctx* ctx, int* done_host, int reset) {
+int helios_ctx_batch_state(helios_ctx* ctx, int* done_host, int* converged_at_host, int* iter_host, int reset) {
     HCTX(ctx);
-    if (ctx->batch.nbatch <= 1) {
-        helios_set_error("helios_ctx_batch_done: not in batch mode");
+    if (!ctx->batch.active) {
+        helios_set_error("helios_ctx_batch_state: not in batch mode");
         return HELIOS_ERR_STATE;
     }
-    if (reset) HCUDA(cudaMemsetAsync(ctx->batch.done, 0, sizeof(int) * (size_t)ctx->batch.nbatch, ctx->stream));
-    if (done_host) {
-        HCUDA(cudaMemcpyAsync(done_host, ctx->batch.done, sizeof(int) * (size_t)ctx->batch.nbatch,
-                              cudaMemcpyDeviceToHost, ctx->stream));
-        HCUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t nb = (size_t)ctx->batch.nbatch;
+    if (reset) HCUDA(cudaMemsetAsync(ctx->batch.done, 0, sizeof(int) * (2 * nb + 1), ctx->stream));
+    if (done_host)
+        HCUDA(cudaMemcpyAsync(done_host, ctx->batch.done, sizeof(int) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (converged_at_host)
+        HCUDA(cudaMemcpyAsync(converged_at_host, ctx->batch.converged_at, sizeof(int) * nb, cudaMemcpyDeviceToHost,
+                              ctx->stream));
+    if (iter_host)
+        HCUDA(cudaMemcpyAsync(iter_host, ctx->batch.iter_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (done_host || converged_at_host || iter_host) HCUDA(cudaStreamSynchronize(ctx->stream));
+    return HELIOS_OK;
+}
+
+int helios_ctx_batch_device_iteration(helios_ctx* ctx, int enable) {
+    HCTX(ctx);
+    if (!ctx->batch.active) {
+        helios_set_error("helios_ctx_batch_device_iteration: not in batch mode");
+        return HELIOS_ERR_STATE;
     }
+    ctx->batch.use_iter_dev = enable != 0;
+    return HELIOS_OK;
+}
+
+// ---------------------------------------------------------------- CUDA graphs
+struct helios_graph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int device = 0;
+    unsigned long long launches = 0;  // kernel launches recorded (bench bookkeeping)
+};
+
+int helios_graph_begin(helios_ctx* ctx) {
+    HCTX(ctx);
+    if (ctx->capturing) {
+        helios_set_error("helios_graph_begin: already capturing");
+        return HELIOS_ERR_STATE;
+    }
+    HCUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    ctx->capture_launches0 = ctx->launches;
+    return HELIOS_OK;
+}
+
+int helios_graph_end(helios_ctx* ctx, helios_graph** out) {
+    HCTX(ctx);
+    HARG(out != nullptr);
+    if (!ctx->capturing) {
+        helios_set_error("helios_graph_end: no capture in progress");
+        return HELIOS_ERR_STATE;
+    }
+    ctx->capturing = false;
+    helios_graph* g = new helios_graph();
+    g->device = ctx->device;
+    g->launches = ctx->launches - ctx->capture_launches0;
+    ctx->launches = ctx->capture_launches0;  // recorded, not executed
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+    if (e != cudaSuccess) {
+        if (g->graph) cudaGraphDestroy(g->graph);
+        delete g;
+        return helios_fail_cuda(e, "graph capture / instantiate", __FILE__, __LINE__);
+    }
+    *out = g;
+    return HELIOS_OK;
+}
+
+int helios_graph_launch(helios_ctx* ctx, helios_graph* g) {
+    HCTX(ctx);
+    HARG(g != nullptr && g->exec != nullptr);
+    HCUDA(cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->launches;
+    return HELIOS_OK;
+}
+
+int helios_graph_destroy(helios_graph* g) {
+    if (g == nullptr) return HELIOS_OK;
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
     return HELIOS_OK;
 }
 

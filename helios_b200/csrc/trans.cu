@@ -452,7 +452,7 @@ int helios_calc_delta_z(helios_ctx* ctx, const double* tlay, const double* pint,
     HARG(tlay && pint && meanmolmass_lay && delta_z_lay && nlayer > 0);
     HBATCHDIMS(ctx, nlayer == ctx->batch.nlayer);
     k_calc_delta_z<<<dim3(ceil_div(nlayer, 128), ctx->batch.nbatch), 128, 0, ctx->stream>>>(
-        tlay, pint, meanmolmass_lay, delta_z_lay, g, nlayer, ctx->batch.nbatch > 1 ? ctx->batch.g : nullptr);
+        tlay, pint, meanmolmass_lay, delta_z_lay, g, nlayer, ctx->batch.active ? ctx->batch.g : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }

@@ -92,8 +92,27 @@ int helios_ctx_set_fband_mode(helios_ctx* ctx, int mode);
 int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int ny, const int* table_index,
                          size_t ktable_stride, size_t crosstable_stride, size_t meanmass_stride, const double* g,
                          const double* planck_star);
-/* copy the done flags to done_host[nbatch] (may be NULL) and/or clear them */
-int helios_ctx_batch_done(helios_ctx* ctx, int* done_host, int reset);
+/* nbatch = 0 leaves batch mode; nbatch = 1 is a single atmosphere WITH the on-device bookkeeping (latch, counter).
+ * Copies the done flags / the iteration counts at which they latched (both [nbatch]) / the device iteration
+ * counter to the host (any pointer may be NULL; the call synchronises if one is given); reset != 0 clears all
+ * three on the device first. */
+int helios_ctx_batch_state(helios_ctx* ctx, int* done_host, int* converged_at_host, int* iter_host, int reset);
+/* enable != 0: rad_temp_iter takes `itervalue` from the device iteration counter instead of its argument, and
+ * abort_sum records the count at which an atmosphere latches; helios_batch_iter_advance (one tiny launch)
+ * increments the counter.  This is what makes a whole block of RT iterations replayable as one CUDA graph. */
+int helios_ctx_batch_device_iteration(helios_ctx* ctx, int enable);
+int helios_batch_iter_advance(helios_ctx* ctx);
+
+/* CUDA-graph capture of a launch sequence (no reference counterpart: the reference launches kernel by kernel with a
+ * full device sync after each, C:60).  Everything issued on the context between begin and end is recorded instead
+ * of executed; helios_graph_launch replays the recording with one driver call.  Entry points that synchronise
+ * (helios_buf_d2h, helios_buf_h2d, helios_ctx_sync, helios_corr_inc_energy with a host result, a first-time
+ * scratch allocation) must not be called while capturing: run the sequence once eagerly first. */
+typedef struct helios_graph helios_graph;
+int helios_graph_begin(helios_ctx* ctx);
+int helios_graph_end(helios_ctx* ctx, helios_graph** out);
+int helios_graph_launch(helios_ctx* ctx, helios_graph* graph);
+int helios_graph_destroy(helios_graph* graph);
 
 /* buffers: replace gpuarray.to_gpu / cuda.mem_alloc / .get() (Q:463-665) */
 int helios_buf_alloc(helios_ctx* ctx, size_t nbytes, void** dptr);

@@ -88,7 +88,10 @@ def test_batched_launch_sites_equal_single_runs_bit_for_bit(ctx, config):
                 b, name, int((~same).sum()), same.size, float(np.nanmax(np.abs(got - want))))
 
 
-def test_batched_radiation_loop_reproduces_every_single_run(ctx):
+@pytest.mark.parametrize("graph", [True, False])
+def test_batched_radiation_loop_reproduces_every_single_run(ctx, graph):
+    """the whole loop: device-side iteration counter + convergence latch, blocks of 10 iterations replayed as one
+    CUDA graph (graph=True) or launched eagerly (graph=False), against the host-driven single-atmosphere loop"""
     singles = _stores("C1", ctx)
     iters = []
     for q in singles:
@@ -101,13 +104,36 @@ def test_batched_radiation_loop_reproduces_every_single_run(ctx):
     qb, bcomp = make_batch(_stores("C1", ctx), ctx)
     bcomp.construct_planck_table(qb)
     bcomp.correct_incident_energy(qb)
-    bcomp.radiation_loop(qb)
-    print("\n[batch] iterations to convergence, single runs %s, batched %s; batched loop %.1f ms for %d atmospheres" %
-          (iters, list(qb.converged_at), bcomp.stats["radiation_loop_ms"], qb.nbatch))
-    assert list(qb.converged_at) == iters
+    bcomp.radiation_loop(qb, graph=graph)
+    print("\n[batch] graph=%s: iterations to convergence, single runs %s, batched %s; batched loop %.1f ms for %d "
+          "atmospheres (%d iterations run)" % (graph, iters, [int(v) for v in qb.converged_at],
+                                               bcomp.stats["radiation_loop_ms"], qb.nbatch, int(qb.iter_value)))
+    assert [int(v) for v in qb.converged_at] == iters
     for b, q in enumerate(singles):
-        for name in ("T_lay", "F_up_band", "F_net", "abort"):
+        for name in ("T_lay", "F_up_band", "F_down_wg", "F_net", "abort", "T_store", "delta_t_prefactor"):
             assert np.array_equal(qb.atmosphere(name, b), getattr(q, "dev_" + name).get()), (b, name)
+
+
+def test_single_atmosphere_on_the_device_loop(ctx):
+    """nbatch = 1: the device-side loop (graph replay) for ONE atmosphere, non-isothermal layers with clouds and a
+    direct beam, against the host-driven loop"""
+    grid = [dict(T_star=6117.0, g=930.0, table_scale=1.0)]
+    q = _stores("C2", ctx, grid)[0]
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    comp.radiation_loop(q, None, None, None)
+    qb, bcomp = make_batch(_stores("C2", ctx, grid), ctx)
+    bcomp.construct_planck_table(qb)
+    bcomp.correct_incident_energy(qb)
+    bcomp.radiation_loop(qb)
+    print("\n[batch] one C2 atmosphere: host loop %d iterations in %.1f ms, device loop %d iterations in %.1f ms" %
+          (int(q.iter_value), comp.stats["radiation_loop_ms"], int(qb.converged_at[0]), bcomp.stats["radiation_loop_ms"]))
+    assert int(qb.converged_at[0]) == int(q.iter_value)
+    for name in ("T_lay", "F_up_band", "Fc_down_wg", "F_net", "abort"):
+        assert np.array_equal(qb.atmosphere(name, 0), getattr(q, "dev_" + name).get()), name
+    np.testing.assert_array_equal(qb.dev_z_lay.get(), q.dev_z_lay.get())
 
 
 def test_unbatched_entry_points_refuse_batch_mode(ctx):
