@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- flux-solve throughput of the HELIOS RT hot path on B200 (one JSON line on rank 0).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2|C1|C4|C5]
 
 Workload at N=1: BASELINE.json configs[1] ("C2"): 100 layers x 385 bins x 20 Gauss points,
 non-isothermal layers, scattering iteration (3*scat+1 = 4 passes), one cloud deck, non-gray albedo and a
@@ -9,14 +9,21 @@ direct beam, on seeded synthetic tables (helios_b200/synthetic.py; the Zenodo in
 offline).  A "step" is one flux solve of the RT iteration: `populate_spectral_flux_iteratively` (all
 passes) + `integrate_flux` (computation.py:881-888).
 
-  value   layer*lambda*g-points/s = nlayer*nbin*ny*n_pass / t, inputs resident in HBM, CUDA-event timed per
-          step on the launching stream, L2 flushed between steps (helios_l2_flush: 2x L2 overwritten, then read back), max over ranks
-  e2e     the same metric for one full RT iteration through the public API (`Compute.*`): the step's
-          temperature profile comes from pinned host memory (H2D), every temperature-dependent quantity is
-          rebuilt (interpolation, transmission, direct beam), the flux solve runs, the temperature step is
-          taken and the per-interface fluxes + new profile + convergence flags are read back (D2H)
-  N > 1   every rank owns its own atmosphere of the same shape (batched grids shard by
-          atmosphere, no data-path collective) -> weak scaling
+  value      layer*lambda*g-points/s = nlayer*nbin*ny*n_pass / t, inputs resident in HBM, CUDA-event timed per
+             step on the launching stream, L2 flushed between steps (helios_l2_flush: 2x L2 overwritten, then
+             read back), max over ranks
+  e2e        the same metric for one RT iteration through the public API (`Compute.*`) with host buffers, on the
+             reference's own schedule (computation.py:851-984): every iteration takes the temperature profile from
+             pinned host memory (H2D), rebuilds the Planck terms, runs the flux solve and the temperature step and
+             reads the per-interface fluxes + new profile + convergence flags back (D2H); every 10th iteration
+             also rebuilds opacities, transmission functions and the direct beam
+  rce        converged RCE atmospheres per hour (the second half of BASELINE.json's metric): one atmosphere from
+             the isothermal start to the reference's convergence criterion, wall clock
+  workloads  (default run only) the other BASELINE.json configurations with the same timing rules:
+             C5 = a batched grid of 128 independent atmospheres per GPU, C4 = a 1e5-bin sampling spectrum
+  N > 1      C1/C2/C5: every rank owns its own atmosphere(s) (batched grids shard by atmosphere, no
+             data-path collective) -> weak scaling;  C4: the spectrum is sharded by wavelength with one fused
+             NVLink peer-memory all-reduce of the flux totals per step -> strong scaling
 
 --impl reference runs the reference's own kernels.cu (compiled verbatim to oracle/_ref/, launched with the
 block/grid shapes and per-launch device syncs of computation.py) on ONE B200: the reference has no CPU
@@ -550,9 +557,16 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     h2d = T_host.nbytes
     res_dev = ctx.zeros(3 * nint + int(q.nlayer) + 1)
 
-    def iteration():
+    def iteration(k):
+        """iteration k of the radiation loop as the reference schedules it (C:851-984): the temperature-dependent
+        opacities, transmission functions and direct beam are rebuilt every 10th iteration (C:860), the Planck
+        terms, the flux solve and the temperature step run every iteration"""
         T_host.h2d_async(ctx, q.dev_T_lay)
-        refresh(comp, q)
+        if k % 10 == 0:
+            refresh(comp, q)
+        else:
+            comp.interpolate_temperatures(q)
+            comp.interpolate_planck(q)
         flux_solve()
         comp.rad_temp_iteration(q)
         for j, name in enumerate(("F_net", "F_up_tot", "F_down_tot")):
@@ -562,19 +576,22 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
         abort_host.d2h_async(ctx, q.dev_abort)
         ctx.synchronize()
 
-    for _ in range(3):
-        iteration()
+    for k in range(10):
+        iteration(k)
     barrier()
     e0, e1 = ctx.event(), ctx.event()
-    e2e_steps = args.steps
-    t_e2e = 0.0
-    for _ in range(e2e_steps):
+    e2e_steps = 10 * max(2, args.steps // 10)  # whole blocks of the reference's 10-iteration schedule
+    t_e2e = t_e2e_refresh = 0.0
+    for k in range(e2e_steps):
         flush()
         e0.record()
-        iteration()
+        iteration(k)
         e1.record()
         e1.synchronize()
-        t_e2e += e0.time_till(e1)
+        dt = e0.time_till(e1)
+        t_e2e += dt
+        if k % 10 == 0:
+            t_e2e_refresh += dt
     barrier()
     rce = None
     if not args.no_rce:
@@ -595,8 +612,12 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                         "l2": l2, "sharding": "one atmosphere per rank, no collective"},
                 e2e={"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
-                     "what": "one full RT iteration via Compute.* (T profile from pinned host, rebuild, flux solve, "
-                             "temperature step, results to host)"},
+                     "ms_per_step_with_rebuild": t_e2e_refresh / (e2e_steps // 10), "steps": e2e_steps,
+                     "what": "one RT iteration through Compute.* with host buffers, averaged over whole blocks of the "
+                             "reference's schedule (C:851-984): every iteration = T profile H2D from pinned memory, Planck "
+                             "terms, flux solve (all passes), band integration, temperature step, fluxes + profile + "
+                             "convergence flags D2H; every 10th iteration additionally rebuilds opacities, transmission "
+                             "functions and the direct beam (C:860)"},
                 gpu_launches=int(launches),
                 roofline=_roofline("k_fband_wp (%s, all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
                                    _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload),

@@ -1,5 +1,5 @@
 // microbenchmark: how fast can the tile access pattern of k_fband_wp phase A stream from HBM?
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o stream_bench stream_bench.cu
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/stream_bench scripts/stream_bench.cu ; gpurun -- "./scripts/stream_bench 1; ./scripts/stream_bench 16"
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
