@@ -82,6 +82,12 @@ def _drive(q, comp, checker):
         checker("integrate_flux", ["F_down_band", "F_up_band", "F_dir_band", "F_down_tot", "F_up_tot"])
         checker("rad_temp_iteration", ["T_lay", "abort", "T_store", "delta_t_prefactor", "F_net_diff"])
         q.iter_value = np.int32(it + 1)
+    # the radiative-convective forward step (K:2768, C:799-825): layer 3 is the first radiative layer above a
+    # convective zone (what mark_convective_layers hands over, C:1135-1137)
+    red = np.zeros(int(q.nlayer) + 1, np.int32)
+    red[3] = 1
+    comp._upload(q, "marked_red", red)
+    checker("conv_temp_iteration", ["T_lay", "T_store", "delta_t_prefactor", "F_net_diff"])
     checker("integrate_optdepth_transmission", ["trans_band", "delta_tau_band"] + ([] if iso else ["delta_tau_all_clouds"]))
     checker("calculate_contribution_function", ["trans_weight_band", "contr_func_band"])
     checker("calculate_mean_opacities", ["planck_opac_T_pl", "ross_opac_T_pl", "planck_opac_T_star",

@@ -39,10 +39,14 @@ class RefBacked(Compute):
         return int(q.dev_abort.get().sum())  # C:927-932
 
 
-def _run(ctx, config, backed, perturb=0.0):
+def _run(ctx, config, backed, perturb=0.0, T_intern=None):
     q = synthetic.make_store(config, ctx=ctx, **SMALL)
     if config == "C2":
         q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+    if T_intern is not None:
+        from helios_b200 import host
+        q.T_intern = np.float64(T_intern)
+        host.calc_F_intern(q)
     if perturb:
         q.T_lay = np.asarray(q.T_lay, np.float64) + perturb
     synthetic.upload(q)
@@ -135,6 +139,45 @@ def test_converged_profile_and_spectrum_match_reference_kernels(ctx, config):
     if ours["conv"] == 0:
         scale = ours["Fdn_top"] + ours["F_intern"]
         assert np.max(np.abs(ours["F_net"] - ours["F_intern"])) / scale < 10 * ours["limit"]
+
+
+def _convection_body(ctx, backed, n_iter):
+    """the first n_iter iterations of the radiative-convective loop from a super-adiabatic start profile"""
+    q = synthetic.make_store("C2", ctx=ctx, **SMALL)
+    q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+    p = np.asarray(q.p_lay)
+    T = np.maximum(3200.0 * (p / p[0]) ** 0.45, 900.0)   # steeper than the dry adiabat (kappa = 2/7) at depth
+    q.T_lay = np.append(T, T[0] * 1.05)
+    q.max_nr_iterations = n_iter
+    synthetic.upload(q)
+    comp = RefBacked(ctx) if backed else Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    stopped = False
+    try:
+        comp.convection_loop(q, None, None, None)
+    except SystemExit:  # the loop's own iteration guard (C:1157-1164): used here to stop after n_iter iterations
+        stopped = True
+    return dict(T=q.dev_T_lay.get().copy(), iters=int(q.iter_value), stopped=stopped,
+                conv_layers=int(np.sum(q.conv_layer)), F_net=q.dev_F_net.get().copy())
+
+
+def test_convection_loop_body_matches_reference_kernels(ctx):
+    """C:992-1174 actually iterating: host-side convective adjustment between flux solves, the kappa hand-over,
+    mark_convective_layers -> conv_temp_iter (K:2768).  With strong internal heating neither backend converges this
+    synthetic case within 15,000 iterations (both abort alike), so the loop BODY is compared instead: the first 40
+    iterations from a super-adiabatic start, before the step-size logic can branch, agree to rounding."""
+    if not ref_gpu.available():
+        pytest.skip("reference cubin not built")
+    ours = _convection_body(ctx, False, 40)
+    ref = _convection_body(ctx, True, 40)
+    rel = float(np.max(np.abs(ours["T"] - ref["T"]) / ref["T"]))
+    print("\n[rce] convection loop body: %d / %d iterations, %d / %d convective layers, max rel dT %.2e" %
+          (ours["iters"], ref["iters"], ours["conv_layers"], ref["conv_layers"], rel))
+    assert ours["stopped"] and ref["stopped"], "the loop was expected to run into the iteration guard"
+    assert ours["iters"] == ref["iters"] and ours["iters"] > 40
+    assert ours["conv_layers"] == ref["conv_layers"] and ours["conv_layers"] > 0
+    assert rel < 1e-8, rel
 
 
 def test_converged_profiles_cross_evaluate_identically(ctx):
