@@ -37,6 +37,7 @@ struct BatchDesc {
     int* converged_at = nullptr;          // device [nbatch]: iteration count at which done[b] latched
     int* iter_dev = nullptr;              // device [1]: iteration counter (rad_temp_iter reads it when `use_iter_dev`)
     bool use_iter_dev = false;
+    unsigned* ticket = nullptr;           // device [1]: blocks finished (helios_rad_temp_iter_latched)
     __host__ __device__ int nint() const { return nlayer + 1; }
     __host__ __device__ size_t wg() const { return (size_t)(nlayer + 1) * nbin * ny; }  // every [i][x][y] array (Q:407)
     __host__ __device__ size_t band_lay() const { return (size_t)nlayer * nbin; }
@@ -67,6 +68,8 @@ struct helios_ctx {
     // them and the G+/- coefficient arrays that only multiply them.  [0] = F_dir_wg, [1] = Fc_dir_wg.
     const void* zero_beam[2] = {nullptr, nullptr};
     size_t zero_beam_bytes = 0;
+    unsigned* integ_ticket = nullptr;  // integrate_flux: blocks finished per (atmosphere, interface)
+    size_t integ_ticket_n = 0;
     void* flush_buf = nullptr;  // helios_l2_flush
     size_t flush_bytes = 0;
     // pow(epsi,-2), pow(mu_star,-2) of calc_trans_*, keyed on (epsi, mu_star): trans.cu

@@ -5,19 +5,33 @@
 // ------------------------------------------------------------------------------------------------
 // integrate_flux (K:2428-2513).  The reference runs ONE 1024-thread block that funnels every cell
 // through fp64 CAS-loop atomics.  Here:
-//   stage 1  grid (x-tiles, interfaces): a block stages XB*ny contiguous doubles of each of the three
-//            wg arrays through shared memory (coalesced), then one thread per bin adds its ny Gauss
-//            points in y order  -> F_*_band[i][x]
-//   stage 2  one block per interface: fixed-shape tree over x -> F_up_tot, F_down_tot, F_net
-// The summation order is fixed, so results are bitwise reproducible run to run.
+//   grid (x-tiles, interfaces, atmospheres): a block stages XB*ny contiguous doubles of each of the three wg arrays
+//   through shared memory (coalesced), one thread per bin adds its ny Gauss points in y order -> F_*_band[i][x];
+//   the block then tree-sums its bins' contributions to the wavelength integral, and the last block of an
+//   interface to finish adds the per-block partial sums in block order -> F_up_tot, F_down_tot, F_net.
+// One launch; the summation order is fixed, so results are bitwise reproducible run to run.
 // ------------------------------------------------------------------------------------------------
 #define IF_THREADS 256
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
 
 __global__ void __launch_bounds__(IF_THREADS)
 k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict__ F_up_wg,
                  const double* __restrict__ F_dir_wg, double* __restrict__ F_down_band,
                  double* __restrict__ F_up_band, double* __restrict__ F_dir_band,
-                 const double* __restrict__ gauss_weight, int nbin, int ny, int xb) {
+                 const double* __restrict__ gauss_weight, int nbin, int ny, int xb,
+                 const double* __restrict__ deltalambda, double* __restrict__ partial, unsigned* __restrict__ ticket,
+                 double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net) {
     extern __shared__ double sm[];
     const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
     double* s_dn = sm;
@@ -41,6 +55,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         s_dr[d] = F_dir_wg[base + k];
     }
     __syncthreads();
+    double t_up = 0.0, t_dn = 0.0;  // this thread's bin in the sum over wavelength (xb <= blockDim.x: one bin each)
     for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
         double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
         for (int y = 0; y < ny; y++) {
@@ -53,90 +68,55 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         F_dir_band[o] = a_dr;
         F_up_band[o] = a_up;
         F_down_band[o] = a_dn;
+        t_up += a_up * deltalambda[x0 + xl];
+        t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
     }
-}
-
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    red[threadIdx.x] = v;
+    // Sum over wavelength in the same launch (K:2484-2509): fixed tree over this block's bins, then the LAST block
+    // of the interface to finish adds the per-block partial sums in block order -- a fixed summation order, bitwise
+    // reproducible run to run, and no second launch.
+    // fixed-shape reduction: shuffle tree inside each warp, then warp 0 adds the 8 warp sums in warp order
+    __shared__ double wsum[2][IF_THREADS / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        t_up += __shfl_down_sync(0xffffffffu, t_up, d);
+        t_dn += __shfl_down_sync(0xffffffffu, t_dn, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        wsum[0][threadIdx.x >> 5] = t_up;
+        wsum[1][threadIdx.x >> 5] = t_dn;
+    }
+    __shared__ bool last;
+    const int ntile = gridDim.x, nint = gridDim.y;
+    const size_t slot = (size_t)blockIdx.z * nint + i;  // (atmosphere, interface)
     __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        t_up = t_dn = 0.0;
+#pragma unroll
+        for (int w = 0; w < IF_THREADS / 32; w++) {
+            t_up += wsum[0][w];
+            t_dn += wsum[1][w];
+        }
+        partial[(slot * ntile + blockIdx.x) * 2] = t_up;
+        partial[(slot * ntile + blockIdx.x) * 2 + 1] = t_dn;
+        __threadfence();
+        last = atomicAdd(ticket + slot, 1u) == (unsigned)ntile - 1;
     }
-    const double r = red[0];
     __syncthreads();
-    return r;
-}
-
-__global__ void __launch_bounds__(IF_THREADS)
-k_total_integrate(const double* __restrict__ deltalambda, const double* __restrict__ F_down_band,
-                  const double* __restrict__ F_up_band, const double* __restrict__ F_dir_band,
-                  double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net,
-                  int nbin) {
-    __shared__ double red[IF_THREADS];
-    const int i = blockIdx.x;
-    {   // batch (blockIdx.y = atmosphere); gridDim.x = ninterface
-        const size_t bd = (size_t)blockIdx.y * gridDim.x * nbin, tt = (size_t)blockIdx.y * gridDim.x;
-        F_down_band += bd; F_up_band += bd; F_dir_band += bd;
-        F_down_tot += tt; F_up_tot += tt; F_net += tt;
-    }
-    double up = 0.0, dn = 0.0;
-    for (int x = threadIdx.x; x < nbin; x += blockDim.x) {
-        const size_t o = (size_t)i * nbin + x;
-        up += F_up_band[o] * deltalambda[x];
-        dn += (F_dir_band[o] + F_down_band[o]) * deltalambda[x];
-    }
-    up = block_sum(up, red);
-    dn = block_sum(dn, red);
-    if (threadIdx.x == 0) {
-        F_up_tot[i] = up;
-        F_down_tot[i] = dn;
-        F_net[i] = up - dn;
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const volatile double* p = partial + slot * ntile * 2;
+        double up = 0.0, dn = 0.0;
+        for (int c = 0; c < ntile; c++) {
+            up += p[2 * c];
+            dn += p[2 * c + 1];
+        }
+        F_up_tot[slot] = up;
+        F_down_tot[slot] = dn;
+        F_net[slot] = up - dn;
+        ticket[slot] = 0u;
     }
 }
 
-// Wide spectra (1e5 sampling bins): one block per interface would leave the chip idle, so the sum over x is
-// split into TI_CHUNK-bin pieces (fixed tree inside a piece) whose partial sums a second kernel adds in chunk
-// order -- still a fixed summation order, bitwise reproducible run to run.
-#define TI_CHUNK 2048
-__global__ void __launch_bounds__(IF_THREADS)
-k_total_partial(const double* __restrict__ deltalambda, const double* __restrict__ F_down_band,
-                const double* __restrict__ F_up_band, const double* __restrict__ F_dir_band,
-                double* __restrict__ partial, int nbin) {
-    __shared__ double red[IF_THREADS];
-    const int i = blockIdx.y, nint = gridDim.y, nchunk = gridDim.x;
-    const size_t bd = (size_t)blockIdx.z * nint * nbin;  // batch (blockIdx.z = atmosphere)
-    const int x0 = blockIdx.x * TI_CHUNK, x1 = min(nbin, x0 + TI_CHUNK);
-    double up = 0.0, dn = 0.0;
-    for (int x = x0 + threadIdx.x; x < x1; x += blockDim.x) {
-        const size_t o = bd + (size_t)i * nbin + x;
-        up += F_up_band[o] * deltalambda[x];
-        dn += (F_dir_band[o] + F_down_band[o]) * deltalambda[x];
-    }
-    up = block_sum(up, red);
-    dn = block_sum(dn, red);
-    if (threadIdx.x == 0) {
-        double* p = partial + (((size_t)blockIdx.z * nint + i) * nchunk + blockIdx.x) * 2;
-        p[0] = up;
-        p[1] = dn;
-    }
-}
-
-__global__ void k_total_final(const double* __restrict__ partial, double* __restrict__ F_down_tot,
-                              double* __restrict__ F_up_tot, double* __restrict__ F_net, int nint, int nchunk,
-                              int nbatch) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // (atmosphere, interface)
-    if (t >= nint * nbatch) return;
-    const double* p = partial + (size_t)t * nchunk * 2;
-    double up = 0.0, dn = 0.0;
-    for (int c = 0; c < nchunk; c++) {
-        up += p[2 * c];
-        dn += p[2 * c + 1];
-    }
-    F_up_tot[t] = up;
-    F_down_tot[t] = dn;
-    F_net[t] = up - dn;
-}
 
 // ------------------------------------------------------------------------------------------------
 // Temperature stepping (K:2606-2884).  One block; the reads of neighbouring temperatures, the
@@ -149,6 +129,12 @@ struct TempScalars {
     const int* done;        // batch: atmospheres that have converged are left untouched
     const double* g_batch;  // batch: per-atmosphere gravity
     const int* iter_dev;    // batch with the on-device iteration counter: overrides itervalue
+    // fused tail (helios_rad_temp_iter_latched): flag sum + convergence latch + counter advance in the same launch
+    int* sums;
+    int* done_w;
+    int* converged_at;
+    int* iter_w;
+    unsigned* ticket;
 };
 
 __global__ void __launch_bounds__(256)
@@ -160,10 +146,11 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
             double* __restrict__ F_smooth, double* __restrict__ F_smooth_sum,
             const double* __restrict__ c_p_lay, const double* __restrict__ mmm_lay, TempScalars s) {
     const int nl = s.numlayers;
+    bool skip = false;  // batch: this atmosphere has converged and is left untouched
     if (s.iter_dev != nullptr) s.itervalue = *s.iter_dev;
     if (gridDim.x > 1 || s.done != nullptr) {  // batch (blockIdx.x = atmosphere)
         const size_t a = blockIdx.x;
-        if (s.done != nullptr && s.done[a] != 0) return;
+        skip = s.done != nullptr && s.done[a] != 0;
         if (s.g_batch != nullptr) s.g = s.g_batch[a];
         const size_t v1 = a * (nl + 1), v0 = a * nl;  // vectors with nlayer + 1 / nlayer entries
         if (F_down_tot) F_down_tot += v1;
@@ -175,6 +162,7 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
         if (c_p_lay) c_p_lay += v0;
         if (mmm_lay) mmm_lay += v0;
     }
+    if (!skip) {
     // phase 1: flux divergence and smoothing force, from the OLD temperatures
     for (int i = threadIdx.x; i < nl; i += blockDim.x) {
         F_net_diff[i] = F_net[i] - F_net[i + 1] + F_add_heat_lay[i];
@@ -260,6 +248,34 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
                 else prefactor[i] *= 1.1;
             }
             tlay[i] = fmax(T_old + delta_T, 1.001);
+        }
+    }
+    }  // !skip
+    if (s.sums != nullptr) {
+        // fused tail: what k_abort_sum + k_iter_advance do, without two more launches per iteration
+        __shared__ int red_i[256];
+        __syncthreads();
+        int a = 0;
+        for (int i = threadIdx.x; i < nl + 1; i += blockDim.x) a += abrt[i];
+        red_i[threadIdx.x] = a;
+        __syncthreads();
+        for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w) red_i[threadIdx.x] += red_i[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int b = blockIdx.x;
+            s.sums[b] = red_i[0];
+            if (red_i[0] == nl + 1 && s.done_w[b] == 0) {
+                s.done_w[b] = 1;
+                s.converged_at[b] = s.itervalue + 1;  // iterations completed
+            }
+            // the LAST block to finish advances the iteration counter: by then every block has read it
+            __threadfence();
+            if (atomicAdd(s.ticket, 1u) == gridDim.x - 1) {
+                *s.ticket = 0u;
+                *s.iter_w = s.itervalue + 1;
+            }
         }
     }
 }
@@ -440,30 +456,64 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
     }
     const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
-    dim3 grid(ceil_div(nbin, xb), numinterfaces, ctx->batch.nbatch);
+    const int ntile = ceil_div(nbin, xb);
+    const int nb = ctx->batch.nbatch;
+    dim3 grid(ntile, numinterfaces, nb);
+    // per-block partial sums (transient, scratch) and one ticket per (atmosphere, interface) (persistent, zeroed)
+    double* scratch = nullptr;
+    const size_t pbytes = (size_t)nb * numinterfaces * ntile * 2 * sizeof(double);
+    int rc = helios_ctx_scratch(ctx, pbytes + 64, &scratch);
+    if (rc) return rc;
+    const size_t nticket = (size_t)nb * numinterfaces;
+    if (ctx->integ_ticket_n < nticket) {
+        if (ctx->integ_ticket) {
+            HCUDA(cudaStreamSynchronize(ctx->stream));
+            HCUDA(cudaFree(ctx->integ_ticket));
+            ctx->integ_ticket = nullptr;
+            ctx->integ_ticket_n = 0;
+        }
+        HCUDA(cudaMalloc((void**)&ctx->integ_ticket, nticket * sizeof(unsigned)));
+        HCUDA(cudaMemsetAsync(ctx->integ_ticket, 0, nticket * sizeof(unsigned), ctx->stream));
+        ctx->integ_ticket_n = nticket;
+    }
     k_band_integrate<<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band,
                                                               F_up_band, F_dir_band, gauss_weight, nbin,
-                                                              ny, xb);
+                                                              ny, xb, deltalambda, scratch + 8, ctx->integ_ticket,
+                                                              F_down_tot, F_up_tot, F_net);
     HLAUNCHED(ctx);
-    if (nbin <= 2 * TI_CHUNK) {
-        k_total_integrate<<<dim3(numinterfaces, ctx->batch.nbatch), IF_THREADS, 0, ctx->stream>>>(
-            deltalambda, F_down_band, F_up_band, F_dir_band, F_down_tot, F_up_tot, F_net, nbin);
-        HLAUNCHED(ctx);
-    } else {
-        const int nchunk = ceil_div(nbin, TI_CHUNK);
-        const int nb = ctx->batch.nbatch;
-        double* scratch = nullptr;
-        const size_t bytes = (size_t)nb * numinterfaces * nchunk * 2 * sizeof(double);
-        int rc = helios_ctx_scratch(ctx, bytes + 64, &scratch);
-        if (rc) return rc;
-        double* partial = scratch + 8;  // clear of the first 64 bytes (small reductions)
-        k_total_partial<<<dim3(nchunk, numinterfaces, nb), IF_THREADS, 0, ctx->stream>>>(
-            deltalambda, F_down_band, F_up_band, F_dir_band, partial, nbin);
-        HLAUNCHED(ctx);
-        k_total_final<<<ceil_div(numinterfaces * nb, 128), 128, 0, ctx->stream>>>(partial, F_down_tot, F_up_tot,
-                                                                              F_net, numinterfaces, nchunk, nb);
-        HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+static int rad_temp_iter_impl(helios_ctx* ctx, const double* F_down_tot, const double* F_net, double* F_net_diff,
+                              double* tlay, const double* play, const double* pint, int* abrt, double* T_store,
+                              double* deltat_prefactor, const double* F_add_heat_lay, const double* F_add_heat_sum,
+                              double* F_smooth, double* F_smooth_sum, const double* c_p_lay,
+                              const double* meanmolmass_lay, int itervalue, double f_factor, int foreplay, double g,
+                              int numlayers, double physical_tstep, double local_limit, int adapt_interval, int smooth,
+                              int dim, int step, double F_intern, int no_atmo, int* sum_dev, const char* who) {
+    if (!(F_down_tot && F_net && F_net_diff && tlay && play && pint && abrt && T_store && deltat_prefactor &&
+          F_add_heat_lay && F_add_heat_sum && F_smooth && F_smooth_sum) ||
+        !(physical_tstep == 0 || (c_p_lay != nullptr && meanmolmass_lay != nullptr)) ||
+        !(numlayers > 1 && adapt_interval > 0)) {
+        helios_set_error("%s: invalid argument", who);
+        return HELIOS_ERR_ARG;
     }
+    HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer);
+    const BatchDesc& bd = ctx->batch;
+    const bool batched = bd.active;
+    if (sum_dev != nullptr && !(batched && bd.use_iter_dev)) {
+        helios_set_error("%s: needs batch mode with the device iteration counter", who);
+        return HELIOS_ERR_STATE;
+    }
+    TempScalars s{itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, 0,
+                  f_factor, g, physical_tstep, local_limit, F_intern,
+                  batched ? bd.done : nullptr, batched ? bd.g : nullptr,
+                  (batched && bd.use_iter_dev) ? bd.iter_dev : nullptr,
+                  sum_dev, bd.done, bd.converged_at, bd.iter_dev, bd.ticket};
+    k_temp_iter<<<bd.nbatch, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
+                                                    deltat_prefactor, nullptr, F_add_heat_lay, F_add_heat_sum,
+                                                    F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay, s);
+    HLAUNCHED(ctx);
     return HELIOS_OK;
 }
 
@@ -478,21 +528,29 @@ int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double
                          double F_intern, int no_atmo) {
     HCTX(ctx);
     (void)F_up_tot; (void)tint;
-    HARG(F_down_tot && F_net && F_net_diff && tlay && play && pint && abrt && T_store && deltat_prefactor &&
-         F_add_heat_lay && F_add_heat_sum && F_smooth && F_smooth_sum);
-    HARG(physical_tstep == 0 || (c_p_lay != nullptr && meanmolmass_lay != nullptr));
-    HARG(numlayers > 1 && adapt_interval > 0);
-    HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer);
-    const bool batched = ctx->batch.active;
-    TempScalars s{itervalue, foreplay, numlayers, adapt_interval, smooth, dim, step, no_atmo, 0,
-                  f_factor, g, physical_tstep, local_limit, F_intern,
-                  batched ? ctx->batch.done : nullptr, batched ? ctx->batch.g : nullptr,
-                  (batched && ctx->batch.use_iter_dev) ? ctx->batch.iter_dev : nullptr};
-    k_temp_iter<<<ctx->batch.nbatch, 256, 0, ctx->stream>>>(F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store,
-                                            deltat_prefactor, nullptr, F_add_heat_lay, F_add_heat_sum,
-                                            F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+    return rad_temp_iter_impl(ctx, F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store, deltat_prefactor,
+                              F_add_heat_lay, F_add_heat_sum, F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay,
+                              itervalue, f_factor, foreplay, g, numlayers, physical_tstep, local_limit,
+                              adapt_interval, smooth, dim, step, F_intern, no_atmo, nullptr, "helios_rad_temp_iter");
+}
+
+int helios_rad_temp_iter_latched(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                                 const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                                 const double* tint, const double* pint, int* abrt, double* T_store,
+                                 double* deltat_prefactor, const double* F_add_heat_lay,
+                                 const double* F_add_heat_sum, double* F_smooth, double* F_smooth_sum,
+                                 const double* c_p_lay, const double* meanmolmass_lay, int itervalue,
+                                 double f_factor, int foreplay, double g, int numlayers, double physical_tstep,
+                                 double local_limit, int adapt_interval, int smooth, int dim, int step,
+                                 double F_intern, int no_atmo, int* sum_dev) {
+    HCTX(ctx);
+    (void)F_up_tot; (void)tint;
+    HARG(sum_dev != nullptr);
+    return rad_temp_iter_impl(ctx, F_down_tot, F_net, F_net_diff, tlay, play, pint, abrt, T_store, deltat_prefactor,
+                              F_add_heat_lay, F_add_heat_sum, F_smooth, F_smooth_sum, c_p_lay, meanmolmass_lay,
+                              itervalue, f_factor, foreplay, g, numlayers, physical_tstep, local_limit,
+                              adapt_interval, smooth, dim, step, F_intern, no_atmo, sum_dev,
+                              "helios_rad_temp_iter_latched");
 }
 
 int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
@@ -508,7 +566,7 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
     HARG(numlayers > 1 && adapt_interval > 0);
     HNOBATCH(ctx);
     TempScalars s{itervalue, 0, numlayers, adapt_interval, smooth, 0, 0, 0, 1, 0.0, 0.0, 0.0, 0.0, F_intern,
-                  nullptr, nullptr, nullptr};
+                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     k_temp_iter<<<1, 256, 0, ctx->stream>>>(nullptr, F_net, F_net_diff, tlay, play, pint, nullptr, T_store,
                                             deltat_prefactor, marked_red, F_add_heat_lay, nullptr, F_smooth,
                                             F_smooth_sum, nullptr, nullptr, s);

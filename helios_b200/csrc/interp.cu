@@ -140,6 +140,73 @@ k_planck_interpol(const double* __restrict__ temp, double* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused per-iteration preparation: temp_inter + planck_interpol_layer + planck_interpol_interface in ONE launch
+// (three launches in the reference, C:856-857; they are the only work besides the flux solve in 9 of 10 iterations).
+// Same formulas, same operation order as the three kernels above -> bitwise the same results.
+//   blockIdx.y <  ytl : 32-row tile of the layer table (rows 0..nl-1 layers, nl = star, nl+1 = surface); the blocks
+//                       of the first x-tile also write T_int (every interface index is < nl + 2)
+//   blockIdx.y >= ytl : 32-row tile of the interface table (non-isothermal only)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double interface_temperature(const double* __restrict__ tlay, int i, int nint) {
+    if (i == 0) return tlay[i] - 0.5 * (tlay[i + 1] - tlay[i]);
+    if (i == nint - 1) return tlay[i - 1] + 0.5 * (tlay[i - 1] - tlay[i - 2]);
+    return tlay[i - 1] + 0.5 * (tlay[i] - tlay[i - 1]);
+}
+
+__global__ void __launch_bounds__(256)
+k_iter_prep(const double* __restrict__ tlay, double* __restrict__ tint, double* __restrict__ planck_lay,
+            double* __restrict__ planck_int, const double* __restrict__ planck_grid,
+            const double* __restrict__ starflux, int realstar, int nl, int nwave, int dim, int step, int ytl,
+            const double* __restrict__ planck_star) {
+    __shared__ double tile[32][33];
+    const int nint = nl + 1;
+    const bool lay = (int)blockIdx.y < ytl;
+    const int nrows = lay ? nl + 2 : nint;
+    {   // batch (blockIdx.z = atmosphere)
+        const size_t b = blockIdx.z;
+        tlay += b * (size_t)nint;
+        tint += b * (size_t)nint;
+        planck_lay += b * (size_t)(nl + 2) * nwave;
+        if (planck_int) planck_int += b * (size_t)nint * nwave;
+        if (starflux) starflux += b * (size_t)nwave;
+        if (planck_star) planck_star += b * (size_t)nwave;
+    }
+    double* __restrict__ out = lay ? planck_lay : planck_int;
+    const int x0 = blockIdx.x * 32, i0 = (lay ? blockIdx.y : blockIdx.y - ytl) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    if (lay && blockIdx.x == 0 && ty == 0) {
+        const int i = i0 + tx;
+        if (i < nint) tint[i] = interface_temperature(tlay, i, nint);
+    }
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, x = x0 + tx;
+        double v = 0.0;
+        if (i < nrows && x < nwave) {
+            if (lay && i == nl) {
+                v = realstar == 1 ? starflux[x] / hc::PI
+                                  : (planck_star ? planck_star[x] : planck_grid[x + (size_t)dim * nwave]);
+            } else {
+                const double Ti = lay ? (i == nl + 1 ? tlay[nl] : tlay[i]) : interface_temperature(tlay, i, nint);
+                double t = (Ti - 1.0) / step;
+                t = fmax(0.001, fmin(dim - 1.001, t));
+                const int tdown = (int)floor(t), tup = (int)ceil(t);
+                if (tdown != tup)
+                    v = planck_grid[x + (size_t)tdown * nwave] * (tup - t) +
+                        planck_grid[x + (size_t)tup * nwave] * (t - tdown);
+                else
+                    v = planck_grid[x + (size_t)tdown * nwave];
+            }
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, i = i0 + tx;
+        if (x < nwave && i < nrows) out[i + (size_t)x * nrows] = tile[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // (P,T) table interpolation (K:524-645, 649-919, 3209-3259).
 // A tiny prep kernel resolves each layer's box once (the reference recomputes the log10 of the
 // grid ends in every thread, K:545-554); the gather kernel then streams the four table rows of
@@ -351,6 +418,23 @@ int helios_planck_interpol_interface(helios_ctx* ctx, const double* temp, double
     dim3 grid(ceil_div(nwave, 32), ceil_div(numinterfaces, 32), ctx->batch.nbatch);
     k_planck_interpol<<<grid, 256, 0, ctx->stream>>>(temp, planckband_int, planck_grid, nullptr, 0, 1, 0,
                                                      numinterfaces, nwave, dim, step, nullptr);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int helios_iteration_prepare(helios_ctx* ctx, const double* tlay, double* tint, double* planckband_lay,
+                             double* planckband_int, const double* planck_grid, const double* starflux,
+                             int realstar, int numlayers, int nwave, int dim, int step) {
+    HCTX(ctx);
+    HARG(tlay && tint && planckband_lay && planck_grid && numlayers > 1 && nwave > 0 && dim > 1 && step > 0);
+    HARG(realstar == 0 || starflux != nullptr);
+    HBATCHDIMS(ctx, numlayers == ctx->batch.nlayer && nwave == ctx->batch.nbin);
+    const int ytl = ceil_div(numlayers + 2, 32);
+    const int yti = planckband_int ? ceil_div(numlayers + 1, 32) : 0;
+    dim3 grid(ceil_div(nwave, 32), ytl + yti, ctx->batch.nbatch);
+    k_iter_prep<<<grid, 256, 0, ctx->stream>>>(tlay, tint, planckband_lay, planckband_int, planck_grid, starflux,
+                                               realstar, numlayers, nwave, dim, step, ytl,
+                                               ctx->batch.active ? ctx->batch.planck_star : nullptr);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }

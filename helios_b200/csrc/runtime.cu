@@ -85,6 +85,7 @@ int helios_ctx_destroy(helios_ctx* ctx) {
     ctx->allocs.clear();
     if (ctx->scratch) cudaFree(ctx->scratch);
     batch_release(ctx);
+    if (ctx->integ_ticket) cudaFree(ctx->integ_ticket);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -152,12 +153,13 @@ int helios_ctx_set_batch(helios_ctx* ctx, int nbatch, int nlayer, int nbin, int 
     b.mmass_stride = meanmass_stride;
     b.g = g;
     b.planck_star = planck_star;
-    // done[nbatch] | converged_at[nbatch] | iteration counter
-    const size_t n = 2 * (size_t)nbatch + 1;
+    // done[nbatch] | converged_at[nbatch] | iteration counter | ticket
+    const size_t n = 2 * (size_t)nbatch + 2;
     HCUDA(cudaMalloc((void**)&b.done, sizeof(int) * n));
     HCUDA(cudaMemset(b.done, 0, sizeof(int) * n));
     b.converged_at = b.done + nbatch;
     b.iter_dev = b.done + 2 * nbatch;
+    b.ticket = reinterpret_cast<unsigned*>(b.done + 2 * nbatch + 1);
     ctx->batch = b;
     return HELIOS_OK;
 }
@@ -169,7 +171,7 @@ int helios_ctx_batch_state(helios_ctx* ctx, int* done_host, int* converged_at_ho
         return HELIOS_ERR_STATE;
     }
     const size_t nb = (size_t)ctx->batch.nbatch;
-    if (reset) HCUDA(cudaMemsetAsync(ctx->batch.done, 0, sizeof(int) * (2 * nb + 1), ctx->stream));
+    if (reset) HCUDA(cudaMemsetAsync(ctx->batch.done, 0, sizeof(int) * (2 * nb + 2), ctx->stream));
     if (done_host)
         HCUDA(cudaMemcpyAsync(done_host, ctx->batch.done, sizeof(int) * nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (converged_at_host)

@@ -161,6 +161,13 @@ int helios_planck_interpol_interface(helios_ctx* ctx, const double* temp, double
                                      const double* planck_grid, int numinterfaces, int nwave,
                                      int dim, int step);
 
+/* temp_inter + planck_interpol_layer + planck_interpol_interface (K:496, K:923, K:981; C:856-857) in ONE launch,
+ * bitwise the same results as the three separate calls: what every RT iteration does before its flux solve.
+ * planckband_int may be NULL (isothermal layers).  B200-side addition used by the device-resident loop. */
+int helios_iteration_prepare(helios_ctx* ctx, const double* tlay, double* tint, double* planckband_lay,
+                             double* planckband_int, const double* planck_grid, const double* starflux,
+                             int realstar, int numlayers, int nwave, int dim, int step);
+
 /* K:524 opac_interpol, C:122-159 */
 int helios_opac_interpol(helios_ctx* ctx, const double* temp, const double* opactemp,
                          const double* press, const double* opacpress, const double* ktable,
@@ -335,6 +342,19 @@ int helios_rad_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double
                          double f_factor, int foreplay, double g, int numlayers,
                          double physical_tstep, double local_limit, int adapt_interval, int smooth,
                          int dim, int step, double F_intern, int no_atmo);
+
+/* rad_temp_iter + abort_sum + helios_batch_iter_advance in ONE launch (batch mode with the device iteration
+ * counter): the block of each atmosphere sums its flags into sum_dev[b] and latches done[b]; the last block to
+ * finish advances the counter.  Same arguments as helios_rad_temp_iter plus sum_dev [nbatch]. */
+int helios_rad_temp_iter_latched(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,
+                                 const double* F_net, double* F_net_diff, double* tlay, const double* play,
+                                 const double* tint, const double* pint, int* abrt, double* T_store,
+                                 double* deltat_prefactor, const double* F_add_heat_lay,
+                                 const double* F_add_heat_sum, double* F_smooth, double* F_smooth_sum,
+                                 const double* c_p_lay, const double* meanmolmass_lay, int itervalue,
+                                 double f_factor, int foreplay, double g, int numlayers,
+                                 double physical_tstep, double local_limit, int adapt_interval, int smooth,
+                                 int dim, int step, double F_intern, int no_atmo, int* sum_dev);
 
 /* K:2768 conv_temp_iter, C:802-823 */
 int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const double* F_up_tot,

@@ -88,8 +88,8 @@ def test_batched_launch_sites_equal_single_runs_bit_for_bit(ctx, config):
                 b, name, int((~same).sum()), same.size, float(np.nanmax(np.abs(got - want))))
 
 
-@pytest.mark.parametrize("graph", [True, False])
-def test_batched_radiation_loop_reproduces_every_single_run(ctx, graph):
+@pytest.mark.parametrize("graph,fused", [(True, True), (True, False), (False, True)])
+def test_batched_radiation_loop_reproduces_every_single_run(ctx, graph, fused):
     """the whole loop: device-side iteration counter + convergence latch, blocks of 10 iterations replayed as one
     CUDA graph (graph=True) or launched eagerly (graph=False), against the host-driven single-atmosphere loop"""
     singles = _stores("C1", ctx)
@@ -104,9 +104,9 @@ def test_batched_radiation_loop_reproduces_every_single_run(ctx, graph):
     qb, bcomp = make_batch(_stores("C1", ctx), ctx)
     bcomp.construct_planck_table(qb)
     bcomp.correct_incident_energy(qb)
-    bcomp.radiation_loop(qb, graph=graph)
-    print("\n[batch] graph=%s: iterations to convergence, single runs %s, batched %s; batched loop %.1f ms for %d "
-          "atmospheres (%d iterations run)" % (graph, iters, [int(v) for v in qb.converged_at],
+    bcomp.radiation_loop(qb, graph=graph, fused=fused)
+    print("\n[batch] graph=%s fused=%s: iterations to convergence, single runs %s, batched %s; batched loop %.1f ms for %d "
+          "atmospheres (%d iterations run)" % (graph, fused, iters, [int(v) for v in qb.converged_at],
                                                bcomp.stats["radiation_loop_ms"], qb.nbatch, int(qb.iter_value)))
     assert [int(v) for v in qb.converged_at] == iters
     for b, q in enumerate(singles):

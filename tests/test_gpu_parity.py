@@ -304,7 +304,7 @@ def test_kappa_cp_entropy_phase_from_file(ctx, iso):
 
 
 def test_wide_spectrum_flux_integration(ctx):
-    """nbin > 4096 takes the two-stage sum over wavelength (flux.cu: k_total_partial / k_total_final)"""
+    """nbin > 4096 takes the two-stage sum over wavelength (many x-tiles per interface: the last block of an interface adds hundreds of partial sums)"""
     from oracle import helios_oracle as O
     rng = np.random.default_rng(3)
     nbin, nint, ny = 9001, 7, 1
