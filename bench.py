@@ -54,11 +54,13 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _traffic_from_profile(workload):
+def _traffic_from_profile(workload, nbatch=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the flux-sweep kernel, from the committed
-    `ncu --set full` summary of this workload (profiles/); None if no capture of this workload is committed"""
+    `ncu --set full` summary of this workload (profiles/); None if no capture of this workload is committed.
+    A capture of a batched launch (file name ..._batchN.csv) is scaled to the batch size of this run."""
     import csv
     import glob
+    import re
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_fband*%s*.csv" % workload.lower()))):
         rows = list(csv.reader(open(path)))
@@ -74,7 +76,11 @@ def _traffic_from_profile(workload):
                 tot += float(r[i]) * scale
             vals.append(tot)
         if vals:
-            best = {"bytes_per_launch": sum(vals) / len(vals), "source": os.path.relpath(path, ROOT)}
+            per_launch = sum(vals) / len(vals)
+            m = re.search(r"_batch(\d+)\.csv$", path)
+            if m and nbatch:
+                per_launch *= float(nbatch) / float(m.group(1))
+            best = {"bytes_per_launch": per_launch, "source": os.path.relpath(path, ROOT)}
     return best
 
 
@@ -401,9 +407,9 @@ def rce_batch(ctx, nbatch=32):
                     "to the reference's convergence criterion, converged ones frozen by the on-device latch" % nbatch}
 
 
-def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload):
+def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload, nbatch=None):
     peak, peak_src = _peaks()
-    traffic = _traffic_from_profile(workload)
+    traffic = _traffic_from_profile(workload, nbatch)
     t_k = t_kernel_ms * 1e-3
     achieved = bpc * cells / t_k / 1e9
     return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -460,7 +466,7 @@ def run_ours(args):
                                  "flux solve, temperature step, profiles + convergence sums to host)"},
                     gpu_launches=None,
                     roofline=_roofline("k_fband_wp (iso, all %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
-                                       r["bpc"], r["cells"], t_fband, r["npass"], "C5"))
+                                       r["bpc"], r["cells"], t_fband, r["npass"], "C5", args.batch))
     elif args.workload == "C4":
         barrier()
         r = bench_c4(ctx, rank, world, steps, warmup, flush, scat=args.c4_scat)
@@ -489,7 +495,7 @@ def run_ours(args):
                     "e2e": {"value": r["points"] / (r["t_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": r["t_e2e"],
                             "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                     "roofline": _roofline("k_fband_wp (iso, %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
-                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5"),
+                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5", args.batch),
                     "setup_s": time.perf_counter() - t0}
                 del r
                 extra["C5_batched_grid"]["rce"] = rce_batch(ctx, 32)
