@@ -326,6 +326,45 @@ def bench_c4(ctx, rank, world, steps, warmup, flush, nbin=100000, scat=1, dim=80
                          (q.nlayer, nbin, q.nbin, npass, scat, world))
 
 
+def bench_mixing(ctx, flush, reps=5):
+    """C3: on-the-fly mixing of 10 species (BASELINE.json configs[2]) -- what every 10th RT iteration does instead of
+    the premixed-table gather: per species a (P,T) interpolation of its own k-table plus correlated-k summation or
+    random overlap (400 k-sums sorted and rebinned per cell).  The species tables stay resident in HBM."""
+    from helios_b200 import synthetic, host
+    from helios_b200.computation import Compute
+    out = {}
+    q = synthetic.make_store("C3", ctx=ctx, kcoeff_mixing="RO")
+    n = int(q.nlayer)
+    q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    comp.interpolate_temperatures(q)
+    host.calculate_meanmolecularmass(q)
+    cells = int(q.nlayer) * int(q.nbin)
+    nspec = len(q.species_list)
+    for mixing in ("RO", "correlated-k"):
+        q.kcoeff_mixing = mixing
+        times = []
+        for k in range(reps + 2):
+            host.nullify_opac_scat_arrays(q)
+            flush()
+            e0, e1 = ctx.event(), ctx.event()
+            e0.record()
+            comp.calculate_total_opacity_and_scat_cross_sections_from_species(q)
+            e1.record()
+            e1.synchronize()
+            if k >= 2:
+                times.append(e0.time_till(e1))
+        ms = float(np.median(times))
+        out[mixing] = {"ms_per_species_loop": ms, "species": nspec, "cells_x_i": cells,
+                       "mixed_cells_per_s": cells * nspec / (ms * 1e-3),
+                       "k_combinations_sorted_per_s": (cells * (nspec - 1) * 400 / (ms * 1e-3)) if mixing == "RO" else None}
+    out["workload"] = ("C3: %d species, %d layers x %d bins x %d gauss points, isothermal layers; one full species loop "
+                       "(interpolation + mixing + scattering cross sections), tables resident in HBM" %
+                       (nspec, q.nlayer, q.nbin, q.ny))
+    return out
+
+
 def rce_leg(ctx, workload, seed_offset=0):
     """converged RCE atmospheres per hour: one atmosphere from the standard isothermal start to the reference's own
     convergence criterion, wall clock with all host logic included.  Two drivers of the same kernels:
@@ -512,6 +551,10 @@ def run_ours(args):
                                                         r["t_fband"], r["npass"], "C4")}
                 except Exception as e:  # noqa: BLE001
                     extra[key] = {"error": repr(e)}
+            try:
+                extra["C3_on_the_fly_mixing"] = bench_mixing(ctx, flush)
+            except Exception as e:  # noqa: BLE001
+                extra["C3_on_the_fly_mixing"] = {"error": repr(e)}
             line["workloads"] = extra
     clocks = sampler.stop() if sampler else None
     if rank == 0:

@@ -9,6 +9,43 @@
 #define RO_PAD 512    // bitonic network size
 #define RO_WARPS 4
 
+// compare-exchange building blocks of the warp-level bitonic network (element e = PER * lane + r in register r)
+__device__ __forceinline__ bool ro_greater(double a, int ta, double b, int tb) {
+    return (a > b) | ((a == b) & ((ta & 511) > (tb & 511)));  // total order on (key, slot); no short-circuit branches
+}
+
+template <int PER, int J>
+__device__ __forceinline__ void ro_in_lane(double (&kv)[PER], int (&tg)[PER], int k, int lane) {
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        if ((r & J) == 0) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int h = r | J;
+            const bool up = (((lane * PER) | r) & k) == 0;
+            const bool sw = ro_greater(kv[r], tg[r], kv[h], tg[h]) == up;
+            const double lo_k = sw ? kv[h] : kv[r], hi_k = sw ? kv[r] : kv[h];
+            const int lo_t = sw ? tg[h] : tg[r], hi_t = sw ? tg[r] : tg[h];
+            kv[r] = lo_k; kv[h] = hi_k;
+            tg[r] = lo_t; tg[h] = hi_t;
+        }
+    }
+}
+
+template <int PER>
+__device__ __forceinline__ void ro_cross_lane(double (&kv)[PER], int (&tg)[PER], int lm, int k, int lane) {
+    const bool is_lo = (lane & lm) == 0;
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        const double ok = __shfl_xor_sync(0xffffffffu, kv[r], lm);
+        const int ot = __shfl_xor_sync(0xffffffffu, tg[r], lm);
+        const bool up = (((lane * PER) | r) & k) == 0;
+        const bool take = (is_lo == up) == ro_greater(kv[r], tg[r], ok, ot);  // keep the smaller one iff (lo == up)
+        kv[r] = take ? ok : kv[r];
+        tg[r] = take ? ot : tg[r];
+    }
+}
+
 // One warp per (x, i) cell.  The reference gives each cell to one thread, which bubble-sorts the
 // 400 sums in local memory (K:3152-3171).  Here the warp builds the 400 (k-sum, slot) pairs in shared
 // memory, sorts them with a 512-wide bitonic network (ties broken by the reference's slot index, which
@@ -68,12 +105,16 @@ k_add_to_mixed_opac(const double* __restrict__ vmr, const double* __restrict__ o
     const bool mixed_outer = mixed[0] > newk[0];  // K:3332
     const int split = yi * RO_NY;
 
-    // build the 400 sums in the reference's slot layout (K:3332-3365); pad with +inf
-    double* key = s_key[wid];
-    int* tag = s_tag[wid];
+    // build the 400 sums in the reference's slot layout (K:3332-3365), padded with +inf to the 512 inputs of the
+    // network.  Element e = 16 * lane + r lives in register r of its lane: the compare-exchange distances below 16
+    // stay inside a lane (pure register work), the larger ones pair lanes through shuffles; shared memory only
+    // receives the sorted result.
+    constexpr int PER = RO_PAD / 32;  // 16 elements per lane
+    double kv[PER];
+    int tg[PER];
 #pragma unroll
-    for (int k = 0; k < RO_PAD / 32; k++) {
-        const int pos = lane + 32 * k;
+    for (int r = 0; r < PER; r++) {
+        const int pos = lane * PER + r;
         double v = DBL_MAX;
         int t = pos;
         if (pos < RO_N2) {
@@ -88,31 +129,29 @@ k_add_to_mixed_opac(const double* __restrict__ vmr, const double* __restrict__ o
             v = mixed[y1] + newk[y2];
             t = pos | (y1 << 9) | (y2 << 14);
         }
-        key[pos] = v;
-        tag[pos] = t;
+        kv[r] = v;
+        tg[r] = t;
+    }
+
+    // bitonic sort, ascending in (key, slot); ties are broken by the reference's slot index, which reproduces the
+    // stable order of its exchange sort (K:3152-3171).  The network is driven by run-time (k, j) over five small
+    // code blocks (four in-lane distances, one cross-lane exchange) so that it stays resident in the instruction
+    // cache; compare-exchanges are branch-free selects.
+    for (int k = 2; k <= RO_PAD; k <<= 1) {
+        for (int j = k >> 1; j >= PER; j >>= 1) ro_cross_lane<PER>(kv, tg, j / PER, k, lane);
+        if (k > 8) ro_in_lane<PER, 8>(kv, tg, k, lane);
+        if (k > 4) ro_in_lane<PER, 4>(kv, tg, k, lane);
+        if (k > 2) ro_in_lane<PER, 2>(kv, tg, k, lane);
+        ro_in_lane<PER, 1>(kv, tg, k, lane);
+    }
+    double* key = s_key[wid];
+    int* tag = s_tag[wid];
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        key[lane * PER + r] = kv[r];
+        tag[lane * PER + r] = tg[r];
     }
     __syncwarp();
-
-    // bitonic sort, ascending in (key, slot)
-    for (int k = 2; k <= RO_PAD; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int m = 0; m < RO_PAD / 64; m++) {
-                const int q = lane + 32 * m;
-                const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
-                const int hi = lo | j;
-                const double a = key[lo], b = key[hi];
-                const int ta = tag[lo], tb = tag[hi];
-                const bool up = (lo & k) == 0;
-                const bool a_gt_b = (a > b) || (a == b && (ta & 511) > (tb & 511));
-                if (a_gt_b == up) {
-                    key[lo] = b; key[hi] = a;
-                    tag[lo] = tb; tag[hi] = ta;
-                }
-            }
-            __syncwarp();
-        }
-    }
 
     // abscissae of the sorted k-function: yg[w] = sum_{m<w} wt[m] + 0.5 wt[w]  (K:3371-3376)
     const int CH = 13;  // 32 * 13 >= 400
