@@ -167,6 +167,7 @@ def refresh(comp, q):
     comp.hsfunc.calculate_height_z(q)
     q.dev_z_lay.set(q.z_lay)
     comp.calculate_direct_beamflux(q)
+    comp.build_flux_plan(q)  # non-isothermal layers: the sweep plan belongs to the refresh (Compute._refresh_atmosphere)
 
 
 def _bytes_per_cell(q):

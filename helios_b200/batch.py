@@ -190,6 +190,7 @@ class BatchCompute(Compute):
         self.calculate_delta_z(quant)
         self._heights(quant)
         self.calculate_direct_beamflux(quant)
+        self.build_flux_plan(quant)
 
     def _iteration(self, quant, refresh, heights=True, fused=True):
         """one RT iteration of C:851-984 on the device (the temperature step reads the device iteration counter).
@@ -213,6 +214,7 @@ class BatchCompute(Compute):
             if heights:
                 self._heights(q)
             self.calculate_direct_beamflux(q)
+            self.build_flux_plan(q)
         self.populate_spectral_flux_iteratively(q)
         self.integrate_flux(q)
         if fused:

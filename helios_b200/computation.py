@@ -26,6 +26,9 @@ class Compute(object):
         self._species_cache = {}
         self._abort_sum = None
         self.fuse_passes = True
+        # non-isothermal layers: form the Planck-independent part of the sweep constants once per opacity refresh
+        # (helios_fband_noniso_plan_build) and run the planned sweep in the iterations in between
+        self.use_flux_plan = True
         self.stats = {"iterations": 0}
         backend.lib()  # fail loudly right here if the CUDA library is missing
 
@@ -125,6 +128,7 @@ class Compute(object):
                           quant.ninterface)
 
     def calculate_transmission(self, quant):  # C:364-462
+        quant._flux_plan_valid = False
         quant.dev_scat_trigger.fill_zero()  # the reference re-uploads a host zero array (C:368)
         q = quant
         tail = (q.g_0, q.epsi, q.epsi2, q.mu_star, q.w_0_limit, q.w_0_scat_limit, q.scat, q.nbin, q.ny, q.nlayer,
@@ -152,6 +156,7 @@ class Compute(object):
 
     def calculate_direct_beamflux(self, quant):  # C:481-526
         q = quant
+        q._flux_plan_valid = False
         tail = (q.dev_z_lay, q.mu_star, q.R_planet, q.R_star, q.a, q.dir_beam, q.geom_zenith_corr, q.ninterface,
                 q.nbin, q.ny)
         if quant.iso == 1:
@@ -159,6 +164,24 @@ class Compute(object):
         elif quant.iso == 0:
             self.ctx.call("fdir_noniso", q.dev_F_dir_wg, q.dev_Fc_dir_wg, q.dev_planckband_lay,
                           q.dev_delta_tau_wg_upper, q.dev_delta_tau_wg_lower, *tail)
+
+    def build_flux_plan(self, quant):
+        """B200-side addition: the sweep plan of the non-isothermal flux solve (include/helios_b200.h).  Valid until
+        the next calculate_transmission / calculate_direct_beamflux."""
+        q = quant
+        if q.iso != 0 or not self.use_flux_plan or int(q.nlayer) > 128:
+            return
+        n = 16 * q._size("ninterface_wg_nbin")
+        if getattr(q, "dev_fband_plan", None) is None or q.dev_fband_plan.size != n:
+            q.dev_fband_plan = self.ctx.zeros(n)
+        self.ctx.call("fband_noniso_plan_build", q.dev_fband_plan, q.dev_F_dir_wg, q.dev_Fc_dir_wg, q.dev_w_0_upper,
+                      q.dev_w_0_lower, q.dev_delta_tau_wg_upper, q.dev_delta_tau_wg_lower,
+                      q.dev_delta_tau_all_clouds_upper, q.dev_delta_tau_all_clouds_lower, q.dev_M_upper, q.dev_M_lower,
+                      q.dev_N_upper, q.dev_N_lower, q.dev_P_upper, q.dev_P_lower, q.dev_G_plus_upper,
+                      q.dev_G_plus_lower, q.dev_G_minus_upper, q.dev_G_minus_lower, q.dev_surf_albedo,
+                      q.dev_g_0_tot_lay, q.dev_g_0_tot_int, q.g_0, q.ninterface, q.nbin, q.mu_star, q.ny, q.epsi,
+                      q.delta_tau_limit, q.clouds, q.scat_corr, q.i2s_transition)
+        q._flux_plan_valid = True
 
     @staticmethod
     def n_scat_passes(quant):
@@ -177,6 +200,10 @@ class Compute(object):
                               q.dev_surf_albedo, q.dev_g_0_tot_lay, q.g_0, q.singlewalk, q.R_star, q.a, q.ninterface,
                               q.nbin, q.f_factor, q.mu_star, q.ny, q.epsi, q.dir_beam, q.clouds, q.scat_corr, q.debug,
                               q.i2s_transition, n)
+            elif q.iso == 0 and self.use_flux_plan and getattr(q, "_flux_plan_valid", False):
+                self.ctx.call("fband_noniso_planned", q.dev_F_down_wg, q.dev_F_up_wg, q.dev_Fc_down_wg, q.dev_Fc_up_wg,
+                              q.dev_fband_plan, q.dev_planckband_lay, q.dev_planckband_int, q.dev_surf_albedo,
+                              q.R_star, q.a, q.ninterface, q.nbin, q.f_factor, q.ny, q.dir_beam, n)
             elif q.iso == 0:
                 self.ctx.call("fband_noniso", q.dev_F_down_wg, q.dev_F_up_wg, q.dev_Fc_down_wg, q.dev_Fc_up_wg,
                               q.dev_F_dir_wg, q.dev_Fc_dir_wg, q.dev_planckband_lay, q.dev_planckband_int,
@@ -256,6 +283,7 @@ class Compute(object):
         hs.calculate_height_z(quant)
         quant.dev_z_lay.set(quant.z_lay)  # in place; the reference allocates a new gpuarray (C:878)
         self.calculate_direct_beamflux(quant)
+        self.build_flux_plan(quant)
 
     def _flux_solve(self, quant):
         if quant.flux_calc_method == "iteration":

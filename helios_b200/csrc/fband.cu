@@ -508,6 +508,15 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         const double* g0_int, double g_0, double Rstar, double a, int nint, int nbin,
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass);
+int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
+                     const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
+                     double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
+                     double i2s);
+int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                         const double* plan, const double* planck_lay, const double* planck_int,
+                         const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
+                         int dir_beam, int npass);
+
 
 static int fband_grid(helios_ctx* ctx, int ncol) {
     const int ntile = (ncol + FB_THREADS - 1) / FB_THREADS;
@@ -617,6 +626,48 @@ int helios_fband_noniso(
                                                      surf_albedo, g_0_tot_lay, g_0_tot_int, s));
     HLAUNCHED(ctx);
     return HELIOS_OK;
+}
+
+int helios_fband_noniso_plan_build(
+    helios_ctx* ctx, double* plan, const double* F_dir_wg, const double* Fc_dir_wg, const double* w_0_upper,
+    const double* w_0_lower, const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
+    const double* delta_tau_all_clouds_upper, const double* delta_tau_all_clouds_lower, const double* M_upper,
+    const double* M_lower, const double* N_upper, const double* N_lower, const double* P_upper, const double* P_lower,
+    const double* G_plus_upper, const double* G_plus_lower, const double* G_minus_upper, const double* G_minus_lower,
+    const double* surf_albedo, const double* g_0_tot_lay, const double* g_0_tot_int, double g_0, int numinterfaces,
+    int nbin, double mu_star, int ny, double epsi, double delta_tau_limit, int clouds, int scat_corr,
+    double i2s_transition) {
+    HCTX(ctx);
+    HARG(plan && F_dir_wg && Fc_dir_wg && w_0_upper && w_0_lower && delta_tau_wg_upper && delta_tau_wg_lower &&
+         delta_tau_all_clouds_upper && delta_tau_all_clouds_lower && M_upper && M_lower && N_upper && N_lower &&
+         P_upper && P_lower && G_plus_upper && G_plus_lower && G_minus_upper && G_minus_lower && surf_albedo);
+    HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
+    HARG(numinterfaces > 1 && nbin > 0 && ny > 0);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
+    CpNonisoCoef cc{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
+                    delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
+                    G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
+    return fband_plan_build(ctx, plan, F_dir_wg, Fc_dir_wg, cc, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0, mu_star,
+                            epsi, delta_tau_limit, numinterfaces, nbin, ny, clouds == 1, scat_corr == 1,
+                            i2s_transition);
+}
+
+int helios_fband_noniso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, double* Fc_down_wg,
+                                double* Fc_up_wg, const double* plan, const double* planckband_lay,
+                                const double* planckband_int, const double* surf_albedo, double Rstar, double a,
+                                int numinterfaces, int nbin, double f_factor, int ny, int dir_beam, int npass) {
+    HCTX(ctx);
+    HARG(F_down_wg && F_up_wg && Fc_down_wg && Fc_up_wg && plan && planckband_lay && planckband_int && surf_albedo);
+    HARG(numinterfaces > 1 && nbin > 0 && ny > 0 && npass > 0);
+    HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
+    const int rc = fband_noniso_planned(ctx, F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, plan, planckband_lay,
+                                        planckband_int, surf_albedo, Rstar, a, numinterfaces, nbin, f_factor, ny,
+                                        dir_beam, npass);
+    if (rc < 0) {
+        helios_set_error("helios_fband_noniso_planned: more than 128 layers are not supported by the planned sweep");
+        return HELIOS_ERR_ARG;
+    }
+    return rc;
 }
 
 int helios_fband_matrix_iso(

@@ -31,6 +31,7 @@
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
+    long long plan_stride;  // PLANNED: elements per plan plane (nbatch * ninterface * ncol)
     int no_beam;      // F_dir / Fc_dir are known to be all -0.0: do not load them, nor G+/-
     int nbatch;       // atmospheres per launch (helios_ctx_set_batch), 1 otherwise
     const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
@@ -102,12 +103,111 @@ __device__ __forceinline__ void beam_pair(double Fa, double Fb, double neg_mu, d
 }
 
 // ------------------------------------------------------------------------------------------------
+// Sweep plan (non-isothermal layers).  Between two opacity refreshes (10 RT iterations, C:860) only the Planck
+// terms change; everything else phase A derives from the coefficient arrays -- 1/M, P/M, N/M, the source factor,
+// the gradient factor, the direct-beam sources with their four divisions -- is the same every iteration.  The
+// source terms are affine in the Planck values of a half-layer,
+//      s = k0 + k1 * B_layer + k2 * B_interface,
+// so k_plan_build evaluates, once per refresh and with the same building blocks as phase A, the 8 constants
+// [a, b, k0d, k1d, k2d, k0u, k1u, k2u] of every half-layer into 16 planes laid out like the coefficient arrays
+// ([i][column]); the planned phase A then reads 16 + 2 values per cell instead of 24 and does 8 multiply-adds
+// instead of ~650 instructions with 12 divisions.  Row nlay of planes 0 and 1 carries the per-column surface
+// constants (emission factor of K:1704, direct beam at BOA).  Rounding differs from the reference's operation
+// order by a few ulp of the source terms (measured against the unplanned kernel: <= 1e-13 on the fluxes).
+// ------------------------------------------------------------------------------------------------
+struct PlanHalf {
+    double a, b, k0d, k1d, k2d, k0u, k1u, k2u;
+};
+
+// lay_first: the half-layer's "B1" of the downward form is the layer value (upper half) or the interface (lower)
+__device__ __forceinline__ PlanHalf plan_half(double w0, double M, double N, double P, double Gp, double Gm, double dt,
+                                              double g0, double Fa_d, double Fb_d, double m1d, double m2d,
+                                              bool upper, double neg_mu, const CpScalars& s, double& E_out) {
+    const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
+    E_out = E;
+    const double invM = 1.0 / M;
+    const double fac = source_factor(s.epsi, w0, E);
+    double Dd, Du;
+    beam_pair(Fa_d, Fb_d, neg_mu, M, N, P, Gp, Gm, m1d, m2d, Dd, Du);
+    double lay_d, int_d, lay_u, int_u;  // coefficients of B_layer / B_interface in the Planck terms
+    if (dt < s.delta_tau_limit) {
+        lay_d = int_d = lay_u = int_u = 0.5 * ((M + N) - P);
+    } else {
+        const double pre = gradient_factor(s.epsi, w0, g0, E);
+        const double cd = (N + (P - M)) * pre / dt;
+        const double cu = ((M - P) - N) * pre / dt;
+        if (upper) {  // down: B1 = layer, B2 = interface above; up: B1 = interface above, B2 = layer
+            lay_d = (M + N) + cd;  int_d = -P - cd;
+            lay_u = cu - P;        int_u = (M + N) - cu;
+        } else {      // down: B1 = interface below, B2 = layer; up: B1 = layer, B2 = interface below
+            lay_d = -P - cd;       int_d = (M + N) + cd;
+            lay_u = (M + N) - cu;  int_u = cu - P;
+        }
+    }
+    PlanHalf h;
+    h.a = invM * P;
+    h.b = invM * N;
+    const double f = invM * fac;
+    h.k0d = invM * Dd;  h.k1d = f * lay_d;  h.k2d = f * int_d;
+    h.k0u = invM * Du;  h.k1u = f * lay_u;  h.k2u = f * int_u;
+    return h;
+}
+
+__global__ void __launch_bounds__(256)
+k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
+             CpNonisoCoef cfg, const double* __restrict__ albedo, const double* __restrict__ g0_lay,
+             const double* __restrict__ g0_int, CpScalars s) {
+    const int nint = s.nint, nlay = nint - 1, ncol = s.nbin * s.ny;
+    const long long per_atm = (long long)ncol * nlay;
+    const long long total = per_atm * s.nbatch;
+    const double neg_mu = -s.mu_star;
+    for (long long ee = blockIdx.x * (long long)blockDim.x + threadIdx.x; ee < total;
+         ee += (long long)gridDim.x * blockDim.x) {
+        const int atm = (int)(ee / per_atm);
+        const long long el = ee - (long long)atm * per_atm;
+        const int i = (int)(el / ncol);
+        const int col = (int)(el - (long long)i * ncol);
+        const int x = col / s.ny;
+        const size_t e = (size_t)atm * ncol * nint + el;
+        const size_t bl = (size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i;
+        const size_t bi = (size_t)atm * s.nbin * nint + (size_t)x + (size_t)s.nbin * i;
+        double g0_up = s.g_0, g0_low = s.g_0;
+        if (s.clouds) {
+            const double gl = g0_lay[bl];
+            g0_up = (gl + g0_int[bi + s.nbin]) / 2.0;
+            g0_low = (g0_int[bi] + gl) / 2.0;
+        }
+        const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol], Fcdir = Fc_dir[e];
+        double E_u, E_l;
+        const double P_u = cfg.P_u[e], Gm_u = cfg.Gm_u[e];
+        const PlanHalf u = plan_half(cfg.w0_u[e], cfg.M_u[e], cfg.N_u[e], P_u, cfg.Gp_u[e], Gm_u,
+                                     cfg.dtau_u[e] + cfg.dtc_u[bl], g0_up, Fcdir, Fdir_ip1, Gm_u, P_u, true, neg_mu, s, E_u);
+        const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e], Gm_l = cfg.Gm_l[e];
+        const PlanHalf l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, cfg.Gp_l[e], Gm_l,
+                                     cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low, Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
+        double* __restrict__ p = plan + e;
+        const size_t ps = (size_t)s.plan_stride;
+        p[0] = u.a;       p[ps] = u.b;       p[2 * ps] = u.k0d;  p[3 * ps] = u.k1d;
+        p[4 * ps] = u.k2d; p[5 * ps] = u.k0u; p[6 * ps] = u.k1u;  p[7 * ps] = u.k2u;
+        p[8 * ps] = l.a;   p[9 * ps] = l.b;   p[10 * ps] = l.k0d; p[11 * ps] = l.k1d;
+        p[12 * ps] = l.k2d; p[13 * ps] = l.k0u; p[14 * ps] = l.k1u; p[15 * ps] = l.k2u;
+        if (i == 0) {  // surface constants in the spare row nlay (K:1704: w0 and E of layer 0's lower half)
+            const size_t top = (size_t)atm * ncol * nint + (size_t)ncol * nlay + col;
+            const double A_s = albedo[x];
+            plan[top] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0_l)),
+                                  __dsub_rn(E_l, w0_l));
+            plan[ps + top] = Fdir_i;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The kernel.  NONISO = false: one step per layer, shared planes a, b, sd, su, F_up(prev)            (5)
 //              NONISO = true : two steps per layer (upper half, lower half): [a, b, sd, su] x 2,
 //                              F_up(prev), Fc_up(prev)                                               (10)
 // Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS>
+template <bool NONISO, int CH, int LPC, int NCOLS, bool PLANNED>
 __global__ void __launch_bounds__(NCOLS * LPC, 2)
 k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
            double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
@@ -138,7 +238,47 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
         const size_t bio = (size_t)atm * s.nbin * nint;        // [interface][x] arrays
         // ================= phase A: coalesced streaming, lanes along columns =================
         // Every thread owns at most CH layer rows (nlay <= LPC*CH).
-        {
+        if constexpr (PLANNED) {
+            // planned form (see k_plan_build): cfg.w0_u is the plan; 16 + 2 loads and 8 multiply-adds per cell
+            const int c = threadIdx.x % NCOLS;
+            const int r = threadIdx.x / NCOLS;
+            const int col = min(tile * NCOLS + c, ncol - 1);
+            const int x = col / s.ny;
+            const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
+            const double* __restrict__ BI = planck_int + bio + (size_t)x * nint;
+            const double* __restrict__ plan = cfg.w0_u;
+            const size_t ps = (size_t)s.plan_stride;
+#pragma unroll
+            for (int m = 0; m < CH; m++) {
+                const int i = r + LPC * m;
+                if (i < nlay) {
+                    const size_t e = wgo + col + (size_t)ncol * i;
+                    double v[16];
+#pragma unroll
+                    for (int z = 0; z < 16; z++) v[z] = plan[z * ps + e];
+                    const double fu = F_up[e], fcu = Fc_up[e];
+                    const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
+                    const int o = c * pitch + (i / CH) * STRIDE + (i % CH);
+                    sm[o] = v[0];
+                    sm[plane + o] = v[1];
+                    sm[2 * plane + o] = __fma_rn(v[3], Blay, __fma_rn(v[4], Bint_hi, v[2]));
+                    sm[3 * plane + o] = __fma_rn(v[6], Blay, __fma_rn(v[7], Bint_hi, v[5]));
+                    sm[4 * plane + o] = v[8];
+                    sm[5 * plane + o] = v[9];
+                    sm[6 * plane + o] = __fma_rn(v[11], Blay, __fma_rn(v[12], Bint_lo, v[10]));
+                    sm[7 * plane + o] = __fma_rn(v[14], Blay, __fma_rn(v[15], Bint_lo, v[13]));
+                    sm[8 * plane + o] = fu;
+                    sm[9 * plane + o] = fcu;
+                    if (i == 0) {
+                        const size_t top = wgo + (size_t)ncol * nlay + col;
+                        c_alb[c] = albedo[x];
+                        c_fdir0[c] = plan[ps + top];
+                        c_emis[c] = __dmul_rn(plan[top], BL[nlay + 1]);
+                        c_toa[c] = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
+                    }
+                }
+            }
+        } else {
             const int c = threadIdx.x % NCOLS;
             const int r = threadIdx.x / NCOLS;  // 0 .. LPC-1
             const int col = min(tile * NCOLS + c, ncol - 1);
@@ -405,7 +545,7 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
 // ------------------------------------------------------------------------------------------------
 // launch planning: LPC = 16 lanes per column (two columns per warp) while nlay <= 128, else 32
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS>
+template <bool NONISO, int CH, int LPC, int NCOLS, bool PLANNED = false>
 static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
                      const double* F_dir, const double* Fc_dir, const double* planck_lay, const double* planck_int,
                      CpNonisoCoef c, const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s,
@@ -425,7 +565,7 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
     if (per_sm < 1) per_sm = 1;
     const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
-    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS>;
+    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS, PLANNED>;
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NCOLS * LPC, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
                                                    planck_int, c, albedo, g0_lay, g0_int, s);
@@ -460,6 +600,51 @@ static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
     return -1;
 }
 
+// planned non-isothermal sweep: same tile shapes as the unplanned kernel
+static int dispatch_wp_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                               const double* planck_lay, const double* planck_int, CpNonisoCoef c,
+                               const double* albedo, CpScalars s, int ncol) {
+    const int nlay = s.nint - 1;
+    const double* F_dir = nullptr;
+    const double* Fc_dir = nullptr;
+    const double* g0_lay = nullptr;
+    const double* g0_int = nullptr;
+#define WP_ARGS ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo, g0_lay, g0_int, s, ncol
+    if (nlay <= 32) return launch_wp<true, 1, 32, 8, true>(WP_ARGS);
+    if (nlay <= 64) return launch_wp<true, 2, 32, 8, true>(WP_ARGS);
+    if (nlay <= 96) return launch_wp<true, 3, 32, 8, true>(WP_ARGS);
+    if (nlay <= 128) return launch_wp<true, 4, 32, 8, true>(WP_ARGS);
+#undef WP_ARGS
+    return -1;
+}
+
+int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
+                     const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
+                     double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
+                     double i2s) {
+    CpScalars s{g_0, 0.0, 0.0, 0.0, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, 0, clouds, scat_corr, 1, 0, 0,
+                0, 0, ctx->batch.nbatch, nullptr};
+    s.plan_stride = (long long)ctx->batch.nbatch * nint * nbin * ny;
+    const long long total = (long long)nbin * ny * (nint - 1) * ctx->batch.nbatch;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)ctx->num_sms * 32;
+    if (blocks > cap) blocks = cap;
+    k_plan_build<<<(int)blocks, 256, 0, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                         const double* plan, const double* planck_lay, const double* planck_int,
+                         const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
+                         int dir_beam, int npass) {
+    CpScalars s{0.0, Rstar, a, f_factor, 0.0, 0.0, 0.0, 0.0, nint, nbin, ny, dir_beam, 0, 0, npass, 0, 0, 0, 0, 1, nullptr};
+    s.plan_stride = (long long)ctx->batch.nbatch * nint * nbin * ny;
+    CpNonisoCoef c{plan, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                   nullptr, nullptr, nullptr, nullptr, nullptr};
+    return dispatch_wp_planned(ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, c, albedo, s, nbin * ny);
+}
+
 // return HELIOS_OK when launched, -1 when the shape does not fit this scheme (the caller then falls back to
 // the one-thread-per-column kernel of fband.cu)
 int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double* F_dir, const double* planck,
@@ -467,7 +652,7 @@ int fband_iso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, const double
                      const double* Gm, const double* albedo, const double* g0tot, double g_0, double Rstar,
                      double a, int nint, int nbin, double f_factor, double mu_star, int ny, double epsi,
                      int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
-    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0,
+    CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, 0.0, i2s, nint, nbin, ny, dir_beam, clouds, scat_corr, npass, 0, 0, 0,
                 (dir_beam == 0 && ctx->zero_beam[0] == F_dir) ? 1 : 0, 1, nullptr};
     CpNonisoCoef c{w_0, nullptr, nullptr, nullptr, nullptr, nullptr, M, nullptr, N, nullptr, P, nullptr, Gp, nullptr, Gm, nullptr};
     return dispatch_wp<false>(ctx, F_down, F_up, nullptr, nullptr, F_dir, nullptr, planck, nullptr, c, albedo, g0tot,
@@ -481,7 +666,7 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass) {
     CpScalars s{g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, dir_beam, clouds,
-                scat_corr, npass, 0, 0,
+                scat_corr, npass, 0, 0, 0,
                 (dir_beam == 0 && ctx->zero_beam[0] == F_dir && ctx->zero_beam[1] == Fc_dir) ? 1 : 0, 1, nullptr};
     return dispatch_wp<true>(ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo,
                              g0_lay, g0_int, s, nbin * ny);

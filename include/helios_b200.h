@@ -294,6 +294,28 @@ int helios_fband_noniso(
     double mu_star, int ny, double epsi, double delta_tau_limit, int dir_beam, int clouds,
     int scat_corr, int debug, double i2s_transition, int npass);
 
+/* Sweep plan for non-isothermal layers (B200-side addition, no reference counterpart).  Between two opacity refreshes
+ * (10 RT iterations, C:860) only the Planck terms of fband_noniso's inputs change.  helios_fband_noniso_plan_build
+ * evaluates everything else the sweep derives from the coefficient arrays -- P/M, N/M, the source and gradient
+ * factors, the direct-beam sources -- once, into `plan`: 16 planes of nbatch*ninterface*ny*nbin doubles (call it
+ * after calc_trans_noniso and fdir_noniso).  helios_fband_noniso_planned then performs the same npass fused sweeps
+ * as helios_fband_noniso from the plan plus the current Planck arrays and the previous fluxes; results agree with
+ * helios_fband_noniso to rounding (<= 1e-13 relative on the fluxes; the plan folds the Planck-independent factors
+ * into affine coefficients).  The plan is invalid as soon as any coefficient array, F_dir or surf_albedo changes. */
+int helios_fband_noniso_plan_build(
+    helios_ctx* ctx, double* plan, const double* F_dir_wg, const double* Fc_dir_wg, const double* w_0_upper,
+    const double* w_0_lower, const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
+    const double* delta_tau_all_clouds_upper, const double* delta_tau_all_clouds_lower, const double* M_upper,
+    const double* M_lower, const double* N_upper, const double* N_lower, const double* P_upper, const double* P_lower,
+    const double* G_plus_upper, const double* G_plus_lower, const double* G_minus_upper, const double* G_minus_lower,
+    const double* surf_albedo, const double* g_0_tot_lay, const double* g_0_tot_int, double g_0, int numinterfaces,
+    int nbin, double mu_star, int ny, double epsi, double delta_tau_limit, int clouds, int scat_corr,
+    double i2s_transition);
+int helios_fband_noniso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, double* Fc_down_wg,
+                                double* Fc_up_wg, const double* plan, const double* planckband_lay,
+                                const double* planckband_int, const double* surf_albedo, double Rstar, double a,
+                                int numinterfaces, int nbin, double f_factor, int ny, int dir_beam, int npass);
+
 /* K:1803 fband_matrix_iso, C:630-668.  alpha/beta/source_term_* are accepted for signature
  * compatibility but not touched: the Thomas coefficients are formed on the fly; c_prime/d_prime
  * (2*ninterface*ny*nbin doubles each) hold the forward elimination. */

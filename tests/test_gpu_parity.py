@@ -354,3 +354,57 @@ def test_known_zero_beam_fast_path_is_bit_identical(ctx, config):
         results.append([getattr(q, "dev_" + name).get() for name in names])
     for name, a, b in zip(names, *results):
         assert np.array_equal(a, b), name
+
+
+@pytest.mark.parametrize("variant", ["C2", "C2_scorr", "C2_60deg"])
+def test_planned_sweep_matches_unplanned_and_reference(ctx, variant):
+    """helios_fband_noniso_plan_build + helios_fband_noniso_planned (the Planck-independent part of the sweep
+    constants formed once per refresh) against helios_fband_noniso on the same state (<= 1e-12: the plan only
+    re-associates a few multiply-adds) and against the reference's kernel (<= the variant's flux tolerance),
+    over two consecutive flux solves with a changed temperature profile in between (the plan stays valid)."""
+    q = _variant(variant, ctx)
+    comp = Compute(ctx, verbose=False)
+    steps = ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+             "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass",
+             "calc_total_g_0_of_gas_and_clouds", "calculate_transmission", "calculate_direct_beamflux"]
+    for m in steps:
+        getattr(comp, m)(q)
+    names = ["F_down_wg", "F_up_wg", "Fc_down_wg", "Fc_up_wg"]
+    results = {}
+    for planned in (False, True):
+        q.dev_T_lay.set(np.asarray(q.T_lay, np.float64))
+        comp.interpolate_temperatures(q)
+        comp.interpolate_planck(q)
+        for n in names:
+            getattr(q, "dev_" + n).fill_zero()
+        if planned:
+            comp.build_flux_plan(q)
+            assert q._flux_plan_valid
+        else:
+            q._flux_plan_valid = False
+        out = []
+        for it in range(2):
+            comp.populate_spectral_flux_iteratively(q)
+            out.append([getattr(q, "dev_" + n).get() for n in names])
+            # a new temperature profile: only the Planck arrays change, the plan stays valid
+            q.dev_T_lay.set(np.asarray(q.T_lay, np.float64) + 35.0 * (it + 1))
+            comp.interpolate_temperatures(q)
+            comp.interpolate_planck(q)
+        results[planned] = out
+    for it in range(2):
+        for n, a, b in zip(names, results[False][it], results[True][it]):
+            assert_close(b, a, "planned vs unplanned, solve %d: %s" % (it, n), rtol=1e-12)
+    if ref_gpu.available():
+        # the reference's own kernel from the state the planned path started its last solve from
+        ref = ref_gpu.RefCompute(ctx.device)
+        q.dev_T_lay.set(np.asarray(q.T_lay, np.float64))
+        comp.interpolate_temperatures(q)
+        comp.interpolate_planck(q)
+        for n in names:
+            getattr(q, "dev_" + n).fill_zero()
+        ctx.synchronize()
+        ref.populate_spectral_flux_iteratively(q)
+        want = [getattr(q, "dev_" + n).get() for n in names]
+        tol = FLUX_TOL.get(variant, {})
+        for n, a, b in zip(names, want, results[True][0]):
+            assert_close(b, a, "planned vs kernels.cu: " + n, rtol=tol.get(n, 1e-10))
