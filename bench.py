@@ -171,7 +171,9 @@ def refresh(comp, q):
 
 
 def _bytes_per_cell(q):
-    """algorithmic bytes of ONE fused flux solve per layer*lambda*g cell (DESIGN.md 'roofline')"""
+    """algorithmic bytes of ONE fused flux solve per layer*lambda*g cell (DESIGN.md 'roofline').  The planned
+    non-isothermal sweep moves the same amount: 16 plan values + 2 previous fluxes in, 4 fluxes out = 22 doubles,
+    where the unplanned one reads 14 coefficients + 2 beam + 2 previous fluxes and writes 4 (+ band terms / ny)"""
     ny = float(q.ny)
     if q.iso == 1:
         return 6 * 8 + 8 + 8 + 16 + (8 + (8 if q.clouds == 1 else 0)) / ny
@@ -658,9 +660,12 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     line = dict(base, value=world * points * args.steps / (t_solve * 1e-3), ms_per_step=t_solve / args.steps,
                 scaling="weak",
                 config={"workload": "%s: %d layers x %d bins x %d gauss points, %s layers, %d fused flux passes, "
-                                    "clouds=%d, dir_beam=%d; one atmosphere per GPU" %
+                                    "clouds=%d, dir_beam=%d; one atmosphere per GPU%s" %
                                     (args.workload, q.nlayer, q.nbin, q.ny, "isothermal" if q.iso == 1 else "non-isothermal",
-                                     npass, q.clouds, q.dir_beam),
+                                     npass, q.clouds, q.dir_beam,
+                                     "; planned sweep (the Planck-independent step constants are formed with the "
+                                     "coefficients at the opacity refresh, every 10th iteration as in C:860, and are "
+                                     "inputs of the flux solve)" if getattr(q, "_flux_plan_valid", False) else ""),
                         "l2": l2, "sharding": "one atmosphere per rank, no collective"},
                 e2e={"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
@@ -671,7 +676,8 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                              "convergence flags D2H; every 10th iteration additionally rebuilds opacities, transmission "
                              "functions and the direct beam (C:860)"},
                 gpu_launches=int(launches),
-                roofline=_roofline("k_fband_wp (%s, all %d passes fused)" % ("iso" if q.iso == 1 else "noniso", npass),
+                roofline=_roofline("k_fband_wp (%s%s, all %d passes fused)" %
+                                   ("iso" if q.iso == 1 else "noniso", ", planned" if getattr(q, "_flux_plan_valid", False) else "", npass),
                                    _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload),
                 rce=rce)
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -13,6 +13,6 @@ echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fband -s 4 -c 2 \
     -o gpurun_out/prof_fband_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu --no-rce --only-main > gpurun_out/ncu_fband_$tag.log 2>&1
 echo "ncu fband rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_calc_trans|k_pt_gather|k_fdir|k_band_integrate|k_iter_prep|k_planck_interpol|k_temp_iter" -c 12 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_calc_trans|k_pt_gather|k_fdir|k_band_integrate|k_plan_build|k_planck_interpol|k_temp_iter" -c 14 \
     -o gpurun_out/prof_rebuild_$tag -f python bench.py --steps 3 --warmup 3 --no-cpu --no-rce --only-main > gpurun_out/ncu_rebuild_$tag.log 2>&1
 echo "ncu rebuild rc=$?"
