@@ -171,7 +171,13 @@ class Compute(object):
         q = quant
         if q.iso != 0 or not self.use_flux_plan or int(q.nlayer) > 128:
             return
-        n = 16 * q._size("ninterface_wg_nbin")
+        import ctypes
+        nd = ctypes.c_size_t()
+        backend._check(backend.lib().helios_fband_noniso_plan_size(self.ctx.handle, int(q.ninterface), int(q.nbin),
+                                                                   int(q.ny), ctypes.byref(nd)), "fband_noniso_plan_size")
+        n = int(nd.value)
+        if n == 0:
+            return
         if getattr(q, "dev_fband_plan", None) is None or q.dev_fband_plan.size != n:
             q.dev_fband_plan = self.ctx.zeros(n)
         self.ctx.call("fband_noniso_plan_build", q.dev_fband_plan, q.dev_F_dir_wg, q.dev_Fc_dir_wg, q.dev_w_0_upper,

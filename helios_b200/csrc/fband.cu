@@ -512,6 +512,7 @@ int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const d
                      const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
                      double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
                      double i2s);
+size_t fband_plan_size(int nint, int ncol, int nbatch);
 int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
                          const double* plan, const double* planck_lay, const double* planck_int,
                          const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
@@ -647,9 +648,21 @@ int helios_fband_noniso_plan_build(
     CpNonisoCoef cc{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
                     delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
                     G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
-    return fband_plan_build(ctx, plan, F_dir_wg, Fc_dir_wg, cc, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0, mu_star,
-                            epsi, delta_tau_limit, numinterfaces, nbin, ny, clouds == 1, scat_corr == 1,
-                            i2s_transition);
+    const int rc = fband_plan_build(ctx, plan, F_dir_wg, Fc_dir_wg, cc, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0,
+                                    mu_star, epsi, delta_tau_limit, numinterfaces, nbin, ny, clouds == 1, scat_corr == 1,
+                                    i2s_transition);
+    if (rc < 0) {
+        helios_set_error("helios_fband_noniso_plan_build: more than 128 layers are not supported by the planned sweep");
+        return HELIOS_ERR_ARG;
+    }
+    return rc;
+}
+
+int helios_fband_noniso_plan_size(helios_ctx* ctx, int numinterfaces, int nbin, int ny, size_t* ndoubles) {
+    HCTX(ctx);
+    HARG(ndoubles != nullptr && numinterfaces > 1 && nbin > 0 && ny > 0);
+    *ndoubles = fband_plan_size(numinterfaces, nbin * ny, ctx->batch.nbatch);
+    return HELIOS_OK;
 }
 
 int helios_fband_noniso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, double* Fc_down_wg,

@@ -153,50 +153,72 @@ __device__ __forceinline__ PlanHalf plan_half(double w0, double M, double N, dou
     return h;
 }
 
-__global__ void __launch_bounds__(256)
+// Plan layout.  The plan is private to these two kernels, so it is stored in exactly the order the planned phase A
+// consumes it: for (tile, round m, thread t) the 16 constants of the thread's cell are 8 double2 values at
+//      plan2[((tile * CH + m) * 8 + k) * THREADS + t],   k = 0..7,
+// i.e. every warp-level load is one contiguous 512-byte run (the coefficient arrays themselves can only be read
+// as 64-byte row segments by an 8-column tile, which caps at 2.3 TB/s on B200: scripts/stream_bench.cu).
+// Behind the tiles: per (tile, column) the two surface constants (emission factor of K:1704, direct beam at BOA).
+template <int CH, int LPC, int NCOLS>
+__host__ __device__ inline size_t plan_cells_doubles(size_t ntiles_total) {
+    return ntiles_total * CH * 16 * (size_t)(NCOLS * LPC);
+}
+
+template <int CH, int LPC, int NCOLS>
+__global__ void __launch_bounds__(NCOLS * LPC)
 k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
              CpNonisoCoef cfg, const double* __restrict__ albedo, const double* __restrict__ g0_lay,
              const double* __restrict__ g0_int, CpScalars s) {
+    constexpr int THREADS = NCOLS * LPC;
     const int nint = s.nint, nlay = nint - 1, ncol = s.nbin * s.ny;
-    const long long per_atm = (long long)ncol * nlay;
-    const long long total = per_atm * s.nbatch;
+    const int ntile = (ncol + NCOLS - 1) / NCOLS;
     const double neg_mu = -s.mu_star;
-    for (long long ee = blockIdx.x * (long long)blockDim.x + threadIdx.x; ee < total;
-         ee += (long long)gridDim.x * blockDim.x) {
-        const int atm = (int)(ee / per_atm);
-        const long long el = ee - (long long)atm * per_atm;
-        const int i = (int)(el / ncol);
-        const int col = (int)(el - (long long)i * ncol);
+    double2* __restrict__ plan2 = reinterpret_cast<double2*>(plan);
+    double* __restrict__ extras = plan + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
+    const int c = threadIdx.x % NCOLS;
+    const int r = threadIdx.x / NCOLS;
+    for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
+        const int atm = gtile / ntile;
+        const int tile = gtile - atm * ntile;
+        const int col = min(tile * NCOLS + c, ncol - 1);
         const int x = col / s.ny;
-        const size_t e = (size_t)atm * ncol * nint + el;
-        const size_t bl = (size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i;
-        const size_t bi = (size_t)atm * s.nbin * nint + (size_t)x + (size_t)s.nbin * i;
-        double g0_up = s.g_0, g0_low = s.g_0;
-        if (s.clouds) {
-            const double gl = g0_lay[bl];
-            g0_up = (gl + g0_int[bi + s.nbin]) / 2.0;
-            g0_low = (g0_int[bi] + gl) / 2.0;
-        }
-        const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol], Fcdir = Fc_dir[e];
-        double E_u, E_l;
-        const double P_u = cfg.P_u[e], Gm_u = cfg.Gm_u[e];
-        const PlanHalf u = plan_half(cfg.w0_u[e], cfg.M_u[e], cfg.N_u[e], P_u, cfg.Gp_u[e], Gm_u,
-                                     cfg.dtau_u[e] + cfg.dtc_u[bl], g0_up, Fcdir, Fdir_ip1, Gm_u, P_u, true, neg_mu, s, E_u);
-        const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e], Gm_l = cfg.Gm_l[e];
-        const PlanHalf l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, cfg.Gp_l[e], Gm_l,
-                                     cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low, Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
-        double* __restrict__ p = plan + e;
-        const size_t ps = (size_t)s.plan_stride;
-        p[0] = u.a;       p[ps] = u.b;       p[2 * ps] = u.k0d;  p[3 * ps] = u.k1d;
-        p[4 * ps] = u.k2d; p[5 * ps] = u.k0u; p[6 * ps] = u.k1u;  p[7 * ps] = u.k2u;
-        p[8 * ps] = l.a;   p[9 * ps] = l.b;   p[10 * ps] = l.k0d; p[11 * ps] = l.k1d;
-        p[12 * ps] = l.k2d; p[13 * ps] = l.k0u; p[14 * ps] = l.k1u; p[15 * ps] = l.k2u;
-        if (i == 0) {  // surface constants in the spare row nlay (K:1704: w0 and E of layer 0's lower half)
-            const size_t top = (size_t)atm * ncol * nint + (size_t)ncol * nlay + col;
-            const double A_s = albedo[x];
-            plan[top] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0_l)),
+#pragma unroll
+        for (int m = 0; m < CH; m++) {
+            const int i = r + LPC * m;
+            if (i >= nlay) continue;
+            const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * i;
+            const size_t bl = (size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i;
+            const size_t bi = (size_t)atm * s.nbin * nint + (size_t)x + (size_t)s.nbin * i;
+            double g0_up = s.g_0, g0_low = s.g_0;
+            if (s.clouds) {
+                const double gl = g0_lay[bl];
+                g0_up = (gl + g0_int[bi + s.nbin]) / 2.0;
+                g0_low = (g0_int[bi] + gl) / 2.0;
+            }
+            const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol], Fcdir = Fc_dir[e];
+            double E_u, E_l;
+            const double P_u = cfg.P_u[e], Gm_u = cfg.Gm_u[e];
+            const PlanHalf u = plan_half(cfg.w0_u[e], cfg.M_u[e], cfg.N_u[e], P_u, cfg.Gp_u[e], Gm_u,
+                                         cfg.dtau_u[e] + cfg.dtc_u[bl], g0_up, Fcdir, Fdir_ip1, Gm_u, P_u, true, neg_mu, s, E_u);
+            const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e], Gm_l = cfg.Gm_l[e];
+            const PlanHalf l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, cfg.Gp_l[e], Gm_l,
+                                         cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low, Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
+            double2* __restrict__ p = plan2 + ((size_t)gtile * CH + m) * 8 * THREADS + threadIdx.x;
+            p[0] = make_double2(u.a, u.b);
+            p[THREADS] = make_double2(u.k0d, u.k1d);
+            p[2 * THREADS] = make_double2(u.k2d, u.k0u);
+            p[3 * THREADS] = make_double2(u.k1u, u.k2u);
+            p[4 * THREADS] = make_double2(l.a, l.b);
+            p[5 * THREADS] = make_double2(l.k0d, l.k1d);
+            p[6 * THREADS] = make_double2(l.k2d, l.k0u);
+            p[7 * THREADS] = make_double2(l.k1u, l.k2u);
+            if (i == 0) {  // surface constants (K:1704: w0 and E of layer 0's lower half)
+                const double A_s = albedo[x];
+                double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + c) * 2;
+                ex[0] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0_l)),
                                   __dsub_rn(E_l, w0_l));
-            plan[ps + top] = Fdir_i;
+                ex[1] = Fdir_i;
+            }
         }
     }
 }
@@ -246,16 +268,22 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
             const int x = col / s.ny;
             const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
             const double* __restrict__ BI = planck_int + bio + (size_t)x * nint;
-            const double* __restrict__ plan = cfg.w0_u;
-            const size_t ps = (size_t)s.plan_stride;
+            constexpr int THREADS = NCOLS * LPC;
+            const double2* __restrict__ plan2 = reinterpret_cast<const double2*>(cfg.w0_u);
+            const double* __restrict__ extras = cfg.w0_u + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
 #pragma unroll
             for (int m = 0; m < CH; m++) {
                 const int i = r + LPC * m;
                 if (i < nlay) {
                     const size_t e = wgo + col + (size_t)ncol * i;
                     double v[16];
+                    const double2* __restrict__ p = plan2 + ((size_t)gtile * CH + m) * 8 * THREADS + threadIdx.x;
 #pragma unroll
-                    for (int z = 0; z < 16; z++) v[z] = plan[z * ps + e];
+                    for (int k = 0; k < 8; k++) {
+                        const double2 w = p[k * THREADS];  // 512 contiguous bytes per warp
+                        v[2 * k] = w.x;
+                        v[2 * k + 1] = w.y;
+                    }
                     const double fu = F_up[e], fcu = Fc_up[e];
                     const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
                     const int o = c * pitch + (i / CH) * STRIDE + (i % CH);
@@ -270,10 +298,10 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                     sm[8 * plane + o] = fu;
                     sm[9 * plane + o] = fcu;
                     if (i == 0) {
-                        const size_t top = wgo + (size_t)ncol * nlay + col;
+                        const double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + c) * 2;
                         c_alb[c] = albedo[x];
-                        c_fdir0[c] = plan[ps + top];
-                        c_emis[c] = __dmul_rn(plan[top], BL[nlay + 1]);
+                        c_fdir0[c] = ex[1];
+                        c_emis[c] = __dmul_rn(ex[0], BL[nlay + 1]);
                         c_toa[c] = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
                     }
                 }
@@ -618,20 +646,46 @@ static int dispatch_wp_planned(helios_ctx* ctx, double* F_down, double* F_up, do
     return -1;
 }
 
+template <int CH, int LPC, int NCOLS>
+static size_t plan_doubles(int ncol, int nbatch) {
+    const size_t ntiles = (size_t)((ncol + NCOLS - 1) / NCOLS) * nbatch;
+    return plan_cells_doubles<CH, LPC, NCOLS>(ntiles) + ntiles * NCOLS * 2;
+}
+
+// number of doubles a plan needs (0: more than 128 layers, not supported by the planned sweep)
+size_t fband_plan_size(int nint, int ncol, int nbatch) {
+    const int nlay = nint - 1;
+    if (nlay <= 32) return plan_doubles<1, 32, 8>(ncol, nbatch);
+    if (nlay <= 64) return plan_doubles<2, 32, 8>(ncol, nbatch);
+    if (nlay <= 96) return plan_doubles<3, 32, 8>(ncol, nbatch);
+    if (nlay <= 128) return plan_doubles<4, 32, 8>(ncol, nbatch);
+    return 0;
+}
+
+template <int CH, int LPC, int NCOLS>
+static int launch_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
+                             const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s) {
+    const int ntile = (s.nbin * s.ny + NCOLS - 1) / NCOLS * s.nbatch;
+    const int cap = ctx->num_sms * 3;
+    k_plan_build<CH, LPC, NCOLS><<<ntile < cap ? ntile : cap, NCOLS * LPC, 0, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo,
+                                                                                         g0_lay, g0_int, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
 int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
                      const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
                      double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
                      double i2s) {
     CpScalars s{g_0, 0.0, 0.0, 0.0, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, 0, clouds, scat_corr, 1, 0, 0,
                 0, 0, ctx->batch.nbatch, nullptr};
-    s.plan_stride = (long long)ctx->batch.nbatch * nint * nbin * ny;
-    const long long total = (long long)nbin * ny * (nint - 1) * ctx->batch.nbatch;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)ctx->num_sms * 32;
-    if (blocks > cap) blocks = cap;
-    k_plan_build<<<(int)blocks, 256, 0, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
+    const int nlay = nint - 1;
+    // the plan is laid out for the tile shape the planned sweep uses at this layer count (dispatch_wp_planned)
+    if (nlay <= 32) return launch_plan_build<1, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 64) return launch_plan_build<2, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 96) return launch_plan_build<3, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 128) return launch_plan_build<4, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    return -1;
 }
 
 int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
@@ -639,7 +693,6 @@ int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* 
                          const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
                          int dir_beam, int npass) {
     CpScalars s{0.0, Rstar, a, f_factor, 0.0, 0.0, 0.0, 0.0, nint, nbin, ny, dir_beam, 0, 0, npass, 0, 0, 0, 0, 1, nullptr};
-    s.plan_stride = (long long)ctx->batch.nbatch * nint * nbin * ny;
     CpNonisoCoef c{plan, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                    nullptr, nullptr, nullptr, nullptr, nullptr};
     return dispatch_wp_planned(ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, c, albedo, s, nbin * ny);

@@ -297,11 +297,13 @@ int helios_fband_noniso(
 /* Sweep plan for non-isothermal layers (B200-side addition, no reference counterpart).  Between two opacity refreshes
  * (10 RT iterations, C:860) only the Planck terms of fband_noniso's inputs change.  helios_fband_noniso_plan_build
  * evaluates everything else the sweep derives from the coefficient arrays -- P/M, N/M, the source and gradient
- * factors, the direct-beam sources -- once, into `plan`: 16 planes of nbatch*ninterface*ny*nbin doubles (call it
- * after calc_trans_noniso and fdir_noniso).  helios_fband_noniso_planned then performs the same npass fused sweeps
+ * factors, the direct-beam sources -- once, into `plan` (helios_fband_noniso_plan_size doubles, laid out in the
+ * order the sweep streams it; 0 = more than 128 layers, unsupported; in batch mode the size covers the batch).
+ * Call it after calc_trans_noniso and fdir_noniso.  helios_fband_noniso_planned then performs the same npass fused sweeps
  * as helios_fband_noniso from the plan plus the current Planck arrays and the previous fluxes; results agree with
  * helios_fband_noniso to rounding (<= 1e-13 relative on the fluxes; the plan folds the Planck-independent factors
  * into affine coefficients).  The plan is invalid as soon as any coefficient array, F_dir or surf_albedo changes. */
+int helios_fband_noniso_plan_size(helios_ctx* ctx, int numinterfaces, int nbin, int ny, size_t* ndoubles);
 int helios_fband_noniso_plan_build(
     helios_ctx* ctx, double* plan, const double* F_dir_wg, const double* Fc_dir_wg, const double* w_0_upper,
     const double* w_0_lower, const double* delta_tau_wg_upper, const double* delta_tau_wg_lower,
