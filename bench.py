@@ -629,8 +629,7 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
         if k % 10 == 0:
             refresh(comp, q)
         else:
-            comp.interpolate_temperatures(q)
-            comp.interpolate_planck(q)
+            comp.prepare_iteration(q)  # interpolate_temperatures + interpolate_planck (C:856-857), one launch
         flux_solve()
         comp.rad_temp_iteration(q)
         for j, name in enumerate(("F_net", "F_up_tot", "F_down_tot")):

@@ -198,9 +198,7 @@ class BatchCompute(Compute):
         counter advance are one launch (5 launches per iteration instead of 9); bitwise the same results."""
         q = quant
         if fused:
-            self.ctx.call("iteration_prepare", q.dev_T_lay, q.dev_T_int, q.dev_planckband_lay,
-                          q.dev_planckband_int if q.iso == 0 else None, q.dev_planckband_grid, q.dev_starflux,
-                          q.real_star, q.nlayer, q.nbin, q.plancktable_dim, q.plancktable_step)
+            self.prepare_iteration(q)
         else:
             self.interpolate_temperatures(q)
             self.interpolate_planck(q)

@@ -119,6 +119,14 @@ class Compute(object):
                           quant.dev_planckband_grid, quant.ninterface, quant.nbin, quant.plancktable_dim,
                           quant.plancktable_step)
 
+    def prepare_iteration(self, quant):
+        """interpolate_temperatures + interpolate_planck (C:856-857) as ONE launch (helios_iteration_prepare):
+        bitwise the same results; what every RT iteration does before its flux solve"""
+        q = quant
+        self.ctx.call("iteration_prepare", q.dev_T_lay, q.dev_T_int, q.dev_planckband_lay,
+                      q.dev_planckband_int if q.iso == 0 else None, q.dev_planckband_grid, q.dev_starflux,
+                      q.real_star, q.nlayer, q.nbin, q.plancktable_dim, q.plancktable_step)
+
     def calc_total_g_0_of_gas_and_clouds(self, quant):  # C:331-362
         self.ctx.call("calc_total_g_0_of_gas_and_clouds", quant.dev_scat_cross_lay, quant.dev_g_0_all_clouds_lay,
                       quant.dev_scat_cross_all_clouds_lay, quant.dev_g_0_tot_lay, quant.g_0, quant.nbin, quant.nlayer)
@@ -337,8 +345,7 @@ class Compute(object):
             it = int(quant.iter_value)
             if it % 100 == 0:
                 ev_loop[0].record()
-            self.interpolate_temperatures(quant)
-            self.interpolate_planck(quant)
+            self.prepare_iteration(quant)  # interpolate_temperatures + interpolate_planck, one launch
             if it % 10 == 0:
                 self._refresh_atmosphere(quant)
             self._flux_solve(quant)

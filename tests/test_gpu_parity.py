@@ -408,3 +408,21 @@ def test_planned_sweep_matches_unplanned_and_reference(ctx, variant):
         tol = FLUX_TOL.get(variant, {})
         for n, a, b in zip(names, want, results[True][0]):
             assert_close(b, a, "planned vs kernels.cu: " + n, rtol=tol.get(n, 1e-10))
+
+
+@pytest.mark.parametrize("config", ["C1", "C2"])
+def test_fused_iteration_prepare_is_bit_identical(ctx, config):
+    """helios_iteration_prepare == temp_inter + planck_interpol_layer (+ planck_interpol_interface), bit for bit"""
+    q = _variant(config, ctx)
+    comp = Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    comp.interpolate_temperatures(q)
+    comp.interpolate_planck(q)
+    names = ["T_int", "planckband_lay"] + ([] if q.iso == 1 else ["planckband_int"])
+    want = [getattr(q, "dev_" + n).get() for n in names]
+    for n in names:
+        getattr(q, "dev_" + n).fill_zero()
+    comp.prepare_iteration(q)
+    for n, w in zip(names, want):
+        assert np.array_equal(getattr(q, "dev_" + n).get(), w), n
