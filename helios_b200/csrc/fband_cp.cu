@@ -31,7 +31,7 @@
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
-    long long plan_stride;  // PLANNED: elements per plan plane (nbatch * ninterface * ncol)
+    long long reserved;     // (kept so that the positional initialisers below stay aligned)
     int no_beam;      // F_dir / Fc_dir are known to be all -0.0: do not load them, nor G+/-
     int nbatch;       // atmospheres per launch (helios_ctx_set_batch), 1 otherwise
     const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
