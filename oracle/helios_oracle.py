@@ -5,13 +5,15 @@ below as K:line), vectorised over the (wavelength, Gauss-point) columns with Pyt
 Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
 `bench.py` may import this module; nothing under `helios_b200/` does.
 
-Parity status: the reference ships no tests, golden vectors or fixtures for this path (SURVEY.md 4,
-8c) and its Python side cannot be imported here (PyCUDA/h5py/astropy absent), so this restatement is
-pinned in two other ways:
-  * closed-form known-answer tests derived from the reference formulas (tests/test_oracle_kat.py);
-  * on the GPU box, against the reference's own kernels.cu compiled verbatim to `oracle/_ref/` and
-    launched with the block/grid shapes of computation.py (oracle/ref_gpu.py, tests/test_ref_cubin.py).
-Until that second check has run green on a GPU, treat the file-level status as "parity unpinned".
+Parity status: PINNED against outputs of the reference itself.  The reference ships no tests, golden vectors or
+fixtures for this path and its Python side cannot be imported here (PyCUDA/h5py/astropy
+absent), so the pin is the reference's own kernels.cu, compiled verbatim to `oracle/_ref/` and launched with the
+block/grid shapes of computation.py (oracle/ref_gpu.py):
+  * tests/golden/ref_kernels_golden.npz holds its outputs at every launch site for 11 seeded cases (generated on a
+    B200 by tests/golden/make_ref_kernel_golden.py); tests/test_oracle_golden.py (CPU) holds this module to them,
+    stage by stage, at 1e-10 with four documented conditioning exceptions;
+  * tests/test_gpu_parity.py / test_gpu_mixing.py compare it live with the same kernels on the GPU box;
+  * tests/test_oracle_kat.py checks closed-form known answers derived from the reference's formulas.
 
 Array conventions are the reference's: "wg" arrays flat [i][x][y] (y fastest, K:1076), band arrays flat
 [i][x] (K:2456), Planck arrays flat [x][i] (i fastest, K:940/1004).  Everything is float64.
