@@ -552,6 +552,15 @@ def run_ours(args):
                     "setup_s": time.perf_counter() - t0}
                 del r
                 extra["C5_batched_grid"]["rce"] = rce_batch(ctx, 32)
+                # the headline physics (C2: non-isothermal, clouds, beam; planned sweep) as a batch of 32 atmospheres:
+                # the dominant kernel without the single-atmosphere tail effect (963 tiles on 296 CTAs)
+                r = bench_batch(ctx, 0, 32, 32, max(5, steps // 5), 3, flush, config="C2")
+                extra["C2_batched_grid_32"] = {
+                    "workload": r["workload"].replace("C5:", "C2 physics:"), "value": r["points"] / (r["t_solve"] * 1e-3),
+                    "unit": UNIT, "ms_per_step": r["t_solve"],
+                    "roofline": _roofline("k_fband_wp (noniso, planned, %d passes fused, 32 atmospheres)" % r["npass"],
+                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C2batch")}
+                del r
             except Exception as e:  # noqa: BLE001 -- the main line must survive a failing extra
                 extra["C5_batched_grid"] = {"error": repr(e)}
             r = None
