@@ -28,6 +28,16 @@
 #include "sweep_math.cuh"
 #include <cstdlib>
 
+#ifndef ISO_NCOLS
+#define ISO_NCOLS 8  // columns per tile of the isothermal sweep at 81..112 layers: 128-thread CTAs, 4 per SM (measured
+                     // 1-2 % faster than 16 columns / 256 threads / 2 per SM: more CTAs in different phases overlap better)
+#endif
+#ifndef PLAN_NCOLS
+#define PLAN_NCOLS 4  // columns per tile of the planned sweep: 128-thread CTAs, 4 per SM; a single C2 atmosphere is
+                      // 1925 tiles on 592 CTA slots instead of 963 on 296 -- the same 3.25 waves but half as long a tail
+                      // (measured 65.1 -> 61.9 us)
+#endif
+
 struct CpScalars {
     double g_0, Rstar, a, f_factor, mu_star, epsi, delta_tau_limit, i2s_transition;
     int nint, nbin, ny, dir_beam, clouds, scat_corr, npass, nchunk, colpitch;
@@ -230,7 +240,7 @@ k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const 
 // Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
 template <bool NONISO, int CH, int LPC, int NCOLS, bool PLANNED>
-__global__ void __launch_bounds__(NCOLS * LPC, 2)
+__global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
 k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
            double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
            const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
@@ -590,7 +600,8 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     s.nbatch = ctx->batch.nbatch;
     s.done = ctx->batch.active ? ctx->batch.done : nullptr;
     int per_sm = (int)((228 * 1024) / (smem + 1024));
-    if (per_sm > 2) per_sm = 2;  // __launch_bounds__(.., 2)
+    const int max_per_sm = (NCOLS * LPC <= 128) ? 4 : 2;  // __launch_bounds__
+    if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
     auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS, PLANNED>;
@@ -620,7 +631,7 @@ static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
         if (nlay <= 32) return launch_wp<NONISO, 2, 16, 16>(WP_ARGS);
         if (nlay <= 48) return launch_wp<NONISO, 3, 16, 16>(WP_ARGS);
         if (nlay <= 80) return launch_wp<NONISO, 5, 16, 16>(WP_ARGS);
-        if (nlay <= 112) return launch_wp<NONISO, 7, 16, 16>(WP_ARGS);
+        if (nlay <= 112) return launch_wp<NONISO, 7, 16, ISO_NCOLS>(WP_ARGS);
         if (nlay <= 128) return launch_wp<NONISO, 8, 16, 16>(WP_ARGS);
         if (nlay <= 256) return launch_wp<NONISO, 8, 32, 8>(WP_ARGS);
     }
@@ -638,10 +649,10 @@ static int dispatch_wp_planned(helios_ctx* ctx, double* F_down, double* F_up, do
     const double* g0_lay = nullptr;
     const double* g0_int = nullptr;
 #define WP_ARGS ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo, g0_lay, g0_int, s, ncol
-    if (nlay <= 32) return launch_wp<true, 1, 32, 8, true>(WP_ARGS);
-    if (nlay <= 64) return launch_wp<true, 2, 32, 8, true>(WP_ARGS);
-    if (nlay <= 96) return launch_wp<true, 3, 32, 8, true>(WP_ARGS);
-    if (nlay <= 128) return launch_wp<true, 4, 32, 8, true>(WP_ARGS);
+    if (nlay <= 32) return launch_wp<true, 1, 32, PLAN_NCOLS, true>(WP_ARGS);
+    if (nlay <= 64) return launch_wp<true, 2, 32, PLAN_NCOLS, true>(WP_ARGS);
+    if (nlay <= 96) return launch_wp<true, 3, 32, PLAN_NCOLS, true>(WP_ARGS);
+    if (nlay <= 128) return launch_wp<true, 4, 32, PLAN_NCOLS, true>(WP_ARGS);
 #undef WP_ARGS
     return -1;
 }
@@ -655,10 +666,10 @@ static size_t plan_doubles(int ncol, int nbatch) {
 // number of doubles a plan needs (0: more than 128 layers, not supported by the planned sweep)
 size_t fband_plan_size(int nint, int ncol, int nbatch) {
     const int nlay = nint - 1;
-    if (nlay <= 32) return plan_doubles<1, 32, 8>(ncol, nbatch);
-    if (nlay <= 64) return plan_doubles<2, 32, 8>(ncol, nbatch);
-    if (nlay <= 96) return plan_doubles<3, 32, 8>(ncol, nbatch);
-    if (nlay <= 128) return plan_doubles<4, 32, 8>(ncol, nbatch);
+    if (nlay <= 32) return plan_doubles<1, 32, PLAN_NCOLS>(ncol, nbatch);
+    if (nlay <= 64) return plan_doubles<2, 32, PLAN_NCOLS>(ncol, nbatch);
+    if (nlay <= 96) return plan_doubles<3, 32, PLAN_NCOLS>(ncol, nbatch);
+    if (nlay <= 128) return plan_doubles<4, 32, PLAN_NCOLS>(ncol, nbatch);
     return 0;
 }
 
@@ -666,7 +677,14 @@ template <int CH, int LPC, int NCOLS>
 static int launch_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
                              const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s) {
     const int ntile = (s.nbin * s.ny + NCOLS - 1) / NCOLS * s.nbatch;
-    const int cap = ctx->num_sms * 3;
+    // as many resident CTAs as the register file allows (the kernel strides over the tiles): 3 of 256 threads, 5 of 128
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_build<CH, LPC, NCOLS>, NCOLS * LPC, 0) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 3;
+    }
+    const int cap = ctx->num_sms * per_sm;
     k_plan_build<CH, LPC, NCOLS><<<ntile < cap ? ntile : cap, NCOLS * LPC, 0, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo,
                                                                                          g0_lay, g0_int, s);
     HLAUNCHED(ctx);
@@ -681,10 +699,10 @@ int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const d
                 0, 0, ctx->batch.nbatch, nullptr};
     const int nlay = nint - 1;
     // the plan is laid out for the tile shape the planned sweep uses at this layer count (dispatch_wp_planned)
-    if (nlay <= 32) return launch_plan_build<1, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 64) return launch_plan_build<2, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 96) return launch_plan_build<3, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 128) return launch_plan_build<4, 32, 8>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 32) return launch_plan_build<1, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 64) return launch_plan_build<2, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 96) return launch_plan_build<3, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
+    if (nlay <= 128) return launch_plan_build<4, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
     return -1;
 }
 
