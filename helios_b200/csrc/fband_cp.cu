@@ -24,6 +24,7 @@
 // Measured deviation from the reference's kernels: <= ~1e-13 relative (tests/test_gpu_parity.py; the bar
 // is 1e-10).  The bit-faithful evaluation order lives in the column-serial kernels of fband.cu
 // (helios_ctx_set_fband_mode(ctx, 1)); consecutive launches and one fused launch agree bit for bit.
+#include <type_traits>
 #include "common.cuh"
 #include "sweep_math.cuh"
 #include <cstdlib>
@@ -119,10 +120,10 @@ __device__ __forceinline__ void beam_pair(double Fa, double Fb, double neg_mu, d
 // source terms are affine in the Planck values of a half-layer,
 //      s = k0 + k1 * B_layer + k2 * B_interface,
 // so k_plan_build evaluates, once per refresh and with the same building blocks as phase A, the 8 constants
-// [a, b, k0d, k1d, k2d, k0u, k1u, k2u] of every half-layer into 16 planes laid out like the coefficient arrays
-// ([i][column]); the planned phase A then reads 16 + 2 values per cell instead of 24 and does 8 multiply-adds
-// instead of ~650 instructions with 12 divisions.  Row nlay of planes 0 and 1 carries the per-column surface
-// constants (emission factor of K:1704, direct beam at BOA).  Rounding differs from the reference's operation
+// [a, b, k0d, k1d, k2d, k0u, k1u, k2u] of every half-layer; the planned sweep (k_fband_lane) then reads 16 + 2 values
+// per cell instead of 24 and does 8 multiply-adds instead of ~650 instructions with 12 divisions.  Per column the plan
+// also carries the surface constants (emission factor of K:1704, direct beam at BOA).  Rounding differs from the
+// reference's operation
 // order by a few ulp of the source terms (measured against the unplanned kernel: <= 1e-13 on the fluxes).
 // ------------------------------------------------------------------------------------------------
 struct PlanHalf {
@@ -163,9 +164,10 @@ __device__ __forceinline__ PlanHalf plan_half(double w0, double M, double N, dou
     return h;
 }
 
-// Plan layout.  The plan is private to these two kernels, so it is stored in exactly the order the planned phase A
-// consumes it: for (tile, round m, thread t) the 16 constants of the thread's cell are 8 double2 values at
-//      plan2[((tile * CH + m) * 8 + k) * THREADS + t],   k = 0..7,
+// Plan layout.  The plan is private to k_plan_build and k_fband_lane, so it is stored in exactly the order the sweep
+// lanes consume it: a tile is NCOLS columns, sweep thread t = column * LPC + chunk owns layers chunk * CH + k
+// (k = 0..CH-1), and the 16 constants of its slot-k layer are 8 double2 values at
+//      plan2[((tile * CH + k) * 8 + j) * THREADS + t],   j = 0..7,
 // i.e. every warp-level load is one contiguous 512-byte run (the coefficient arrays themselves can only be read
 // as 64-byte row segments by an 8-column tile, which caps at 2.3 TB/s on B200: scripts/stream_bench.cu).
 // Behind the tiles: per (tile, column) the two surface constants (emission factor of K:1704, direct beam at BOA).
@@ -213,7 +215,8 @@ k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const 
             const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e], Gm_l = cfg.Gm_l[e];
             const PlanHalf l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, cfg.Gp_l[e], Gm_l,
                                          cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low, Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
-            double2* __restrict__ p = plan2 + ((size_t)gtile * CH + m) * 8 * THREADS + threadIdx.x;
+            // lane order: the cell of layer i, column c belongs to sweep thread c * LPC + i / CH, slot i % CH
+            double2* __restrict__ p = plan2 + ((size_t)gtile * CH + (i % CH)) * 8 * THREADS + (c * LPC + i / CH);
             p[0] = make_double2(u.a, u.b);
             p[THREADS] = make_double2(u.k0d, u.k1d);
             p[2 * THREADS] = make_double2(u.k2d, u.k0u);
@@ -239,7 +242,7 @@ k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const 
 //                              F_up(prev), Fc_up(prev)                                               (10)
 // Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS, bool PLANNED>
+template <bool NONISO, int CH, int LPC, int NCOLS>
 __global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
 k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
            double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
@@ -270,53 +273,7 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
         const size_t bio = (size_t)atm * s.nbin * nint;        // [interface][x] arrays
         // ================= phase A: coalesced streaming, lanes along columns =================
         // Every thread owns at most CH layer rows (nlay <= LPC*CH).
-        if constexpr (PLANNED) {
-            // planned form (see k_plan_build): cfg.w0_u is the plan; 16 + 2 loads and 8 multiply-adds per cell
-            const int c = threadIdx.x % NCOLS;
-            const int r = threadIdx.x / NCOLS;
-            const int col = min(tile * NCOLS + c, ncol - 1);
-            const int x = col / s.ny;
-            const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
-            const double* __restrict__ BI = planck_int + bio + (size_t)x * nint;
-            constexpr int THREADS = NCOLS * LPC;
-            const double2* __restrict__ plan2 = reinterpret_cast<const double2*>(cfg.w0_u);
-            const double* __restrict__ extras = cfg.w0_u + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
-#pragma unroll
-            for (int m = 0; m < CH; m++) {
-                const int i = r + LPC * m;
-                if (i < nlay) {
-                    const size_t e = wgo + col + (size_t)ncol * i;
-                    double v[16];
-                    const double2* __restrict__ p = plan2 + ((size_t)gtile * CH + m) * 8 * THREADS + threadIdx.x;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        const double2 w = p[k * THREADS];  // 512 contiguous bytes per warp
-                        v[2 * k] = w.x;
-                        v[2 * k + 1] = w.y;
-                    }
-                    const double fu = F_up[e], fcu = Fc_up[e];
-                    const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
-                    const int o = c * pitch + (i / CH) * STRIDE + (i % CH);
-                    sm[o] = v[0];
-                    sm[plane + o] = v[1];
-                    sm[2 * plane + o] = __fma_rn(v[3], Blay, __fma_rn(v[4], Bint_hi, v[2]));
-                    sm[3 * plane + o] = __fma_rn(v[6], Blay, __fma_rn(v[7], Bint_hi, v[5]));
-                    sm[4 * plane + o] = v[8];
-                    sm[5 * plane + o] = v[9];
-                    sm[6 * plane + o] = __fma_rn(v[11], Blay, __fma_rn(v[12], Bint_lo, v[10]));
-                    sm[7 * plane + o] = __fma_rn(v[14], Blay, __fma_rn(v[15], Bint_lo, v[13]));
-                    sm[8 * plane + o] = fu;
-                    sm[9 * plane + o] = fcu;
-                    if (i == 0) {
-                        const double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + c) * 2;
-                        c_alb[c] = albedo[x];
-                        c_fdir0[c] = ex[1];
-                        c_emis[c] = __dmul_rn(ex[0], BL[nlay + 1]);
-                        c_toa[c] = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
-                    }
-                }
-            }
-        } else {
+        {
             const int c = threadIdx.x % NCOLS;
             const int r = threadIdx.x / NCOLS;  // 0 .. LPC-1
             const int col = min(tile * NCOLS + c, ncol - 1);
@@ -581,9 +538,192 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// Planned sweep, lane-ordered plan.  The plan is private to k_plan_build and this kernel, so it is stored
+// per SWEEP LANE: thread t = column * LPC + chunk of a tile finds the 16 constants of its slot-k layer as 8 double2 at
+//      plan2[((tile * CH + k) * 8 + j) * THREADS + t],   j = 0..7
+// (512 contiguous bytes per warp and load).  Each lane derives the source terms of its own CH layers from the Planck
+// values, parks them in its private shared-memory slots and runs the chunk-parallel sweeps of k_fband_wp's phase B:
+// there is no phase A, no transposition through shared memory and no block-wide barrier -- a warp is one column and
+// the warps of a CTA drift freely, loads of one overlapping the shuffle scans of another.  The sweep arithmetic is
+// phase B of k_fband_wp operation for operation (an earlier build that staged the plan through phase A and shared
+// memory gave bit-identical fluxes at 62 us per C2 solve; this form takes 56 us).
+// ------------------------------------------------------------------------------------------------
+template <int CH, int LPC, int NCOLS, bool FULL>
+__global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
+k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
+             double* __restrict__ Fc_up, const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
+             const double* __restrict__ plan, const double* __restrict__ albedo, CpScalars s) {
+    extern __shared__ double sm[];  // [4 * CH][THREADS]: sd, su of the upper half, sd, su of the lower half, per slot
+    constexpr int THREADS = NCOLS * LPC;
+    const int nint = s.nint, nlay = nint - 1, nch = s.nchunk;
+    const int ncol = s.nbin * s.ny;
+    const int ntile = (ncol + NCOLS - 1) / NCOLS;
+    const int t = threadIdx.x;
+    const int cw = t / LPC;  // column of this lane segment
+    const int sl = t % LPC;  // chunk index
+    const int lo = sl * CH;
+    const bool act = sl < nch;
+    const int hi = min(lo + CH, nlay);
+    const double2* __restrict__ plan2 = reinterpret_cast<const double2*>(plan);
+    const double* __restrict__ extras = plan + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
+    double* __restrict__ my = sm + t;
+    for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
+        const int atm = gtile / ntile;
+        const int tile = gtile - atm * ntile;
+        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per block
+        const size_t wgo = (size_t)atm * ncol * nint;          // [i][x][y] arrays
+        const int col = tile * NCOLS + cw;
+        const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
+        const int colc = live ? col : ncol - 1;
+        const int x = colc / s.ny;
+        const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
+        const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
+        double a[2][CH], b[2][CH], Fu_reg[CH], Fd_reg[CH], Fcu_reg[CH], Fcd_reg[CH], cc[2][CH];
+        // load phase: per slot 8 x 16-byte plan loads (512 contiguous bytes per warp each), the previous upward
+        // fluxes and the Planck values; the source terms go to the lane's private shared-memory slots.  (Two slots
+        // of loads in flight per thread were measured slower: the registers are not there, the spills cost more.)
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const bool in = act && (FULL || lo + k < hi);
+            a[0][k] = a[1][k] = 1.0;  // identity step outside the column
+            b[0][k] = b[1][k] = 0.0;
+            Fu_reg[k] = Fcu_reg[k] = Fd_reg[k] = Fcd_reg[k] = 0.0;
+            double sdu = 0.0, suu = 0.0, sdl = 0.0, sul = 0.0;
+            if (in) {
+                const int i = lo + k;
+                const double2* __restrict__ p = plan2 + ((size_t)gtile * CH + k) * 8 * THREADS + t;
+                double v[16];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const double2 w = p[j * THREADS];
+                    v[2 * j] = w.x;
+                    v[2 * j + 1] = w.y;
+                }
+                const size_t e = wgo + colc + (size_t)ncol * i;
+                Fu_reg[k] = F_up[e];
+                Fcu_reg[k] = Fc_up[e];
+                const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
+                a[0][k] = v[0];
+                b[0][k] = v[1];
+                sdu = __fma_rn(v[3], Blay, __fma_rn(v[4], Bint_hi, v[2]));
+                suu = __fma_rn(v[6], Blay, __fma_rn(v[7], Bint_hi, v[5]));
+                a[1][k] = v[8];
+                b[1][k] = v[9];
+                sdl = __fma_rn(v[11], Blay, __fma_rn(v[12], Bint_lo, v[10]));
+                sul = __fma_rn(v[14], Blay, __fma_rn(v[15], Bint_lo, v[13]));
+            }
+            my[(0 * CH + k) * THREADS] = sdu;
+            my[(1 * CH + k) * THREADS] = suu;
+            my[(2 * CH + k) * THREADS] = sdl;
+            my[(3 * CH + k) * THREADS] = sul;
+        }
+        const double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + cw) * 2;
+        const double A_s = albedo[x], Fdir0 = ex[1], emis = __dmul_rn(ex[0], BL[nlay + 1]);
+        const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
+        // One pass = downward sweep + upward sweep.  Branch-free: cells outside the column are identity steps
+        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally and only the stores of the LAST pass
+        // (WRITE) are predicated.  FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
+        // per-cell "inside" selects vanish; otherwise the identity cells of the top lane pass the flux through.
+        const bool st_ok = live && act;
+        const size_t off = wgo + colc + (size_t)ncol * lo;
+        auto one_pass = [&](auto write_tag) {
+            constexpr bool WRITE = decltype(write_tag)::value;
+            // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
+            Aff m{1.0, 0.0};
+#pragma unroll
+            for (int k = CH - 1; k >= 0; k--) {
+                cc[0][k] = my[(0 * CH + k) * THREADS] - b[0][k] * Fcu_reg[k];
+                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                cc[1][k] = my[(2 * CH + k) * THREADS] - b[1][k] * Fu_reg[k];
+                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+            }
+            Aff sc = scan_from_top<LPC>(m, sl, nch);
+            const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
+            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
+            if (sl >= nch - 1) F = toa;
+            if (WRITE && live && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
+#pragma unroll
+            for (int k = CH - 1; k >= 0; k--) {
+                const bool in = FULL || lo + k < hi;
+                double Fn = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                if (!FULL) Fn = in ? Fn : F;
+                Fcd_reg[k] = Fn;
+                if (WRITE) { if (st_ok && in) Fc_down[off + (size_t)(k * ncol)] = Fn; }
+                double Fm = tiny_to_abs(a[1][k] * Fn + cc[1][k]);
+                if (!FULL) Fm = in ? Fm : F;
+                Fd_reg[k] = Fm;
+                if (WRITE) { if (st_ok && in) F_down[off + (size_t)(k * ncol)] = Fm; }
+                F = Fm;
+            }
+            // the flux at my top interface as WALKED (and stored) by the lane above
+            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+            if (sl >= nch - 1) Fd_hi = toa;
+            // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
+            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+            m = Aff{1.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                // identity cells above the column carry the entering flux (toa) unchanged, so no "inside" test
+                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                cc[1][k] = my[(3 * CH + k) * THREADS] - b[1][k] * Fcd_reg[k];
+                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+                cc[0][k] = my[(1 * CH + k) * THREADS] - b[0][k] * Fd_top;
+                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+            }
+            sc = scan_from_bottom<LPC>(m, sl);
+            const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
+            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
+            if (sl == 0) F = fu0;
+            if (WRITE && live && sl == 0) F_up[wgo + colc] = fu0;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const bool in = FULL || lo + k < hi;
+                Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
+                // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
+                double Fn = a[1][k] * F + cc[1][k];
+                if (!FULL) Fn = in ? Fn : F;
+                Fcu_reg[k] = Fn;
+                if (WRITE) { if (st_ok && in) Fc_up[off + (size_t)(k * ncol)] = Fn; }
+                double Fm = tiny_to_abs(a[0][k] * Fn + cc[0][k]);
+                if (!FULL) Fm = in ? Fm : F;
+                if (WRITE) { if (st_ok && in) F_up[off + (size_t)((k + 1) * ncol)] = Fm; }
+                F = Fm;
+            }
+            // next pass: the flux at my bottom interface as walked by the lane below
+            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
+        };
+        for (int pass = 0; pass + 1 < s.npass; pass++) one_pass(std::false_type{});
+        one_pass(std::true_type{});  // only the last pass writes the flux arrays
+    }
+}
+
+template <int CH, int LPC, int NCOLS>
+static int launch_lane(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                       const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
+                       CpScalars s, int ncol) {
+    const int nlay = s.nint - 1;
+    s.nchunk = (nlay + CH - 1) / CH;
+    if (s.nchunk > LPC) return -1;
+    constexpr int THREADS = NCOLS * LPC;
+    const size_t smem = (size_t)4 * CH * THREADS * sizeof(double);
+    const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
+    s.nbatch = ctx->batch.nbatch;
+    s.done = ctx->batch.active ? ctx->batch.done : nullptr;
+    const int per_sm = (THREADS <= 128) ? 4 : 2;  // __launch_bounds__
+    const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
+    auto kern = (nlay == s.nchunk * CH) ? k_fband_lane<CH, LPC, NCOLS, true> : k_fband_lane<CH, LPC, NCOLS, false>;
+    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, THREADS, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch planning: LPC = 16 lanes per column (two columns per warp) while nlay <= 128, else 32
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS, bool PLANNED = false>
+template <bool NONISO, int CH, int LPC, int NCOLS>
 static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
                      const double* F_dir, const double* Fc_dir, const double* planck_lay, const double* planck_int,
                      CpNonisoCoef c, const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s,
@@ -604,7 +744,7 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
-    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS, PLANNED>;
+    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS>;
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NCOLS * LPC, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
                                                    planck_int, c, albedo, g0_lay, g0_int, s);
@@ -639,21 +779,17 @@ static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
     return -1;
 }
 
-// planned non-isothermal sweep: same tile shapes as the unplanned kernel
+// planned non-isothermal sweep: one warp per column, CH = ceil(nlay / 32) layers per lane
 static int dispatch_wp_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
                                const double* planck_lay, const double* planck_int, CpNonisoCoef c,
                                const double* albedo, CpScalars s, int ncol) {
     const int nlay = s.nint - 1;
-    const double* F_dir = nullptr;
-    const double* Fc_dir = nullptr;
-    const double* g0_lay = nullptr;
-    const double* g0_int = nullptr;
-#define WP_ARGS ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo, g0_lay, g0_int, s, ncol
-    if (nlay <= 32) return launch_wp<true, 1, 32, PLAN_NCOLS, true>(WP_ARGS);
-    if (nlay <= 64) return launch_wp<true, 2, 32, PLAN_NCOLS, true>(WP_ARGS);
-    if (nlay <= 96) return launch_wp<true, 3, 32, PLAN_NCOLS, true>(WP_ARGS);
-    if (nlay <= 128) return launch_wp<true, 4, 32, PLAN_NCOLS, true>(WP_ARGS);
-#undef WP_ARGS
+#define LN_ARGS ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, c.w0_u, albedo, s, ncol
+    if (nlay <= 32) return launch_lane<1, 32, PLAN_NCOLS>(LN_ARGS);
+    if (nlay <= 64) return launch_lane<2, 32, PLAN_NCOLS>(LN_ARGS);
+    if (nlay <= 96) return launch_lane<3, 32, PLAN_NCOLS>(LN_ARGS);
+    if (nlay <= 128) return launch_lane<4, 32, PLAN_NCOLS>(LN_ARGS);
+#undef LN_ARGS
     return -1;
 }
 
