@@ -242,7 +242,7 @@ k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const 
 //                              F_up(prev), Fc_up(prev)                                               (10)
 // Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS>
+template <bool NONISO, int CH, int LPC, int NCOLS, bool FULL>
 __global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
 k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
            double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
@@ -423,23 +423,28 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
         }
         __syncthreads();
         // ================= phase B: LPC lanes per column, lane = chunk of CH layers =================
+        // Branch-free passes: cells outside the column are identity steps (a = 1, b = 0, s = 0), the arithmetic
+        // runs unconditionally and the stores follow the last pass.  A lane without a chunk
+        // (sl >= nch) recomputes chunk 0 -- nothing of it is ever consumed: the scans, the edge shuffles and the
+        // stores all look at sl < nch.  FULL (nlay == nch * CH): no partial chunk, the "inside" selects vanish.
         {
             const int cw = threadIdx.x / LPC;  // column of this lane segment
             const int sl = threadIdx.x % LPC;  // chunk index
             const int col = tile * NCOLS + cw;
             const bool live = col < ncol;      // uniform per segment; dead segments still shuffle
             const int colc = live ? col : ncol - 1;
-            const int lo = sl * CH;
             const bool act = sl < nch;
-            const int hi = min(lo + CH, nlay);
-            const int base = cw * pitch + sl * STRIDE;
+            const int lo = sl * CH;
+            const int hi = act ? min(lo + CH, nlay) : CH;  // idle lanes: chunk 0 is complete (nlay >= CH or nch == 1)
+            const int base = cw * pitch + (act ? sl : 0) * STRIDE;
             const double toa = c_toa[cw], A_s = c_alb[cw], Fdir0 = c_fdir0[cw], emis = c_emis[cw];
             // step constants kept in registers: a, b of every step; sd / su are re-read from shared memory
             constexpr int NS = NONISO ? 2 : 1;  // steps per layer
             double a[NS][CH], b[NS][CH], Fu_reg[CH], Fd_reg[CH], Fcu_reg[CH], Fcd_reg[CH], cc[NS][CH];
+            const int lo_c = act ? lo : 0;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
-                const bool in = act && lo + k < hi;
+                const bool in = FULL || lo_c + k < hi;
                 a[0][k] = in ? sm[base + k] : 1.0;  // identity step outside the column
                 b[0][k] = in ? sm[plane + base + k] : 0.0;
                 if (NONISO) {
@@ -450,13 +455,14 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                 Fcu_reg[k] = (NONISO && in) ? sm[9 * plane + base + k] : 0.0;
                 Fd_reg[k] = Fcd_reg[k] = 0.0;
             }
-            for (int pass = 0; pass < s.npass; pass++) {
-                const bool wr = live && pass == s.npass - 1;  // only the last pass writes the flux arrays
+            const bool st_ok = live && act;
+            const size_t off = wgo + colc + (size_t)ncol * lo;
+            auto one_pass = [&]() -> double {
                 // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
                 Aff m{1.0, 0.0};
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
-                    const bool in = act && lo + k < hi;
+                    const bool in = FULL || lo_c + k < hi;
                     if (NONISO) {
                         cc[0][k] = (in ? sm[2 * plane + base + k] : 0.0) - b[0][k] * Fcu_reg[k];
                         m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
@@ -468,24 +474,25 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                     }
                 }
                 Aff sc = scan_from_top<LPC>(m, sl, nch);
-                const double Fbot = sc.A * toa + sc.B;                       // flux leaving my chunk (interface lo)
-                double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);      // = flux entering it (interface hi)
+                const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
+                double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
                 if (sl >= nch - 1) F = toa;
-                if (wr && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
 #pragma unroll
                 for (int k = CH - 1; k >= 0; k--) {
-                    if (act && lo + k < hi) {
-                        if (NONISO) {
-                            F = tiny_to_abs(a[0][k] * F + cc[0][k]);
-                            Fcd_reg[k] = F;
-                            if (wr) Fc_down[wgo + colc + (size_t)ncol * (lo + k)] = F;
-                            F = tiny_to_abs(a[1][k] * F + cc[1][k]);
-                        } else {
-                            F = tiny_to_abs(a[0][k] * F + cc[0][k]);
-                        }
-                        Fd_reg[k] = F;
-                        if (wr) F_down[wgo + colc + (size_t)ncol * (lo + k)] = F;
+                    const bool in = FULL || lo_c + k < hi;
+                    if (NONISO) {
+                        double Fn = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                        if (!FULL) Fn = in ? Fn : F;  // identity cells pass the entering flux through unchanged
+                        Fcd_reg[k] = Fn;
+                        double Fm = tiny_to_abs(a[1][k] * Fn + cc[1][k]);
+                        if (!FULL) Fm = in ? Fm : F;
+                        F = Fm;
+                    } else {
+                        double Fm = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                        if (!FULL) Fm = in ? Fm : F;
+                        F = Fm;
                     }
+                    Fd_reg[k] = F;
                 }
                 // the flux at my top interface as WALKED (and stored) by the lane above: every flux consumed
                 // later is bit-identical to what the output arrays hold
@@ -497,8 +504,9 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                 m = Aff{1.0, 0.0};
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
-                    const bool in = act && lo + k < hi;
-                    const double Fd_top = (k + 1 < CH && lo + k + 1 < hi) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                    const bool in = FULL || lo_c + k < hi;
+                    // identity cells above the column hold the entering flux (= Fd_hi), so no "inside" test here
+                    const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
                     if (NONISO) {
                         cc[1][k] = (in ? sm[7 * plane + base + k] : 0.0) - b[1][k] * Fcd_reg[k];
                         m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
@@ -510,27 +518,55 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                     }
                 }
                 sc = scan_from_bottom<LPC>(m, sl);
-                const double Ftop = sc.A * fu0 + sc.B;                       // flux leaving my chunk (interface hi)
-                F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);               // = flux entering it (interface lo)
+                const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
+                F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
                 if (sl == 0) F = fu0;
-                if (wr && sl == 0) F_up[wgo + colc] = fu0;
 #pragma unroll
                 for (int k = 0; k < CH; k++) {
-                    if (act && lo + k < hi) {
-                        Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
-                        if (NONISO) {
-                            // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
-                            F = a[1][k] * F + cc[1][k];
-                            Fcu_reg[k] = F;
-                            if (wr) Fc_up[wgo + colc + (size_t)ncol * (lo + k)] = F;
-                        }
-                        F = tiny_to_abs(a[0][k] * F + cc[0][k]);
-                        if (wr) F_up[wgo + colc + (size_t)ncol * (lo + k + 1)] = F;
+                    const bool in = FULL || lo_c + k < hi;
+                    Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
+                    if (NONISO) {
+                        // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
+                        double Fn = a[1][k] * F + cc[1][k];
+                        if (!FULL) Fn = in ? Fn : F;
+                        Fcu_reg[k] = Fn;
+                        double Fm = tiny_to_abs(a[0][k] * Fn + cc[0][k]);
+                        if (!FULL) Fm = in ? Fm : F;
+                        F = Fm;
+                    } else {
+                        double Fm = tiny_to_abs(a[0][k] * F + cc[0][k]);
+                        if (!FULL) Fm = in ? Fm : F;
+                        F = Fm;
                     }
                 }
-                // next pass: the flux at my bottom interface as walked by the lane below
+                // the flux at my bottom interface as walked by the lane below (next pass, and what F_up holds there)
                 const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
                 Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
+                return F;  // the flux leaving my chunk upwards (interface hi)
+            };
+            double F_out = 0.0;
+            for (int pass = 0; pass < s.npass; pass++) F_out = one_pass();
+            // Only the fluxes of the last pass are stored, and every one of them is still in a register: the lane's
+            // downward fluxes at interfaces lo..lo+CH-1, its upward fluxes at the same interfaces (Fu_reg[0] is the
+            // value the lane below walked to, bit for bit) and, in the top lane, interface nlay.
+            if (st_ok) {
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    if (FULL || lo + k < hi) {
+                        const size_t e = off + (size_t)(k * ncol);
+                        F_down[e] = Fd_reg[k];
+                        F_up[e] = Fu_reg[k];
+                        if (NONISO) {
+                            Fc_down[e] = Fcd_reg[k];
+                            Fc_up[e] = Fcu_reg[k];
+                        }
+                    }
+                }
+                if (sl == nch - 1) {
+                    const size_t e = wgo + colc + (size_t)ncol * nlay;
+                    F_down[e] = toa;
+                    F_up[e] = F_out;
+                }
             }
         }
         __syncthreads();  // the next tile overwrites the shared planes
@@ -553,7 +589,7 @@ __global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
 k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
              double* __restrict__ Fc_up, const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
              const double* __restrict__ plan, const double* __restrict__ albedo, CpScalars s) {
-    extern __shared__ double sm[];  // [4 * CH][THREADS]: sd, su of the upper half, sd, su of the lower half, per slot
+    extern __shared__ double sm[];  // [CH * 6][THREADS] double2, thread-private columns (see the load phase)
     constexpr int THREADS = NCOLS * LPC;
     const int nint = s.nint, nlay = nint - 1, nch = s.nchunk;
     const int ncol = s.nbin * s.ny;
@@ -566,7 +602,8 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
     const int hi = min(lo + CH, nlay);
     const double2* __restrict__ plan2 = reinterpret_cast<const double2*>(plan);
     const double* __restrict__ extras = plan + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
-    double* __restrict__ my = sm + t;
+    double2* __restrict__ my2 = reinterpret_cast<double2*>(sm) + t;  // my private rows: [CH * 6][THREADS] double2
+    const unsigned my_s = (unsigned)__cvta_generic_to_shared(my2);
     for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
         const int atm = gtile / ntile;
         const int tile = gtile - atm * ntile;
@@ -579,80 +616,91 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
         const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
         const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
         double a[2][CH], b[2][CH], Fu_reg[CH], Fd_reg[CH], Fcu_reg[CH], Fcd_reg[CH], cc[2][CH];
-        // load phase: per slot 8 x 16-byte plan loads (512 contiguous bytes per warp each), the previous upward
-        // fluxes and the Planck values; the source terms go to the lane's private shared-memory slots.  (Two slots
-        // of loads in flight per thread were measured slower: the registers are not there, the spills cost more.)
+        // Load phase.  Everything a tile needs is requested at once, so the lane waits ONE memory round trip per tile
+        // instead of one per slot (registers allow only one slot of plan constants in flight, and with 16 warps per SM
+        // those round trips were 40 % of the stall samples): a, b (they live in registers for all passes anyway) and
+        // the previous upward fluxes go straight to their registers; the 12 Planck-term constants of each slot go
+        // from global to the lane's private shared-memory rows with 16-byte cp.async -- no registers involved.
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const bool in = act && (FULL || lo + k < hi);
             a[0][k] = a[1][k] = 1.0;  // identity step outside the column
             b[0][k] = b[1][k] = 0.0;
             Fu_reg[k] = Fcu_reg[k] = Fd_reg[k] = Fcd_reg[k] = 0.0;
-            double sdu = 0.0, suu = 0.0, sdl = 0.0, sul = 0.0;
             if (in) {
-                const int i = lo + k;
                 const double2* __restrict__ p = plan2 + ((size_t)gtile * CH + k) * 8 * THREADS + t;
-                double v[16];
+                constexpr int JJ[6] = {1, 2, 3, 5, 6, 7};
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const double2 w = p[j * THREADS];
-                    v[2 * j] = w.x;
-                    v[2 * j + 1] = w.y;
-                }
-                const size_t e = wgo + colc + (size_t)ncol * i;
+                for (int jj = 0; jj < 6; jj++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my_s + (unsigned)((k * 6 + jj) * THREADS * 16)),
+                                 "l"(p + JJ[jj] * THREADS)
+                                 : "memory");
+                const double2 u = p[0], l = p[4 * THREADS];
+                a[0][k] = u.x;
+                b[0][k] = u.y;
+                a[1][k] = l.x;
+                b[1][k] = l.y;
+                const size_t e = wgo + colc + (size_t)ncol * (lo + k);
                 Fu_reg[k] = F_up[e];
                 Fcu_reg[k] = Fc_up[e];
-                const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
-                a[0][k] = v[0];
-                b[0][k] = v[1];
-                sdu = __fma_rn(v[3], Blay, __fma_rn(v[4], Bint_hi, v[2]));
-                suu = __fma_rn(v[6], Blay, __fma_rn(v[7], Bint_hi, v[5]));
-                a[1][k] = v[8];
-                b[1][k] = v[9];
-                sdl = __fma_rn(v[11], Blay, __fma_rn(v[12], Bint_lo, v[10]));
-                sul = __fma_rn(v[14], Blay, __fma_rn(v[15], Bint_lo, v[13]));
             }
-            my[(0 * CH + k) * THREADS] = sdu;
-            my[(1 * CH + k) * THREADS] = suu;
-            my[(2 * CH + k) * THREADS] = sdl;
-            my[(3 * CH + k) * THREADS] = sul;
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
         const double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + cw) * 2;
         const double A_s = albedo[x], Fdir0 = ex[1], emis = __dmul_rn(ex[0], BL[nlay + 1]);
         const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // my own copies have landed (nobody else reads them)
+        // source terms from the Planck values, written over the head of each slot's rows:
+        // row 0 = (sd upper half, sd lower half) for the downward sweep, row 1 = (su upper, su lower) for the upward
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const bool in = act && (FULL || lo + k < hi);
+            double2 sd = make_double2(0.0, 0.0), su = make_double2(0.0, 0.0);
+            if (in) {
+                const int i = lo + k;
+                const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
+                double2 q[6];
+#pragma unroll
+                for (int jj = 0; jj < 6; jj++) q[jj] = my2[(k * 6 + jj) * THREADS];
+                // q[0] = (k0d, k1d), q[1] = (k2d, k0u), q[2] = (k1u, k2u) of the upper half; q[3..5] of the lower half
+                sd.x = __fma_rn(q[0].y, Blay, __fma_rn(q[1].x, Bint_hi, q[0].x));
+                su.x = __fma_rn(q[2].x, Blay, __fma_rn(q[2].y, Bint_hi, q[1].y));
+                sd.y = __fma_rn(q[3].y, Blay, __fma_rn(q[4].x, Bint_lo, q[3].x));
+                su.y = __fma_rn(q[5].x, Blay, __fma_rn(q[5].y, Bint_lo, q[4].y));
+            }
+            my2[(k * 6 + 0) * THREADS] = sd;
+            my2[(k * 6 + 1) * THREADS] = su;
+        }
         // One pass = downward sweep + upward sweep.  Branch-free: cells outside the column are identity steps
-        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally and only the stores of the LAST pass
-        // (WRITE) are predicated.  FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
+        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally; the stores follow the last pass.
+        // FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
         // per-cell "inside" selects vanish; otherwise the identity cells of the top lane pass the flux through.
         const bool st_ok = live && act;
         const size_t off = wgo + colc + (size_t)ncol * lo;
-        auto one_pass = [&](auto write_tag) {
-            constexpr bool WRITE = decltype(write_tag)::value;
+        auto one_pass = [&]() -> double {
             // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
             Aff m{1.0, 0.0};
 #pragma unroll
             for (int k = CH - 1; k >= 0; k--) {
-                cc[0][k] = my[(0 * CH + k) * THREADS] - b[0][k] * Fcu_reg[k];
+                const double2 sd = my2[(k * 6 + 0) * THREADS];
+                cc[0][k] = sd.x - b[0][k] * Fcu_reg[k];
                 m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
-                cc[1][k] = my[(2 * CH + k) * THREADS] - b[1][k] * Fu_reg[k];
+                cc[1][k] = sd.y - b[1][k] * Fu_reg[k];
                 m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
             }
             Aff sc = scan_from_top<LPC>(m, sl, nch);
             const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
             double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
             if (sl >= nch - 1) F = toa;
-            if (WRITE && live && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
 #pragma unroll
             for (int k = CH - 1; k >= 0; k--) {
                 const bool in = FULL || lo + k < hi;
                 double Fn = tiny_to_abs(a[0][k] * F + cc[0][k]);
                 if (!FULL) Fn = in ? Fn : F;
                 Fcd_reg[k] = Fn;
-                if (WRITE) { if (st_ok && in) Fc_down[off + (size_t)(k * ncol)] = Fn; }
                 double Fm = tiny_to_abs(a[1][k] * Fn + cc[1][k]);
                 if (!FULL) Fm = in ? Fm : F;
                 Fd_reg[k] = Fm;
-                if (WRITE) { if (st_ok && in) F_down[off + (size_t)(k * ncol)] = Fm; }
                 F = Fm;
             }
             // the flux at my top interface as WALKED (and stored) by the lane above
@@ -666,16 +714,16 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
             for (int k = 0; k < CH; k++) {
                 // identity cells above the column carry the entering flux (toa) unchanged, so no "inside" test
                 const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                cc[1][k] = my[(3 * CH + k) * THREADS] - b[1][k] * Fcd_reg[k];
+                const double2 su = my2[(k * 6 + 1) * THREADS];
+                cc[1][k] = su.y - b[1][k] * Fcd_reg[k];
                 m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
-                cc[0][k] = my[(1 * CH + k) * THREADS] - b[0][k] * Fd_top;
+                cc[0][k] = su.x - b[0][k] * Fd_top;
                 m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
             }
             sc = scan_from_bottom<LPC>(m, sl);
             const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
             F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
             if (sl == 0) F = fu0;
-            if (WRITE && live && sl == 0) F_up[wgo + colc] = fu0;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const bool in = FULL || lo + k < hi;
@@ -684,18 +732,37 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
                 double Fn = a[1][k] * F + cc[1][k];
                 if (!FULL) Fn = in ? Fn : F;
                 Fcu_reg[k] = Fn;
-                if (WRITE) { if (st_ok && in) Fc_up[off + (size_t)(k * ncol)] = Fn; }
                 double Fm = tiny_to_abs(a[0][k] * Fn + cc[0][k]);
                 if (!FULL) Fm = in ? Fm : F;
-                if (WRITE) { if (st_ok && in) F_up[off + (size_t)((k + 1) * ncol)] = Fm; }
                 F = Fm;
             }
-            // next pass: the flux at my bottom interface as walked by the lane below
+            // the flux at my bottom interface as walked by the lane below (next pass, and what F_up holds there)
             const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
             Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
+            return F;  // the flux leaving my chunk upwards (interface hi)
         };
-        for (int pass = 0; pass + 1 < s.npass; pass++) one_pass(std::false_type{});
-        one_pass(std::true_type{});  // only the last pass writes the flux arrays
+        double F_out = 0.0;
+        for (int pass = 0; pass < s.npass; pass++) F_out = one_pass();
+        // Only the fluxes of the last pass are stored, and every one of them is still in a register: the lane's
+        // downward fluxes at interfaces lo..lo+CH-1 (F_down, Fc_down), its upward fluxes at the same interfaces
+        // (Fu_reg[0] is the value the lane below walked to, bit for bit) and, in the top lane, interface nlay.
+        if (st_ok) {
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                if (FULL || lo + k < hi) {
+                    const size_t e = off + (size_t)(k * ncol);
+                    F_down[e] = Fd_reg[k];
+                    Fc_down[e] = Fcd_reg[k];
+                    F_up[e] = Fu_reg[k];
+                    Fc_up[e] = Fcu_reg[k];
+                }
+            }
+            if (sl == nch - 1) {
+                const size_t e = wgo + colc + (size_t)ncol * nlay;
+                F_down[e] = toa;
+                F_up[e] = F_out;
+            }
+        }
     }
 }
 
@@ -707,7 +774,7 @@ static int launch_lane(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
     s.nchunk = (nlay + CH - 1) / CH;
     if (s.nchunk > LPC) return -1;
     constexpr int THREADS = NCOLS * LPC;
-    const size_t smem = (size_t)4 * CH * THREADS * sizeof(double);
+    const size_t smem = (size_t)CH * 6 * THREADS * sizeof(double2);
     const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
     s.nbatch = ctx->batch.nbatch;
     s.done = ctx->batch.active ? ctx->batch.done : nullptr;
@@ -744,7 +811,7 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
-    auto kern = k_fband_wp<NONISO, CH, LPC, NCOLS>;
+    auto kern = (nlay == nchunk * CH) ? k_fband_wp<NONISO, CH, LPC, NCOLS, true> : k_fband_wp<NONISO, CH, LPC, NCOLS, false>;
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NCOLS * LPC, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
                                                    planck_int, c, albedo, g0_lay, g0_int, s);
@@ -759,7 +826,7 @@ static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
                        const double* g0_int, CpScalars s, int ncol) {
     const int nlay = s.nint - 1;
 #define WP_ARGS ctx, F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay, planck_int, c, albedo, g0_lay, g0_int, s, ncol
-    if (NONISO) {
+    if constexpr (NONISO) {
         // twice the constants per layer: 32 lanes per column keep the per-lane register arrays short
         if (nlay <= 32) return launch_wp<NONISO, 1, 32, 8>(WP_ARGS);
         if (nlay <= 64) return launch_wp<NONISO, 2, 32, 8>(WP_ARGS);
