@@ -553,12 +553,12 @@ def run_ours(args):
                 del r
                 extra["C5_batched_grid"]["rce"] = rce_batch(ctx, 32)
                 # the headline physics (C2: non-isothermal, clouds, beam; planned sweep) as a batch of 32 atmospheres:
-                # the dominant kernel without the single-atmosphere tail effect (963 tiles on 296 CTAs)
+                # the dominant kernel without the single-atmosphere tail effect (1925 tiles on 592 CTAs)
                 r = bench_batch(ctx, 0, 32, 32, max(5, steps // 5), 3, flush, config="C2")
                 extra["C2_batched_grid_32"] = {
                     "workload": r["workload"].replace("C5:", "C2 physics:"), "value": r["points"] / (r["t_solve"] * 1e-3),
                     "unit": UNIT, "ms_per_step": r["t_solve"],
-                    "roofline": _roofline("k_fband_wp (noniso, planned, %d passes fused, 32 atmospheres)" % r["npass"],
+                    "roofline": _roofline("k_fband_lane (noniso, planned, %d passes fused, 32 atmospheres)" % r["npass"],
                                           r["bpc"], r["cells"], r["t_fband"], r["npass"], "C2batch")}
                 del r
             except Exception as e:  # noqa: BLE001 -- the main line must survive a failing extra
@@ -695,8 +695,9 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                              "convergence flags D2H; every 10th iteration additionally rebuilds opacities, transmission "
                              "functions and the direct beam (C:860)"},
                 gpu_launches=int(launches),
-                roofline=_roofline("k_fband_wp (%s%s, all %d passes fused)" %
-                                   ("iso" if q.iso == 1 else "noniso", ", planned" if getattr(q, "_flux_plan_valid", False) else "", npass),
+                roofline=_roofline("%s (%s%s, all %d passes fused)" %
+                                   ("k_fband_lane" if getattr(q, "_flux_plan_valid", False) else "k_fband_wp",
+                                    "iso" if q.iso == 1 else "noniso", ", planned" if getattr(q, "_flux_plan_valid", False) else "", npass),
                                    _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload),
                 rce=rce)
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -242,7 +242,7 @@ k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const 
 //                              F_up(prev), Fc_up(prev)                                               (10)
 // Block: NCOLS columns, LPC lanes per column (NCOLS * LPC threads), CH = ceil(nlay / LPC) layers per lane.
 // ------------------------------------------------------------------------------------------------
-template <bool NONISO, int CH, int LPC, int NCOLS, bool FULL>
+template <bool NONISO, int CH, int LPC, int NCOLS, bool FULL, bool HOIST>
 __global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
 k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
            double* __restrict__ Fc_up, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
@@ -457,6 +457,30 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
             }
             const bool st_ok = live && act;
             const size_t off = wgo + colc + (size_t)ncol * lo;
+            // Pass-invariant half of the scans (HOIST: isothermal kernel, long pass sequences): the A parts of the affine maps are
+            // products of the a's only, so the chunk products, the multiplier each Kogge-Stone step applies to the
+            // incoming B (0 where the step does not apply to this lane -- that replaces the select) and the final
+            // prefix products are formed once per tile; a pass shuffles and multiply-adds the B parts only.
+            double scA_dn = 1.0, scA_up = 1.0;
+            double2* __restrict__ as2 = reinterpret_cast<double2*>(c_emis + NCOLS) + threadIdx.x;
+            if constexpr (HOIST) {
+                double Adn = 1.0, Aup = 1.0;
+#pragma unroll
+                for (int k = CH - 1; k >= 0; k--) Adn = a[0][k] * Adn;
+#pragma unroll
+                for (int k = 0; k < CH; k++) Aup = a[0][k] * Aup;
+#pragma unroll
+                for (int r = 0, d = 1; d < LPC; r++, d <<= 1) {
+                    const double odn = __shfl_down_sync(0xffffffffu, Adn, d, LPC);
+                    const double oup = __shfl_up_sync(0xffffffffu, Aup, d, LPC);
+                    const bool okd = sl + d < nch, oku = sl >= d;
+                    as2[r * (NCOLS * LPC)] = make_double2(okd ? Adn : 0.0, oku ? Aup : 0.0);
+                    if (okd) Adn = Adn * odn;
+                    if (oku) Aup = Aup * oup;
+                }
+                scA_dn = Adn;
+                scA_up = Aup;
+            }
             auto one_pass = [&]() -> double {
                 // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
                 Aff m{1.0, 0.0};
@@ -470,10 +494,19 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                         m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
                     } else {
                         cc[0][k] = (in ? sm[2 * plane + base + k] : 0.0) - b[0][k] * Fu_reg[k];
-                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                        m = Aff{HOIST ? 1.0 : a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
                     }
                 }
-                Aff sc = scan_from_top<LPC>(m, sl, nch);
+                Aff sc;
+                if constexpr (HOIST) {
+                    double mB = m.B;
+#pragma unroll
+                    for (int r = 0, d = 1; d < LPC; r++, d <<= 1)
+                        mB = __fma_rn(as2[r * (NCOLS * LPC)].x, __shfl_down_sync(0xffffffffu, mB, d, LPC), mB);
+                    sc = Aff{scA_dn, mB};
+                } else {
+                    sc = scan_from_top<LPC>(m, sl, nch);
+                }
                 const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
                 double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
                 if (sl >= nch - 1) F = toa;
@@ -514,10 +547,18 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
                         m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
                     } else {
                         cc[0][k] = (in ? sm[3 * plane + base + k] : 0.0) - b[0][k] * Fd_top;
-                        m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                        m = Aff{HOIST ? 1.0 : a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
                     }
                 }
-                sc = scan_from_bottom<LPC>(m, sl);
+                if constexpr (HOIST) {
+                    double mB = m.B;
+#pragma unroll
+                    for (int r = 0, d = 1; d < LPC; r++, d <<= 1)
+                        mB = __fma_rn(as2[r * (NCOLS * LPC)].y, __shfl_up_sync(0xffffffffu, mB, d, LPC), mB);
+                    sc = Aff{scA_up, mB};
+                } else {
+                    sc = scan_from_bottom<LPC>(m, sl);
+                }
                 const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
                 F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
                 if (sl == 0) F = fu0;
@@ -672,12 +713,14 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
             my2[(k * 6 + 1) * THREADS] = su;
         }
         // One pass = downward sweep + upward sweep.  Branch-free: cells outside the column are identity steps
-        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally; the stores follow the last pass.
-        // FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
+        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally and only the stores of the LAST pass
+        // (WRITE) are predicated -- for this kernel measured faster than storing from the registers after the last
+        // pass, which is what k_fband_wp does.  FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
         // per-cell "inside" selects vanish; otherwise the identity cells of the top lane pass the flux through.
         const bool st_ok = live && act;
         const size_t off = wgo + colc + (size_t)ncol * lo;
-        auto one_pass = [&]() -> double {
+        auto one_pass = [&](auto write_tag) {
+            constexpr bool WRITE = decltype(write_tag)::value;
             // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
             Aff m{1.0, 0.0};
 #pragma unroll
@@ -692,15 +735,18 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
             const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
             double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
             if (sl >= nch - 1) F = toa;
+            if (WRITE && live && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
 #pragma unroll
             for (int k = CH - 1; k >= 0; k--) {
                 const bool in = FULL || lo + k < hi;
                 double Fn = tiny_to_abs(a[0][k] * F + cc[0][k]);
                 if (!FULL) Fn = in ? Fn : F;
                 Fcd_reg[k] = Fn;
+                if (WRITE) { if (st_ok && in) Fc_down[off + (size_t)(k * ncol)] = Fn; }
                 double Fm = tiny_to_abs(a[1][k] * Fn + cc[1][k]);
                 if (!FULL) Fm = in ? Fm : F;
                 Fd_reg[k] = Fm;
+                if (WRITE) { if (st_ok && in) F_down[off + (size_t)(k * ncol)] = Fm; }
                 F = Fm;
             }
             // the flux at my top interface as WALKED (and stored) by the lane above
@@ -724,6 +770,7 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
             const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
             F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
             if (sl == 0) F = fu0;
+            if (WRITE && live && sl == 0) F_up[wgo + colc] = fu0;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const bool in = FULL || lo + k < hi;
@@ -732,37 +779,18 @@ k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __r
                 double Fn = a[1][k] * F + cc[1][k];
                 if (!FULL) Fn = in ? Fn : F;
                 Fcu_reg[k] = Fn;
+                if (WRITE) { if (st_ok && in) Fc_up[off + (size_t)(k * ncol)] = Fn; }
                 double Fm = tiny_to_abs(a[0][k] * Fn + cc[0][k]);
                 if (!FULL) Fm = in ? Fm : F;
+                if (WRITE) { if (st_ok && in) F_up[off + (size_t)((k + 1) * ncol)] = Fm; }
                 F = Fm;
             }
-            // the flux at my bottom interface as walked by the lane below (next pass, and what F_up holds there)
+            // next pass: the flux at my bottom interface as walked by the lane below
             const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
             Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
-            return F;  // the flux leaving my chunk upwards (interface hi)
         };
-        double F_out = 0.0;
-        for (int pass = 0; pass < s.npass; pass++) F_out = one_pass();
-        // Only the fluxes of the last pass are stored, and every one of them is still in a register: the lane's
-        // downward fluxes at interfaces lo..lo+CH-1 (F_down, Fc_down), its upward fluxes at the same interfaces
-        // (Fu_reg[0] is the value the lane below walked to, bit for bit) and, in the top lane, interface nlay.
-        if (st_ok) {
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                if (FULL || lo + k < hi) {
-                    const size_t e = off + (size_t)(k * ncol);
-                    F_down[e] = Fd_reg[k];
-                    Fc_down[e] = Fcd_reg[k];
-                    F_up[e] = Fu_reg[k];
-                    Fc_up[e] = Fcu_reg[k];
-                }
-            }
-            if (sl == nch - 1) {
-                const size_t e = wgo + colc + (size_t)ncol * nlay;
-                F_down[e] = toa;
-                F_up[e] = F_out;
-            }
-        }
+        for (int pass = 0; pass + 1 < s.npass; pass++) one_pass(std::false_type{});
+        one_pass(std::true_type{});  // only the last pass writes the flux arrays
     }
 }
 
@@ -801,7 +829,12 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (pitch % 2 == 0) pitch += 1;  // odd column pitch: the phase-A stores of 16 lanes hit distinct banks
     s.nchunk = nchunk;
     s.colpitch = pitch;
-    const size_t smem = ((size_t)(NONISO ? 10 : 5) * NCOLS * pitch + 4 * NCOLS) * sizeof(double);
+    // Hoisting the pass-invariant scan multipliers (HOIST) costs one extra scan per tile and log2(LPC) double2 of
+    // shared memory per thread: measured on B200 it loses 10 % at 1 and 4 passes (C4 single pass, C5) and wins 16 % at
+    // 1001 passes (C4 with scattering), so it is used for long pass sequences of the isothermal kernel only.
+    const bool hoist = !NONISO && s.npass >= 8;
+    const size_t smem = ((size_t)(NONISO ? 10 : 5) * NCOLS * pitch + 4 * NCOLS) * sizeof(double) +
+                        (hoist ? (size_t)(LPC == 32 ? 5 : 4) * NCOLS * LPC * sizeof(double2) : 0);
     if (nchunk > LPC || smem > 227 * 1024) return -1;
     const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
     s.nbatch = ctx->batch.nbatch;
@@ -811,7 +844,9 @@ static int launch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_d
     if (per_sm > max_per_sm) per_sm = max_per_sm;
     if (per_sm < 1) per_sm = 1;
     const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
-    auto kern = (nlay == nchunk * CH) ? k_fband_wp<NONISO, CH, LPC, NCOLS, true> : k_fband_wp<NONISO, CH, LPC, NCOLS, false>;
+    const bool full = nlay == nchunk * CH;
+    auto kern = hoist ? (full ? k_fband_wp<NONISO, CH, LPC, NCOLS, true, !NONISO> : k_fband_wp<NONISO, CH, LPC, NCOLS, false, !NONISO>)
+                      : (full ? k_fband_wp<NONISO, CH, LPC, NCOLS, true, false> : k_fband_wp<NONISO, CH, LPC, NCOLS, false, false>);
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NCOLS * LPC, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, F_dir, Fc_dir, planck_lay,
                                                    planck_int, c, albedo, g0_lay, g0_int, s);

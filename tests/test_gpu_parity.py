@@ -469,3 +469,51 @@ def test_unusual_layer_counts(ctx, config, nlayer):
         stage_vs_oracle(q, comp, oc, "integrate_flux", ["F_down_band", "F_up_band", "F_down_tot", "F_up_tot"], soft=bad)
     stage_vs_oracle(q, comp, oc, "rad_temp_iteration", ["T_lay", "abort"], soft=bad)
     bad.check()
+
+SHAPES = [("C1", 16), ("C1", 30), ("C1", 31), ("C1", 47), ("C1", 48), ("C1", 77), ("C1", 80), ("C1", 100), ("C1", 112),
+          ("C1", 120), ("C1", 128), ("C1", 200), ("C1", 203), ("C1", 256),
+          ("C2", 32), ("C2", 33), ("C2", 64), ("C2", 70), ("C2", 96), ("C2", 98), ("C2", 100), ("C2", 127), ("C2", 128),
+          ("C2", 129), ("C2", 256)]
+
+
+@pytest.mark.parametrize("config,nlayer", SHAPES)
+def test_sweep_tile_shapes(ctx, config, nlayer):
+    """every instantiation of the layer-parallel sweeps (layers per lane 1..8, 16 / 32 lanes per column), with and
+    without a partial top chunk and with every lane of a column in use (128 / 256 layers): two consecutive flux solves
+    against the reference's kernel (1e-10), and for non-isothermal columns of <= 128 layers the planned sweep against
+    the unplanned one from the same state (1e-12).  5 bins x 20 Gauss points = 100 columns: the last tile is partial."""
+    from util import HostMirror, restore
+    q = synthetic.make_store(config, ctx=ctx, nbin=5, nlayer=nlayer, ntemp=12, npress=8, plancktable_dim=700,
+                             plancktable_step=10)
+    q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+    n = int(q.nlayer)
+    q.T_lay = np.concatenate([np.linspace(2300.0, 900.0, n), [2400.0]])
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    iso = int(q.iso) == 1
+    q.iter_value = np.int32(0)
+    for m in ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+              "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass",
+              "calc_total_g_0_of_gas_and_clouds", "calculate_transmission", "calculate_direct_beamflux"]:
+        getattr(comp, m)(q)
+    fl = ["F_down_wg", "F_up_wg"] + ([] if iso else ["Fc_down_wg", "Fc_up_wg"])
+    bad = Failures()
+    ref = ref_gpu.RefCompute(ctx.device) if ref_gpu.available() else None
+    q._flux_plan_valid = False
+    for _ in range(2):
+        if ref is not None:
+            stage_vs_ref(q, comp, ref, "populate_spectral_flux_iteratively", fl, soft=bad)
+        else:
+            comp.populate_spectral_flux_iteratively(q)
+    if not iso and n <= 128:
+        ctx.synchronize()
+        before = HostMirror(q)
+        comp.populate_spectral_flux_iteratively(q)
+        want = {name: getattr(q, "dev_" + name).get() for name in fl}
+        restore(q, before)
+        comp.build_flux_plan(q)
+        assert q._flux_plan_valid
+        comp.populate_spectral_flux_iteratively(q)
+        for name in fl:
+            assert_close(getattr(q, "dev_" + name).get(), want[name], "planned vs unplanned: " + name, rtol=1e-12, soft=bad)
+    bad.check()
