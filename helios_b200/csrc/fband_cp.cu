@@ -17,7 +17,13 @@
 //     entering its chunk, and the lane then walks its own CH layers.  A sweep is 2*CH + 5 short steps
 //     instead of nlayer long ones; all passes run back to back inside the warp with no block barrier, the
 //     fluxes needed from the other direction / the previous pass stay in registers (chunk-edge values are
-//     handed over by shuffle), and only the last pass writes the flux arrays.
+//     handed over by shuffle).  The passes are branch-free (cells outside the column are identity steps) and
+//     store nothing; the fluxes of the last pass are stored from the registers afterwards.
+//
+//   Non-isothermal layers between two opacity refreshes take the PLANNED form further down (k_plan_build +
+//   k_fband_lane): the Planck-independent part of the step constants is formed once per refresh and stored in
+//   the order the sweep lanes consume it, so the sweep has no phase A at all -- one warp per column, loads by
+//   cp.async into thread-private shared-memory rows, then the same passes.
 //
 // Arithmetic: a F - b F_opp + s is the reference's 1/M (P F - N F_opp + ...) with the division by M
 // distributed, and the chunk-entry flux comes from composed maps: both reorder a few multiply-adds.
