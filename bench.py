@@ -63,12 +63,13 @@ def _traffic_from_profile(workload, nbatch=None):
     import glob
     import re
     best = None
+    # newest round last (r2_... sorts after r1_...): the latest committed capture of this workload wins
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_fband*%s*.csv" % workload.lower()))):
         rows = list(csv.reader(open(path)))
         h, units = rows[0], rows[1]
         vals = []
         for r in rows[2:]:
-            if "fband" not in r[0]:
+            if "fband" not in r[0] and "k_sweep" not in r[0]:
                 continue
             tot = 0.0
             for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
@@ -171,14 +172,45 @@ def refresh(comp, q):
     comp.build_flux_plan(q)  # non-isothermal layers: the sweep plan belongs to the refresh (Compute._refresh_atmosphere)
 
 
+def _no_beam(q):
+    """the direct-beam arrays are known to be all zero (fdir_* ran with dir_beam == 0): the sweeps skip them"""
+    return int(q.dir_beam) == 0
+
+
 def _bytes_per_cell(q):
-    """algorithmic bytes of ONE fused flux solve per layer*lambda*g cell (DESIGN.md 'roofline').  The planned
-    non-isothermal sweep moves the same amount: 16 plan values + 2 previous fluxes in, 4 fluxes out = 22 doubles,
-    where the unplanned one reads 14 coefficients + 2 beam + 2 previous fluxes and writes 4 (+ band terms / ny)"""
+    """bytes ONE fused flux solve has to move per layer*lambda*g cell with the kernel that actually runs (DESIGN.md
+    'roofline'): what is loaded once and stored once, nothing that is skipped.
+      planned isothermal sweep      3 plan constants (5 with a beam) + previous F_up in, F_down + F_up out, Planck / ny
+      planned non-isothermal sweep  8 plan constants (12 with a beam) + previous F_up, Fc_up in, 4 fluxes out,
+                                    layer + interface Planck / ny
+      unplanned sweeps              the reference's coefficient arrays, minus F_dir and G+- when the beam is
+                                    known to be zero"""
+    ny = float(q.ny)
+    planned = bool(getattr(q, "_flux_plan_valid", False))
+    nobeam = _no_beam(q)
+    if q.iso == 1:
+        if planned:
+            return (3 if nobeam else 5) * 8 + 8 + 16 + 8 / ny
+        return (4 if nobeam else 6) * 8 + (0 if nobeam else 8) + 8 + 16 + (8 + (8 if q.clouds == 1 else 0)) / ny
+    if planned:
+        return (8 if nobeam else 12) * 8 + 16 + 32 + 16 / ny
+    return (10 if nobeam else 14) * 8 + (0 if nobeam else 16) + 16 + 32 + (2 * 8 + 2 * 8 + (2 * 8 if q.clouds == 1 else 0)) / ny
+
+
+def _survey_bytes_per_cell(q):
+    """SURVEY.md 8(d)'s per-unit figure for the reference's algorithm (all coefficient arrays of fband_* read once):
+    80.4 B isothermal, 176 B (+ band terms) non-isothermal.  Reported beside `frac` for continuity with round 1."""
     ny = float(q.ny)
     if q.iso == 1:
         return 6 * 8 + 8 + 8 + 16 + (8 + (8 if q.clouds == 1 else 0)) / ny
     return 14 * 8 + 16 + 16 + 32 + (2 * 8 + 2 * 8 + (2 * 8 if q.clouds == 1 else 0)) / ny
+
+
+def _sweep_kernel_name(q):
+    planned = bool(getattr(q, "_flux_plan_valid", False))
+    if q.iso == 1:
+        return "k_sweep_iso (planned, TMA-staged)" if planned else "k_fband_wp (iso)"
+    return "k_sweep_noniso (planned, TMA-staged)" if planned else "k_fband_wp (noniso)"
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -273,7 +305,7 @@ def bench_batch(ctx, rank, world, nbatch, steps, warmup, flush, config="C1"):
     qb.leave()
     bpc = _bytes_per_cell(qb)
     return dict(qb=qb, comp=comp, npass=npass, cells=cells, points=cells * npass, t_solve=t_solve, t_fband=t_fband,
-                t_e2e=t_e2e, bpc=bpc, h2d=T_host.nbytes, d2h=res_host.nbytes + sums_host.nbytes,
+                t_e2e=t_e2e, bpc=bpc, sbpc=_survey_bytes_per_cell(qb), kernel=_sweep_kernel_name(qb), h2d=T_host.nbytes, d2h=res_host.nbytes + sums_host.nbytes,
                 workload="C5: %d independent atmospheres per GPU (T_star x log g x opacity scaling grid), each %d layers x "
                          "%d bins x %d gauss points, %s layers, %d fused flux passes; one launch per kernel for the "
                          "whole batch, %d opacity tables shared" % (nbatch, qb.nlayer, qb.nbin, qb.ny,
@@ -324,7 +356,7 @@ def bench_c4(ctx, rank, world, steps, warmup, flush, nbin=100000, scat=1, dim=80
 
     t_solve, t_fband = _timed(ctx, step, steps, warmup, flush)
     return dict(q=q, comp=comp, npass=npass, cells=cells, points=cells * npass, t_solve=t_solve, t_fband=t_fband,
-                bpc=_bytes_per_cell(q),
+                bpc=_bytes_per_cell(q), sbpc=_survey_bytes_per_cell(q), kernel=_sweep_kernel_name(q),
                 workload="C4: post-processing spectrum, %d layers x %d bins x 1 point (this rank: %d bins), %d fused "
                          "flux passes (scat=%d), wavelength-sharded over %d GPU(s)" %
                          (q.nlayer, nbin, q.nbin, npass, scat, world))
@@ -460,16 +492,25 @@ def rce_batch(ctx, nbatch=32):
                     "to the reference's convergence criterion, converged ones frozen by the on-device latch" % nbatch}
 
 
-def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload, nbatch=None):
+def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload, nbatch=None, survey_bpc=None):
     peak, peak_src = _peaks()
     traffic = _traffic_from_profile(workload, nbatch)
     t_k = t_kernel_ms * 1e-3
     achieved = bpc * cells / t_k / 1e9
-    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": (traffic or {}).get("bytes_per_launch"),
-            "traffic_source": (traffic or {}).get("source"), "algorithmic_bytes_per_launch": bpc * cells,
-            "peak_source": peak_src, "bytes_per_cell_per_solve": bpc, "kernel_ms": t_kernel_ms,
-            "per_pass_equiv_GBs": achieved * npass}
+    out = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+           "frac": achieved / peak, "traffic": (traffic or {}).get("bytes_per_launch"),
+           "traffic_source": (traffic or {}).get("source"), "algorithmic_bytes_per_launch": bpc * cells,
+           "peak_source": peak_src, "bytes_per_cell_per_solve": bpc, "kernel_ms": t_kernel_ms,
+           "bytes_basis": "what the running kernel must load and store once per flux solve (skipped arrays not counted)"}
+    if out["traffic"]:
+        out["traffic_over_algorithmic"] = out["traffic"] / (bpc * cells)
+    if survey_bpc is not None:
+        out["frac_at_survey_bytes"] = survey_bpc * cells / t_k / 1e9 / peak
+        out["survey_bytes_per_cell"] = survey_bpc
+    if npass >= 8:
+        # long pass sequences run from registers: the launch is bound by the dependent fp64 chain, not by HBM
+        out["note"] = "compute-bound launch (%d fused passes in registers): the HBM fraction is not the binding roofline" % npass
+    return out
 
 
 def run_ours(args):
@@ -518,8 +559,8 @@ def run_ours(args):
                          "what": "one full batched RT iteration via BatchCompute.* (T profiles from pinned host, rebuild, "
                                  "flux solve, temperature step, profiles + convergence sums to host)"},
                     gpu_launches=None,
-                    roofline=_roofline("k_fband_wp (iso, all %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
-                                       r["bpc"], r["cells"], t_fband, r["npass"], "C5", args.batch))
+                    roofline=_roofline("%s, all %d passes fused, %d atmospheres" % (r["kernel"], r["npass"], args.batch),
+                                       r["bpc"], r["cells"], t_fband, r["npass"], "C5", args.batch, r["sbpc"]))
     elif args.workload == "C4":
         barrier()
         r = bench_c4(ctx, rank, world, steps, warmup, flush, scat=args.c4_scat)
@@ -532,8 +573,8 @@ def run_ours(args):
                             "sharding": "contiguous wavelength ranges per rank; one fused NVLink peer-memory all-reduce of "
                                         "the per-interface flux totals per step"},
                     e2e=None, gpu_launches=None,
-                    roofline=_roofline("k_fband_wp (iso, %d passes fused)" % r["npass"], r["bpc"], r["cells"], t_fband,
-                                       r["npass"], "C4"))
+                    roofline=_roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), r["bpc"], r["cells"], t_fband,
+                                       r["npass"], "C4", None, r["sbpc"]))
         del pts
     else:
         line = _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max)
@@ -547,8 +588,8 @@ def run_ours(args):
                     "ms_per_step": r["t_solve"],
                     "e2e": {"value": r["points"] / (r["t_e2e"] * 1e-3), "unit": UNIT, "ms_per_step": r["t_e2e"],
                             "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-                    "roofline": _roofline("k_fband_wp (iso, %d passes fused, %d atmospheres)" % (r["npass"], args.batch),
-                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5", args.batch),
+                    "roofline": _roofline("%s, %d passes fused, %d atmospheres" % (r["kernel"], r["npass"], args.batch),
+                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C5", args.batch, r["sbpc"]),
                     "setup_s": time.perf_counter() - t0}
                 del r
                 extra["C5_batched_grid"]["rce"] = rce_batch(ctx, 32)
@@ -558,8 +599,8 @@ def run_ours(args):
                 extra["C2_batched_grid_32"] = {
                     "workload": r["workload"].replace("C5:", "C2 physics:"), "value": r["points"] / (r["t_solve"] * 1e-3),
                     "unit": UNIT, "ms_per_step": r["t_solve"],
-                    "roofline": _roofline("k_fband_lane (noniso, planned, %d passes fused, 32 atmospheres)" % r["npass"],
-                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C2batch")}
+                    "roofline": _roofline("%s, %d passes fused, 32 atmospheres" % (r["kernel"], r["npass"]),
+                                          r["bpc"], r["cells"], r["t_fband"], r["npass"], "C2batch", 32, r["sbpc"])}
                 del r
             except Exception as e:  # noqa: BLE001 -- the main line must survive a failing extra
                 extra["C5_batched_grid"] = {"error": repr(e)}
@@ -570,8 +611,8 @@ def run_ours(args):
                     r = bench_c4(ctx, 0, 1, max(3, steps // 10), 3, flush, scat=scat, reuse=r)
                     extra[key] = {"workload": r["workload"], "value": r["points"] / (r["t_solve"] * 1e-3), "unit": UNIT,
                                   "ms_per_step": r["t_solve"],
-                                  "roofline": _roofline("k_fband_wp (iso, %d passes fused)" % r["npass"], r["bpc"], r["cells"],
-                                                        r["t_fband"], r["npass"], "C4")}
+                                  "roofline": _roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), r["bpc"], r["cells"],
+                                                        r["t_fband"], r["npass"], "C4", None, r["sbpc"])}
                 except Exception as e:  # noqa: BLE001
                     extra[key] = {"error": repr(e)}
             try:
@@ -695,10 +736,9 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                              "convergence flags D2H; every 10th iteration additionally rebuilds opacities, transmission "
                              "functions and the direct beam (C:860)"},
                 gpu_launches=int(launches),
-                roofline=_roofline("%s (%s%s, all %d passes fused)" %
-                                   ("k_fband_lane" if getattr(q, "_flux_plan_valid", False) else "k_fband_wp",
-                                    "iso" if q.iso == 1 else "noniso", ", planned" if getattr(q, "_flux_plan_valid", False) else "", npass),
-                                   _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload),
+                roofline=_roofline("%s, all %d passes fused" % (_sweep_kernel_name(q), npass),
+                                   _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload, None,
+                                   _survey_bytes_per_cell(q)),
                 rce=rce)
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(q, args.workload)

@@ -241,6 +241,14 @@ class BatchCompute(Compute):
         q = quant
         if int(q.foreplay) != 0 or q.physical_tstep != 0 or q.singlewalk == 1:
             raise ValueError("the batched loop covers the default iterative run (foreplay = 0, no physical timestep)")
+        # The host looks at the state once per block of 10 iterations, so the criterion relaxation of C:974 (applied
+        # when iter_value == n exactly) can only be reproduced for relaxation numbers on a block boundary; the default
+        # param.dat uses 1e4 and 2e4.  Anything else would switch up to 9 iterations late -> refuse instead of drifting.
+        # Not reproduced here (documented deviation): the reference's escape to the convection loop when the surface
+        # temperature leaves the Planck table (C:946-952) -- the temperature step clamps to the table instead.
+        bad = [n for n in (q.crit_relaxation_numbers or []) if int(n) % 10 != 0]
+        if bad:
+            raise ValueError("the batched loop needs crit_relaxation_numbers that are multiples of 10, got %r" % bad)
         q.enter()
         q.iter_value = np.int32(0)  # the kernels read the device counter; the argument is ignored
         lib = backend.lib()

@@ -24,11 +24,13 @@ class Compute(object):
         self.hsfunc = hsfunc if hsfunc is not None else _host
         self.verbose = verbose
         self._species_cache = {}
+        self._h2o_scat_lay = self._h2o_scat_int = None  # H2O Rayleigh scratch (never a resident species table)
         self._abort_sum = None
         self.fuse_passes = True
         # non-isothermal layers: form the Planck-independent part of the sweep constants once per opacity refresh
         # (helios_fband_noniso_plan_build) and run the planned sweep in the iterations in between
         self.use_flux_plan = True
+        self.use_iso_plan = True  # the same for isothermal layers (helios_fband_iso_plan_build)
         self.stats = {"iterations": 0}
         backend.lib()  # fail loudly right here if the CUDA library is missing
 
@@ -177,9 +179,25 @@ class Compute(object):
         """B200-side addition: the sweep plan of the non-isothermal flux solve (include/helios_b200.h).  Valid until
         the next calculate_transmission / calculate_direct_beamflux."""
         q = quant
-        if q.iso != 0 or not self.use_flux_plan or int(q.nlayer) > 128:
+        if not self.use_flux_plan or int(q.nlayer) > (256 if q.iso == 1 else 128):
             return
         import ctypes
+        if q.iso == 1:
+            # isothermal layers: [a, b, Planck factor (, beam sources)] per cell
+            nd = ctypes.c_size_t()
+            backend._check(backend.lib().helios_fband_iso_plan_size(self.ctx.handle, int(q.ninterface), int(q.nbin),
+                                                                    int(q.ny), ctypes.byref(nd)), "fband_iso_plan_size")
+            n = int(nd.value)
+            if n == 0 or not self.use_iso_plan:
+                return
+            if getattr(q, "dev_fband_plan", None) is None or q.dev_fband_plan.size != n:
+                q.dev_fband_plan = self.ctx.zeros(n)
+            self.ctx.call("fband_iso_plan_build", q.dev_fband_plan, q.dev_F_dir_wg, q.dev_w_0, q.dev_M_term,
+                          q.dev_N_term, q.dev_P_term, q.dev_G_plus, q.dev_G_minus, q.dev_surf_albedo, q.dev_g_0_tot_lay,
+                          q.g_0, q.ninterface, q.nbin, q.mu_star, q.ny, q.epsi, q.dir_beam, q.clouds, q.scat_corr,
+                          q.i2s_transition)
+            q._flux_plan_valid = True
+            return
         nd = ctypes.c_size_t()
         backend._check(backend.lib().helios_fband_noniso_plan_size(self.ctx.handle, int(q.ninterface), int(q.nbin),
                                                                    int(q.ny), ctypes.byref(nd)), "fband_noniso_plan_size")
@@ -208,7 +226,11 @@ class Compute(object):
         npass = self.n_scat_passes(q)
         chunks = [npass] if self.fuse_passes else [1] * npass
         for n in chunks:
-            if q.iso == 1:
+            if q.iso == 1 and self.use_flux_plan and self.use_iso_plan and getattr(q, "_flux_plan_valid", False):
+                self.ctx.call("fband_iso_planned", q.dev_F_down_wg, q.dev_F_up_wg, q.dev_fband_plan,
+                              q.dev_planckband_lay, q.dev_surf_albedo, q.R_star, q.a, q.ninterface, q.nbin, q.f_factor,
+                              q.ny, q.dir_beam, n)
+            elif q.iso == 1:
                 self.ctx.call("fband_iso", q.dev_F_down_wg, q.dev_F_up_wg, q.dev_F_dir_wg, q.dev_planckband_lay,
                               q.dev_w_0, q.dev_M_term, q.dev_N_term, q.dev_P_term, q.dev_G_plus, q.dev_G_minus,
                               q.dev_surf_albedo, q.dev_g_0_tot_lay, q.g_0, q.singlewalk, q.R_star, q.a, q.ninterface,
@@ -354,7 +376,8 @@ class Compute(object):
                 break
 
             converged = 0
-            quant.marked_red = np.zeros(full)
+            if it < quant.foreplay:
+                quant.marked_red = np.zeros(full)  # C:929: recomputed every iteration; nothing is marked before the foreplay ends
             if it % 100 == 0:
                 self._say("\nWe are running \"" + str(quant.name) + "\" at iteration step nr. : " + str(it))
                 if it > 99:
@@ -368,8 +391,10 @@ class Compute(object):
                     self.interpolate_kappa_and_cp(quant)
                 self.rad_temp_iteration(quant)
                 converged = self._layers_converged(quant)
-                if it % 100 == 0 or converged == full:
-                    # the flag array itself is only needed for reporting / the hand-over to convection
+                plot_next = quant.realtime_plot == 1 and (it + 1) % quant.n_plot == 0
+                if it % 100 == 0 or converged == full or plot_next:
+                    # the flag array itself is only needed for reporting / plotting (realtime_plotting.py:66) / the
+                    # hand-over to convection; in between the last fetched marking is kept
                     quant.abort = quant.dev_abort.get()
                     quant.marked_red = (quant.abort == 0).astype(np.float64)
                 if it % 100 == 0:
@@ -627,11 +652,16 @@ class Compute(object):
                 self.add_to_mixed_opacity(q, sp.weight, s)
             if sp.scattering == "yes":
                 if sp.name == "H2O":
-                    if getattr(q, "dev_scat_cross_spec_lay", None) is None or q.dev_scat_cross_spec_lay.size != q.nbin * q.nlayer:
-                        q.dev_scat_cross_spec_lay = self.ctx.zeros(int(q.nbin) * int(q.nlayer))
-                    if q.iso == 0 and (getattr(q, "dev_scat_cross_spec_int", None) is None
-                                       or q.dev_scat_cross_spec_int.size != q.nbin * q.ninterface):
-                        q.dev_scat_cross_spec_int = self.ctx.zeros(int(q.nbin) * int(q.ninterface))
+                    # private scratch: calc_h2o_scat writes every element, so it must never land in another
+                    # species' resident cross-section table (the reference allocates fresh zeros, C:1483-1486)
+                    n_lay, n_int = int(q.nbin) * int(q.nlayer), int(q.nbin) * int(q.ninterface)
+                    if self._h2o_scat_lay is None or self._h2o_scat_lay.size != n_lay:
+                        self._h2o_scat_lay = self.ctx.zeros(n_lay)
+                    q.dev_scat_cross_spec_lay = self._h2o_scat_lay
+                    if q.iso == 0:
+                        if self._h2o_scat_int is None or self._h2o_scat_int.size != n_int:
+                            self._h2o_scat_int = self.ctx.zeros(n_int)
+                        q.dev_scat_cross_spec_int = self._h2o_scat_int
                     self.calculate_H2O_Rayleigh_scattering(q, s)
                 else:
                     q.dev_scat_cross_spec_lay = self._resident(("sl", s), sp.scat_cross_sect_layer)

@@ -45,6 +45,13 @@ struct BatchDesc {
     __host__ __device__ size_t planck_lay() const { return (size_t)(nlayer + 2) * nbin; }
 };
 
+struct helios_plan_info {
+    const void* ptr = nullptr;
+    size_t bytes = 0;
+    int kind = 0;  // 1 = isothermal, 2 = non-isothermal
+    int nobeam = 0, nint = 0, ncol = 0, nbatch = 0;
+};
+
 struct helios_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -68,6 +75,9 @@ struct helios_ctx {
     // them and the G+/- coefficient arrays that only multiply them.  [0] = F_dir_wg, [1] = Fc_dir_wg.
     const void* zero_beam[2] = {nullptr, nullptr};
     size_t zero_beam_bytes = 0;
+    // sweep plans built by this context (fband_plan.cu): the layout of a plan depends on how it was built (beam rows
+    // present or not), so the planned sweeps only accept plans recorded here and not overwritten since
+    helios_plan_info plans[4];
     unsigned* integ_ticket = nullptr;  // integrate_flux: blocks finished per (atmosphere, interface)
     size_t integ_ticket_n = 0;
     void* flush_buf = nullptr;  // helios_l2_flush
@@ -143,6 +153,37 @@ static inline void helios_note_write(helios_ctx* ctx, const void* p, size_t nbyt
         const char* z = static_cast<const char*>(ctx->zero_beam[k]);
         if (z != nullptr && lo < z + ctx->zero_beam_bytes && z < lo + nbytes) ctx->zero_beam[k] = nullptr;
     }
+    for (auto& pi : ctx->plans) {
+        const char* z = static_cast<const char*>(pi.ptr);
+        if (z != nullptr && lo < z + pi.bytes && z < lo + nbytes) pi.ptr = nullptr;
+    }
+}
+
+static inline void helios_plan_record(helios_ctx* ctx, const void* ptr, size_t bytes, int kind, int nobeam, int nint,
+                                      int ncol) {
+    helios_plan_info* slot = nullptr;
+    for (auto& pi : ctx->plans)
+        if (pi.ptr == ptr) slot = &pi;
+    if (slot == nullptr)
+        for (auto& pi : ctx->plans)
+            if (pi.ptr == nullptr) slot = &pi;
+    if (slot == nullptr) slot = &ctx->plans[0];
+    slot->ptr = ptr;
+    slot->bytes = bytes;
+    slot->kind = kind;
+    slot->nobeam = nobeam;
+    slot->nint = nint;
+    slot->ncol = ncol;
+    slot->nbatch = ctx->batch.nbatch;
+}
+
+static inline const helios_plan_info* helios_plan_lookup(const helios_ctx* ctx, const void* ptr, int kind, int nint,
+                                                         int ncol) {
+    for (const auto& pi : ctx->plans)
+        if (pi.ptr == ptr && ptr != nullptr && pi.kind == kind && pi.nint == nint && pi.ncol == ncol &&
+            pi.nbatch == ctx->batch.nbatch)
+            return &pi;
+    return nullptr;
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

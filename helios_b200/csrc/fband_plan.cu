@@ -1,0 +1,1053 @@
+// Planned two-stream sweeps (round 2): one warp owns a column (or a pair of columns), everything it needs for its NEXT
+// tile is staged into warp-private shared memory while it sweeps the current one, and the passes run from registers.
+//
+// Why a plan.  Between two opacity refreshes (10 RT iterations, C:860) only the Planck terms change.  The sweep of
+// K:1366-1799 is, per (half-)layer, the affine step
+//      F_out = a F_in - b F_opp + s,        a = P/M,  b = N/M,
+//      isothermal     (K:1443-1451):  s_down = k0d + k1 B_layer,            s_up = k0u + k1 B_layer
+//      non-isothermal (K:1640-1795):  s_down = k0d + k1 B_layer + k2 B_int, s_up = k0u + k2 B_layer + k1 B_int
+// with k0 = beam source / M and k1, k2 = products of 1/M, the source factor 2 pi eps (1-w0)/(E-w0) and the Planck
+// weights of the half-layer.  (The up-going weights ARE the down-going ones swapped, bit for bit: (M-P)-N == -(N+(P-M)),
+// so the six constants [a, b, k0d, k0u, k1, k2] carry what round 1 stored as eight.)  The plan-build kernels evaluate
+// them once per refresh with the rounding-exact building blocks of sweep_math.cuh; with the beam known to be zero the two
+// k0 rows are not stored at all.
+//
+// Plan layout = the shared-memory image of a warp's tile.  A warp tile is CPW = 32/LPC columns; lane = (column, chunk of
+// CH layers).  Its block is NR*CH rows of RL = CPW*RS doubles (RS = active lanes per column, rounded to even; a lane's
+// element sits at column*RS + chunk), row (k*NR + j) = constant j of the lane's k-th layer, followed by 4 doubles of
+// per-column surface constants.  The block is contiguous in HBM, so ONE cp.async.bulk (TMA, SASS UBLKCP) per tile brings
+// it in, completion on a warp-private mbarrier; the previous upward fluxes and the Planck values of the tile come by
+// 8-byte cp.async (LDGSTS) into rows of the same shape.  The copies for tile n+1 are issued as soon as tile n has been
+// lifted into registers, so the memory round trip overlaps the ~thousands of cycles of dependent sweep arithmetic:
+// no block barrier anywhere, warps of a CTA drift freely.
+//
+// The passes (phase B of k_fband_wp, operation for operation): every lane composes the affine map of its chunk, a
+// Kogge-Stone shuffle scan over the lanes of the column hands it the flux entering the chunk, the lane walks its layers.
+// Cells outside the column are identity steps BY DATA (a = 1, b = 0, s = 0: 1*F + 0 == F exactly), so there is no
+// "inside" select.  The reference's tiny-value clean-up (fabs(f) < 1e-100 ? fabs(f) : f, K:1453) costs 18 of the 26 cycles
+// of a dependent walk step, yet it changes a value only when the sign bit is set and |f| < 1e-100: the walk runs
+// WITHOUT it, tests the high word of every result with integer instructions off the critical path, and only if any lane
+// saw such a value (warp vote) redoes the walk with the exact clean-up -- bit-identical results, 8-cycle steps.
+#include "common.cuh"
+#include "sweep_math.cuh"
+#include "fband_plan.cuh"
+#include <cstdlib>
+
+namespace {
+
+struct PlanScalars {
+    double Rstar, a, f_factor;
+    int nint, nbin, ny, dir_beam, npass, nch, rs, nbatch;
+    const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
+};
+
+// ---------------------------------------------------------------- async-copy plumbing (PTX) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// would tiny_to_abs change f?  (sign bit set and |f| < 1e-100, or f == -0.0.)  Conservative on the low word: the exact
+// test decides in the slow path.  1e-100 = 0x2B2BFF2EE48E0530.
+__device__ __forceinline__ bool cleanup_candidate(double f) {
+    return ((unsigned)__double2hiint(f) ^ 0x80000000u) <= 0x2B2BFF2Eu;
+}
+
+// affine maps x -> A x + B; Kogge-Stone scans inside segments of LPC lanes (one segment = one column)
+struct Aff {
+    double A, B;
+};
+template <int LPC>
+__device__ __forceinline__ Aff scan_from_top(Aff m, int sl, int n) {  // lane j: maps of lanes j..n-1, highest first
+#pragma unroll
+    for (int d = 1; d < LPC; d <<= 1) {
+        const double oA = __shfl_down_sync(0xffffffffu, m.A, d, LPC);
+        const double oB = __shfl_down_sync(0xffffffffu, m.B, d, LPC);
+        if (sl + d < n) {
+            m.B = m.A * oB + m.B;
+            m.A = m.A * oA;
+        }
+    }
+    return m;
+}
+template <int LPC>
+__device__ __forceinline__ Aff scan_from_bottom(Aff m, int sl) {  // lane j: maps of lanes j..0, lane 0 first
+#pragma unroll
+    for (int d = 1; d < LPC; d <<= 1) {
+        const double oA = __shfl_up_sync(0xffffffffu, m.A, d, LPC);
+        const double oB = __shfl_up_sync(0xffffffffu, m.B, d, LPC);
+        if (sl >= d) {
+            m.B = m.A * oB + m.B;
+            m.A = m.A * oA;
+        }
+    }
+    return m;
+}
+
+template <int LPC>
+struct Log2;
+template <>
+struct Log2<16> {
+    static constexpr int v = 4;
+};
+template <>
+struct Log2<32> {
+    static constexpr int v = 5;
+};
+
+// Warp-private staging area (doubles): [mbarrier 2][plan block PB][previous fluxes NF*CH*RL][Planck NB*RL][column consts 8]
+template <int CH, int NR, int NF, int NB>
+struct TileShape {
+    __host__ __device__ static int rl(int rs, int cpw) { return rs * cpw; }
+    __host__ __device__ static int plan_doubles(int rs, int cpw) { return CH * NR * rs * cpw + 4; }
+    __host__ __device__ static int stage_doubles(int rs, int cpw) {
+        return 2 + plan_doubles(rs, cpw) + NF * CH * rs * cpw + NB * rs * cpw + 8;
+    }
+};
+
+// =================================================================================================
+// Isothermal layers: NR = 3 rows per layer [a, b, k1] (+ [k0d, k0u] with a beam), one previous flux, CH Planck values.
+// =================================================================================================
+template <int CH, int LPC, bool NOBEAM, bool HOIST, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double* __restrict__ planck_lay,
+            const double* __restrict__ plan, const double* __restrict__ albedo, PlanScalars s) {
+    constexpr int NR = NOBEAM ? 3 : 5;
+    constexpr int CPW = 32 / LPC;
+    constexpr int NST = Log2<LPC>::v;
+    using TS = TileShape<CH, NR, 1, CH>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rs = s.rs, rl = rs * CPW;
+    const int ncol = s.nbin * s.ny;
+    const int ntw = (ncol + CPW - 1) / CPW;
+    const long long total = (long long)ntw * s.nbatch;
+    const int PB = TS::plan_doubles(rs, CPW);
+    double* stage = smem + (size_t)warp * TS::stage_doubles(rs, CPW);
+    double* pbuf = stage + 2;
+    double* fbuf = pbuf + PB;
+    double* bbuf = fbuf + CH * rl;
+    double* cbuf = bbuf + CH * rl;
+    const unsigned bar = smem_u32(stage), pbuf_s = smem_u32(pbuf), fbuf_s = smem_u32(fbuf), bbuf_s = smem_u32(bbuf),
+                   cbuf_s = smem_u32(cbuf);
+    const int cw = lane / LPC, sl = lane % LPC;
+    const bool act = sl < nch;
+    const int lo = sl * CH;
+    const int me = cw * rs + sl;  // my element of a staged row
+    // rows never written by the copies (layers beyond the column) must read as zeros
+    for (int k = lane; k < 2 * CH * rl + 8; k += 32) fbuf[k] = 0.0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncwarp();
+
+    auto issue = [&](long long wt) {
+        const int atm = (int)(wt / ntw);
+        const int tile = (int)(wt - (long long)atm * ntw);
+        const int colc = min(tile * CPW + cw, ncol - 1);
+        const int x = colc / s.ny;
+        if (lane == 0) {
+            fence_proxy_async();  // the generic-proxy reads of the previous tile are ordered before the bulk write
+            mbar_expect_tx(bar, (unsigned)PB * 8u);
+            bulk_g2s(pbuf_s, plan + (size_t)wt * PB, (unsigned)PB * 8u, bar);
+        }
+        const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
+        const double* __restrict__ Fu = F_up + (size_t)atm * ncol * nint + colc;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const int i = lo + k;
+                if (i < nlay) {
+                    cp_async8(fbuf_s + (unsigned)(k * rl + me) * 8u, Fu + (size_t)ncol * i);
+                    cp_async8(bbuf_s + (unsigned)(k * rl + me) * 8u, BL + i);
+                }
+            }
+        }
+        if (sl < 3) cp_async8(cbuf_s + (unsigned)(cw * 4 + sl) * 8u, sl == 0 ? BL + nlay : (sl == 1 ? BL + nlay + 1 : albedo + x));
+        cp_async_commit();
+    };
+
+    const long long first = (long long)blockIdx.x * WARPS + warp, stride = (long long)gridDim.x * WARPS;
+    if (first < total) issue(first);
+    unsigned phase = 0;
+    const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
+    for (long long wt = first; wt < total; wt += stride) {
+        const int atm = (int)(wt / ntw);
+        const int tile = (int)(wt - (long long)atm * ntw);
+        const int col = tile * CPW + cw;
+        const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
+        const int colc = live ? col : ncol - 1;
+        // ---- lift the staged tile into registers
+        cp_async_wait_all();
+        __syncwarp();
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        double a[CH], b[CH], sd[CH], su[NOBEAM ? 1 : CH], Fu_reg[CH], Fd_reg[CH], cc[CH];
+        const int mec = act ? me : cw * rs;  // idle lanes mirror chunk 0 of their column; nothing of theirs is consumed
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const double B = bbuf[k * rl + mec];
+            a[k] = pbuf[(k * NR + 0) * rl + mec];
+            b[k] = pbuf[(k * NR + 1) * rl + mec];
+            const double k1 = pbuf[(k * NR + 2) * rl + mec];
+            Fu_reg[k] = fbuf[k * rl + mec];
+            Fd_reg[k] = 0.0;
+            if (NOBEAM) {
+                sd[k] = __dmul_rn(k1, B);
+            } else {
+                sd[k] = __fma_rn(k1, B, pbuf[(k * NR + 3) * rl + mec]);
+                su[k] = __fma_rn(k1, B, pbuf[(k * NR + 4) * rl + mec]);
+            }
+        }
+        const double emis = __dmul_rn(pbuf[CH * NR * rl + cw * 2], cbuf[cw * 4 + 1]);
+        const double Fdir0 = pbuf[CH * NR * rl + cw * 2 + 1];
+        const double toa = toa_scale * cbuf[cw * 4 + 0];
+        const double A_s = cbuf[cw * 4 + 2];
+        __syncwarp();  // every lane has read the staging area: the next tile's copies may overwrite it
+        if (wt + stride < total) issue(wt + stride);
+        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per warp
+
+        // Pass-invariant half of the scans (HOIST, long pass sequences): the A parts of the affine maps are products of
+        // the a's only; the multiplier each Kogge-Stone step applies to the incoming B (0 where the step does not apply
+        // to this lane) and the final prefix products are formed once per tile.
+        double mdn[HOIST ? NST : 1], mup[HOIST ? NST : 1], scA_dn = 1.0, scA_up = 1.0;
+        if constexpr (HOIST) {
+            double Adn = 1.0, Aup = 1.0;
+#pragma unroll
+            for (int k = CH - 1; k >= 0; k--) Adn = a[k] * Adn;
+#pragma unroll
+            for (int k = 0; k < CH; k++) Aup = a[k] * Aup;
+#pragma unroll
+            for (int r = 0, d = 1; d < LPC; r++, d <<= 1) {
+                const double odn = __shfl_down_sync(0xffffffffu, Adn, d, LPC);
+                const double oup = __shfl_up_sync(0xffffffffu, Aup, d, LPC);
+                const bool okd = sl + d < nch, oku = sl >= d;
+                mdn[r] = okd ? Adn : 0.0;
+                mup[r] = oku ? Aup : 0.0;
+                if (okd) Adn = Adn * odn;
+                if (oku) Aup = Aup * oup;
+            }
+            scA_dn = Adn;
+            scA_up = Aup;
+        }
+        double F_out = 0.0;
+        for (int pass = 0; pass < s.npass; pass++) {
+            // ---------------- downward sweep ----------------
+            Aff m{1.0, 0.0};
+#pragma unroll
+            for (int k = CH - 1; k >= 0; k--) {
+                cc[k] = sd[k] - b[k] * Fu_reg[k];
+                m.B = a[k] * m.B + cc[k];
+                if (!HOIST) m.A = a[k] * m.A;
+            }
+            Aff sc;
+            if constexpr (HOIST) {
+                double mB = m.B;
+#pragma unroll
+                for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mdn[r], __shfl_down_sync(0xffffffffu, mB, d, LPC), mB);
+                sc = Aff{scA_dn, mB};
+            } else {
+                sc = scan_from_top<LPC>(m, sl, nch);
+            }
+            const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
+            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it
+            if (sl >= nch - 1) F = toa;
+            {
+                const double Fin = F;
+                bool flag = false;
+#pragma unroll
+                for (int k = CH - 1; k >= 0; k--) {
+                    F = __fma_rn(a[k], F, cc[k]);
+                    flag |= cleanup_candidate(F);
+                    Fd_reg[k] = F;
+                }
+                if (__any_sync(0xffffffffu, flag)) {  // rare: redo the walk with the reference's clean-up
+                    F = Fin;
+#pragma unroll
+                    for (int k = CH - 1; k >= 0; k--) {
+                        F = tiny_to_abs(__fma_rn(a[k], F, cc[k]));
+                        Fd_reg[k] = F;
+                    }
+                }
+            }
+            // the flux at my top interface as WALKED (and stored) by the lane above
+            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+            if (sl >= nch - 1) Fd_hi = toa;
+            // ---------------- upward sweep ----------------
+            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+            m = Aff{1.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                cc[k] = (NOBEAM ? sd[k] : su[NOBEAM ? 0 : k]) - b[k] * Fd_top;
+                m.B = a[k] * m.B + cc[k];
+                if (!HOIST) m.A = a[k] * m.A;
+            }
+            if constexpr (HOIST) {
+                double mB = m.B;
+#pragma unroll
+                for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mup[r], __shfl_up_sync(0xffffffffu, mB, d, LPC), mB);
+                sc = Aff{scA_up, mB};
+            } else {
+                sc = scan_from_bottom<LPC>(m, sl);
+            }
+            const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
+            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
+            if (sl == 0) F = fu0;
+            {
+                const double Fin = F;
+                bool flag = false;
+                double Fu_new[CH];
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    Fu_new[k] = F;  // interface lo+k: what the next pass's downward sweep reads
+                    F = __fma_rn(a[k], F, cc[k]);
+                    flag |= cleanup_candidate(F);
+                }
+                if (__any_sync(0xffffffffu, flag)) {
+                    F = Fin;
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        Fu_new[k] = F;
+                        F = tiny_to_abs(__fma_rn(a[k], F, cc[k]));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CH; k++) Fu_reg[k] = Fu_new[k];
+            }
+            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;  // as walked by the lane below: bit-identical to what F_up holds there
+            F_out = F;
+        }
+        // the fluxes of the last pass, from the registers
+        if (live && act) {
+            const size_t off = (size_t)atm * ncol * nint + colc + (size_t)ncol * lo;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                if (lo + k < nlay) {
+                    const size_t e = off + (size_t)k * ncol;
+                    F_down[e] = Fd_reg[k];
+                    F_up[e] = Fu_reg[k];
+                }
+            }
+            if (sl == nch - 1) {
+                const size_t e = (size_t)atm * ncol * nint + colc + (size_t)ncol * nlay;
+                F_down[e] = toa;
+                F_up[e] = F_out;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// Non-isothermal layers: two steps per layer (upper half, lower half).  NR = 8 rows per layer
+// [a_u, b_u, k1_u, k2_u, a_l, b_l, k1_l, k2_l] (+ [k0d_u, k0u_u, k0d_l, k0u_l] with a beam), two previous fluxes
+// (F_up, Fc_up), CH layer Planck values + CH+1 interface Planck values.  One column per warp (LPC = 32).
+// =================================================================================================
+template <int CH, bool NOBEAM, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
+               double* __restrict__ Fc_up, const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
+               const double* __restrict__ plan, const double* __restrict__ albedo, PlanScalars s) {
+    constexpr int NR = NOBEAM ? 8 : 12;
+    constexpr int LPC = 32;
+    constexpr int NBV = 2 * CH + 1;
+    using TS = TileShape<CH, NR, 2, NBV>;
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rl = s.rs;
+    const int ncol = s.nbin * s.ny;
+    const long long total = (long long)ncol * s.nbatch;
+    const int PB = TS::plan_doubles(rl, 1);
+    double* stage = smem + (size_t)warp * TS::stage_doubles(rl, 1);
+    double* pbuf = stage + 2;
+    double* fbuf = pbuf + PB;            // [2*CH][rl]: F_up (k), Fc_up (CH + k)
+    double* bbuf = fbuf + 2 * CH * rl;   // [2*CH+1][rl]: B_layer (k), B_interface (CH + k), k = 0..CH
+    double* cbuf = bbuf + NBV * rl;
+    const unsigned bar = smem_u32(stage), pbuf_s = smem_u32(pbuf), fbuf_s = smem_u32(fbuf), bbuf_s = smem_u32(bbuf),
+                   cbuf_s = smem_u32(cbuf);
+    const int sl = lane;
+    const bool act = sl < nch;
+    const int lo = sl * CH;
+    for (int k = lane; k < (2 * CH + NBV) * rl + 8; k += 32) fbuf[k] = 0.0;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+    }
+    __syncwarp();
+
+    auto issue = [&](long long wt) {
+        const int atm = (int)(wt / ncol);
+        const int col = (int)(wt - (long long)atm * ncol);
+        const int x = col / s.ny;
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(bar, (unsigned)PB * 8u);
+            bulk_g2s(pbuf_s, plan + (size_t)wt * PB, (unsigned)PB * 8u, bar);
+        }
+        const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
+        const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
+        const size_t wgo = (size_t)atm * ncol * nint + col;
+        if (act) {
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const int i = lo + k;
+                if (i < nlay) {
+                    cp_async8(fbuf_s + (unsigned)(k * rl + sl) * 8u, F_up + wgo + (size_t)ncol * i);
+                    cp_async8(fbuf_s + (unsigned)((CH + k) * rl + sl) * 8u, Fc_up + wgo + (size_t)ncol * i);
+                    cp_async8(bbuf_s + (unsigned)(k * rl + sl) * 8u, BL + i);
+                    cp_async8(bbuf_s + (unsigned)((CH + k) * rl + sl) * 8u, BI + i);
+                    if (k == CH - 1 || i == nlay - 1) cp_async8(bbuf_s + (unsigned)((CH + k + 1) * rl + sl) * 8u, BI + i + 1);
+                }
+            }
+        }
+        if (sl < 3) cp_async8(cbuf_s + (unsigned)sl * 8u, sl == 0 ? BL + nlay : (sl == 1 ? BL + nlay + 1 : albedo + x));
+        cp_async_commit();
+    };
+
+    const long long first = (long long)blockIdx.x * WARPS + warp, stride = (long long)gridDim.x * WARPS;
+    if (first < total) issue(first);
+    unsigned phase = 0;
+    const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
+    for (long long wt = first; wt < total; wt += stride) {
+        const int atm = (int)(wt / ncol);
+        const int col = (int)(wt - (long long)atm * ncol);
+        cp_async_wait_all();
+        __syncwarp();
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        // step constants: [0] = upper half, [1] = lower half of the lane's k-th layer
+        double a[2][CH], b[2][CH], sd[2][CH], su[2][CH], Fu_reg[CH], Fcu_reg[CH], Fd_reg[CH], Fcd_reg[CH], cc[2][CH];
+        const int mec = act ? sl : 0;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            const double Blay = bbuf[k * rl + mec], Bint_lo = bbuf[(CH + k) * rl + mec];
+            // the interface above my k-th layer: my own next row, or -- at the top of the chunk -- row CH + k + 1
+            const double Bint_hi = bbuf[(CH + k + 1) * rl + mec];
+            const double* __restrict__ p = pbuf + (size_t)(k * NR) * rl + mec;
+            a[0][k] = p[0];
+            b[0][k] = p[rl];
+            const double k1u = p[2 * rl], k2u = p[3 * rl];
+            a[1][k] = p[4 * rl];
+            b[1][k] = p[5 * rl];
+            const double k1l = p[6 * rl], k2l = p[7 * rl];
+            double k0d_u = 0.0, k0u_u = 0.0, k0d_l = 0.0, k0u_l = 0.0;
+            if (!NOBEAM) {
+                k0d_u = p[8 * rl];
+                k0u_u = p[9 * rl];
+                k0d_l = p[10 * rl];
+                k0u_l = p[11 * rl];
+            }
+            sd[0][k] = __fma_rn(k1u, Blay, __fma_rn(k2u, Bint_hi, k0d_u));
+            su[0][k] = __fma_rn(k2u, Blay, __fma_rn(k1u, Bint_hi, k0u_u));
+            sd[1][k] = __fma_rn(k1l, Blay, __fma_rn(k2l, Bint_lo, k0d_l));
+            su[1][k] = __fma_rn(k2l, Blay, __fma_rn(k1l, Bint_lo, k0u_l));
+            Fu_reg[k] = fbuf[k * rl + mec];
+            Fcu_reg[k] = fbuf[(CH + k) * rl + mec];
+            Fd_reg[k] = Fcd_reg[k] = 0.0;
+        }
+        const double emis = __dmul_rn(pbuf[CH * NR * rl], cbuf[1]);
+        const double Fdir0 = pbuf[CH * NR * rl + 1];
+        const double toa = toa_scale * cbuf[0];
+        const double A_s = cbuf[2];
+        __syncwarp();
+        if (wt + stride < total) issue(wt + stride);
+        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per warp
+
+        double F_out = 0.0;
+        for (int pass = 0; pass < s.npass; pass++) {
+            // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
+            Aff m{1.0, 0.0};
+#pragma unroll
+            for (int k = CH - 1; k >= 0; k--) {
+                cc[0][k] = sd[0][k] - b[0][k] * Fcu_reg[k];
+                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+                cc[1][k] = sd[1][k] - b[1][k] * Fu_reg[k];
+                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+            }
+            Aff sc = scan_from_top<LPC>(m, sl, nch);
+            const double Fbot = sc.A * toa + sc.B;
+            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);
+            if (sl >= nch - 1) F = toa;
+            {
+                const double Fin = F;
+                bool flag = false;
+#pragma unroll
+                for (int k = CH - 1; k >= 0; k--) {
+                    F = __fma_rn(a[0][k], F, cc[0][k]);
+                    flag |= cleanup_candidate(F);
+                    Fcd_reg[k] = F;
+                    F = __fma_rn(a[1][k], F, cc[1][k]);
+                    flag |= cleanup_candidate(F);
+                    Fd_reg[k] = F;
+                }
+                if (__any_sync(0xffffffffu, flag)) {
+                    F = Fin;
+#pragma unroll
+                    for (int k = CH - 1; k >= 0; k--) {
+                        F = tiny_to_abs(__fma_rn(a[0][k], F, cc[0][k]));
+                        Fcd_reg[k] = F;
+                        F = tiny_to_abs(__fma_rn(a[1][k], F, cc[1][k]));
+                        Fd_reg[k] = F;
+                    }
+                }
+            }
+            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+            if (sl >= nch - 1) Fd_hi = toa;
+            // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
+            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+            m = Aff{1.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                cc[1][k] = su[1][k] - b[1][k] * Fcd_reg[k];
+                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
+                cc[0][k] = su[0][k] - b[0][k] * Fd_top;
+                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
+            }
+            sc = scan_from_bottom<LPC>(m, sl);
+            const double Ftop = sc.A * fu0 + sc.B;
+            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);
+            if (sl == 0) F = fu0;
+            {
+                const double Fin = F;
+                bool flag = false;
+                double Fu_new[CH];
+#pragma unroll
+                for (int k = 0; k < CH; k++) {
+                    Fu_new[k] = F;
+                    // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
+                    F = __fma_rn(a[1][k], F, cc[1][k]);
+                    Fcu_reg[k] = F;
+                    F = __fma_rn(a[0][k], F, cc[0][k]);
+                    flag |= cleanup_candidate(F);
+                }
+                if (__any_sync(0xffffffffu, flag)) {
+                    F = Fin;
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        Fu_new[k] = F;
+                        F = __fma_rn(a[1][k], F, cc[1][k]);
+                        Fcu_reg[k] = F;
+                        F = tiny_to_abs(__fma_rn(a[0][k], F, cc[0][k]));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < CH; k++) Fu_reg[k] = Fu_new[k];
+            }
+            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
+            F_out = F;
+        }
+        if (act) {
+            const size_t off = (size_t)atm * ncol * nint + col + (size_t)ncol * lo;
+#pragma unroll
+            for (int k = 0; k < CH; k++) {
+                if (lo + k < nlay) {
+                    const size_t e = off + (size_t)k * ncol;
+                    F_down[e] = Fd_reg[k];
+                    Fc_down[e] = Fcd_reg[k];
+                    F_up[e] = Fu_reg[k];
+                    Fc_up[e] = Fcu_reg[k];
+                }
+            }
+            if (sl == nch - 1) {
+                const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * nlay;
+                F_down[e] = toa;
+                F_up[e] = F_out;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// Plan builders.  A CTA owns TC consecutive columns: its threads read the coefficient arrays with lanes along the
+// columns (coalesced row segments), form the constants, place them at their position of the tile blocks in shared
+// memory (the transposition), and the finished blocks -- contiguous in the plan -- go out as full 16-byte vector stores.
+// =================================================================================================
+struct BuildScalars {
+    double g_0, mu_star, epsi, delta_tau_limit, i2s_transition;
+    int nint, nbin, ny, clouds, scat_corr, no_beam, nch, rs, nbatch;
+};
+
+__device__ __forceinline__ void beam_pair(double Fa, double Fb, double neg_mu, double M, double N, double P, double G_pl,
+                                          double G_min, double m1d, double m2d, double& Dd, double& Du) {
+    Dd = 0.0;
+    Du = 0.0;
+    if (Fa != 0.0 || Fb != 0.0) {  // min(0, +-0) contributes nothing; also saves the four fp64 divisions
+        Dd = beam_source(Fa, Fb, neg_mu, M, G_min, N, G_pl, m1d, m2d);
+        Du = beam_source(Fb, Fa, neg_mu, N, G_min, M, G_pl, P, G_pl);
+    }
+}
+
+template <int CH, int LPC, int TC>
+__global__ void __launch_bounds__(256)
+k_plan_build_iso(double* __restrict__ plan, const double* __restrict__ F_dir, const double* __restrict__ w_0,
+                 const double* __restrict__ Mt, const double* __restrict__ Nt, const double* __restrict__ Pt,
+                 const double* __restrict__ Gp, const double* __restrict__ Gm, const double* __restrict__ albedo,
+                 const double* __restrict__ g0_lay, BuildScalars s) {
+    constexpr int CPW = 32 / LPC;
+    constexpr int TPB = TC / CPW;  // warp tiles per CTA
+    extern __shared__ __align__(16) double sm[];
+    const int NR = s.no_beam ? 3 : 5;
+    const int nint = s.nint, nlay = nint - 1, ncol = s.nbin * s.ny, rs = s.rs, rl = rs * CPW;
+    const int ntw = (ncol + CPW - 1) / CPW;
+    const int PB = CH * NR * rl + 4;
+    const int nblk = (ntw + TPB - 1) / TPB;  // CTAs' worth of tiles per atmosphere
+    const double neg_mu = -s.mu_star;
+    const int c = threadIdx.x % TC, r0 = threadIdx.x / TC;
+    constexpr int RSTEP = 256 / TC;
+    for (int blk = blockIdx.x; blk < nblk * s.nbatch; blk += gridDim.x) {
+        const int atm = blk / nblk;
+        const int t0 = (blk - atm * nblk) * TPB;  // first warp tile of this CTA
+        const int ntl = min(TPB, ntw - t0);
+        // identity steps everywhere first (cells outside the column, idle lanes): a = 1, everything else 0
+        for (int k = threadIdx.x; k < ntl * PB; k += 256) {
+            const int w = k % PB;
+            sm[k] = (w < CH * NR * rl && (w / rl) % NR == 0) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const int col = min(t0 * CPW + c, ncol - 1);
+        const int x = col / s.ny;
+        const int tl = c / CPW, cw = c % CPW;  // tile within the CTA, column within the tile
+        if (tl < ntl) {
+            for (int i = r0; i < nlay; i += RSTEP) {
+                const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * i;
+                const double w0 = w_0[e], M = Mt[e], N = Nt[e], P = Pt[e];
+                const double g0 = s.clouds ? g0_lay[(size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i] : s.g_0;
+                const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
+                double Dd = 0.0, Du = 0.0, Fdir_i = -0.0;
+                if (!s.no_beam) {
+                    Fdir_i = F_dir[e];
+                    const double gm = Gm[e];
+                    beam_pair(Fdir_i, F_dir[e + ncol], neg_mu, M, N, P, Gp[e], gm, P, gm, Dd, Du);
+                }
+                const double invM = 1.0 / M;
+                const double f = invM * source_factor(s.epsi, w0, E);
+                double* __restrict__ p = sm + (size_t)tl * PB + (size_t)((i % CH) * NR) * rl + cw * rs + i / CH;
+                p[0] = invM * P;
+                p[rl] = invM * N;
+                p[2 * rl] = f * ((M + N) - P);
+                if (!s.no_beam) {
+                    p[3 * rl] = invM * Dd;
+                    p[4 * rl] = invM * Du;
+                }
+                if (i == 0) {  // surface constants (K:1472: w0 and E of layer 0)
+                    const double A_s = albedo[x];
+                    double* __restrict__ ex = sm + (size_t)tl * PB + CH * NR * rl + cw * 2;
+                    ex[0] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0)),
+                                      __dsub_rn(E, w0));
+                    ex[1] = Fdir_i;
+                }
+            }
+        }
+        __syncthreads();
+        double2* __restrict__ dst = reinterpret_cast<double2*>(plan + ((size_t)atm * ntw + t0) * PB);
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(sm);
+        for (int k = threadIdx.x; k < ntl * PB / 2; k += 256) dst[k] = src[k];
+        __syncthreads();
+    }
+}
+
+struct NonisoCoefP {
+    const double *w0_u, *w0_l, *dtau_u, *dtau_l, *dtc_u, *dtc_l, *M_u, *M_l, *N_u, *N_l, *P_u, *P_l, *Gp_u, *Gp_l, *Gm_u,
+        *Gm_l;
+};
+
+struct Half {
+    double a, b, k0d, k0u, k1, k2;
+};
+
+// one half-layer (K:1640-1691 down, K:1744-1795 up).  `upper`: B1 of the downward form is the layer value.
+__device__ __forceinline__ Half plan_half(double w0, double M, double N, double P, double Gp, double Gm, double dt, double g0,
+                                          double Fa_d, double Fb_d, double m1d, double m2d, bool upper, double neg_mu,
+                                          const BuildScalars& s, double& E_out) {
+    const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
+    E_out = E;
+    const double invM = 1.0 / M;
+    const double fac = source_factor(s.epsi, w0, E);
+    double Dd, Du;
+    beam_pair(Fa_d, Fb_d, neg_mu, M, N, P, Gp, Gm, m1d, m2d, Dd, Du);
+    double lay_d, int_d;  // weights of B_layer / B_interface in the downward Planck term; upward: swapped (see header)
+    if (dt < s.delta_tau_limit) {
+        lay_d = int_d = 0.5 * ((M + N) - P);
+    } else {
+        const double pre = gradient_factor(s.epsi, w0, g0, E);
+        const double cd = (N + (P - M)) * pre / dt;
+        if (upper) {  // down: B1 = layer, B2 = interface above
+            lay_d = (M + N) + cd;
+            int_d = -P - cd;
+        } else {      // down: B1 = interface below, B2 = layer
+            lay_d = -P - cd;
+            int_d = (M + N) + cd;
+        }
+    }
+    const double f = invM * fac;
+    return Half{invM * P, invM * N, invM * Dd, invM * Du, f * lay_d, f * int_d};
+}
+
+template <int CH, int TC>
+__global__ void __launch_bounds__(256)
+k_plan_build_noniso(double* __restrict__ plan, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
+                    NonisoCoefP cfg, const double* __restrict__ albedo, const double* __restrict__ g0_lay,
+                    const double* __restrict__ g0_int, BuildScalars s) {
+    extern __shared__ __align__(16) double sm[];
+    const int NR = s.no_beam ? 8 : 12;
+    const int nint = s.nint, nlay = nint - 1, ncol = s.nbin * s.ny, rl = s.rs;
+    const int PB = CH * NR * rl + 4;
+    const int nblk = (ncol + TC - 1) / TC;
+    const double neg_mu = -s.mu_star;
+    const int c = threadIdx.x % TC, r0 = threadIdx.x / TC;
+    constexpr int RSTEP = 256 / TC;
+    for (int blk = blockIdx.x; blk < nblk * s.nbatch; blk += gridDim.x) {
+        const int atm = blk / nblk;
+        const int t0 = (blk - atm * nblk) * TC;
+        const int ntl = min(TC, ncol - t0);
+        for (int k = threadIdx.x; k < ntl * PB; k += 256) {
+            const int w = k % PB;
+            const int row = (w / rl) % NR;
+            sm[k] = (w < CH * NR * rl && (row == 0 || row == 4)) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        const int col = min(t0 + c, ncol - 1);
+        const int x = col / s.ny;
+        if (c < ntl) {
+            for (int i = r0; i < nlay; i += RSTEP) {
+                const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * i;
+                const size_t bl = (size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i;
+                const size_t bi = (size_t)atm * s.nbin * nint + (size_t)x + (size_t)s.nbin * i;
+                double g0_up = s.g_0, g0_low = s.g_0;
+                if (s.clouds) {
+                    const double gl = g0_lay[bl];
+                    g0_up = (gl + g0_int[bi + s.nbin]) / 2.0;
+                    g0_low = (g0_int[bi] + gl) / 2.0;
+                }
+                double Fdir_i = -0.0, Fdir_ip1 = -0.0, Fcdir = -0.0;
+                double Gp_u = 0.0, Gm_u = 0.0, Gp_l = 0.0, Gm_l = 0.0;
+                if (!s.no_beam) {
+                    Fdir_i = F_dir[e];
+                    Fdir_ip1 = F_dir[e + ncol];
+                    Fcdir = Fc_dir[e];
+                    Gp_u = cfg.Gp_u[e];
+                    Gm_u = cfg.Gm_u[e];
+                    Gp_l = cfg.Gp_l[e];
+                    Gm_l = cfg.Gm_l[e];
+                }
+                double E_u, E_l;
+                const double P_u = cfg.P_u[e];
+                const Half u = plan_half(cfg.w0_u[e], cfg.M_u[e], cfg.N_u[e], P_u, Gp_u, Gm_u, cfg.dtau_u[e] + cfg.dtc_u[bl],
+                                         g0_up, Fcdir, Fdir_ip1, Gm_u, P_u, true, neg_mu, s, E_u);
+                const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e];
+                const Half l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, Gp_l, Gm_l, cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low,
+                                         Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
+                double* __restrict__ p = sm + (size_t)c * PB + (size_t)((i % CH) * NR) * rl + i / CH;
+                p[0] = u.a;
+                p[rl] = u.b;
+                p[2 * rl] = u.k1;
+                p[3 * rl] = u.k2;
+                p[4 * rl] = l.a;
+                p[5 * rl] = l.b;
+                p[6 * rl] = l.k1;
+                p[7 * rl] = l.k2;
+                if (!s.no_beam) {
+                    p[8 * rl] = u.k0d;
+                    p[9 * rl] = u.k0u;
+                    p[10 * rl] = l.k0d;
+                    p[11 * rl] = l.k0u;
+                }
+                if (i == 0) {  // surface constants (K:1704: w0 and E of layer 0's lower half)
+                    const double A_s = albedo[x];
+                    double* __restrict__ ex = sm + (size_t)c * PB + CH * NR * rl;
+                    ex[0] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0_l)),
+                                      __dsub_rn(E_l, w0_l));
+                    ex[1] = Fdir_i;
+                }
+            }
+        }
+        __syncthreads();
+        double2* __restrict__ dst = reinterpret_cast<double2*>(plan + ((size_t)atm * ncol + t0) * PB);
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(sm);
+        for (int k = threadIdx.x; k < ntl * PB / 2; k += 256) dst[k] = src[k];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- host side ----------------------
+inline int even_up(int v) { return (v + 1) & ~1; }
+
+// tile shapes of the isothermal plan: CH layers per lane
+#define ISO_SHAPES(X)                     \
+    if (nlay <= 16) { X(1, 16); }         \
+    else if (nlay <= 32) { X(2, 16); }    \
+    else if (nlay <= 48) { X(3, 16); }    \
+    else if (nlay <= 80) { X(5, 16); }    \
+    else if (nlay <= 112) { X(7, 16); }   \
+    else if (nlay <= 128) { X(8, 16); }   \
+    else if (nlay <= 192) { X(6, 32); }   \
+    else if (nlay <= 256) { X(8, 32); }
+
+#define NONISO_SHAPES(X)               \
+    if (nlay <= 32) { X(1); }          \
+    else if (nlay <= 64) { X(2); }     \
+    else if (nlay <= 96) { X(3); }     \
+    else if (nlay <= 128) { X(4); }
+
+constexpr int ISO_TC = 32;    // columns per CTA of the isothermal plan build (256-byte row segments)
+constexpr int NONISO_TC = 8;  // non-isothermal: a column's block is 4x larger, 8 columns fill the shared memory
+
+struct IsoGeom {
+    int CH, LPC, nch, rs, cpw, ntw;
+    size_t pb;
+};
+bool iso_geom(int nlay, int ncol, bool nobeam, IsoGeom& g) {
+    g.CH = 0;
+#define X(CH_, LPC_) { g.CH = CH_; g.LPC = LPC_; }
+    ISO_SHAPES(X)
+#undef X
+    if (g.CH == 0) return false;
+    g.nch = (nlay + g.CH - 1) / g.CH;
+    g.rs = even_up(g.nch);
+    g.cpw = 32 / g.LPC;
+    g.ntw = (ncol + g.cpw - 1) / g.cpw;
+    g.pb = (size_t)g.CH * (nobeam ? 3 : 5) * g.rs * g.cpw + 4;
+    return true;
+}
+struct NonisoGeom {
+    int CH, nch, rs;
+    size_t pb;
+};
+bool noniso_geom(int nlay, bool nobeam, NonisoGeom& g) {
+    g.CH = 0;
+#define X(CH_) { g.CH = CH_; }
+    NONISO_SHAPES(X)
+#undef X
+    if (g.CH == 0) return false;
+    g.nch = (nlay + g.CH - 1) / g.CH;
+    g.rs = even_up(g.nch);
+    g.pb = (size_t)g.CH * (nobeam ? 8 : 12) * g.rs + 4;
+    return true;
+}
+
+// persistent grid: as many CTAs as fit per SM (registers, shared memory), capped by the work.  The occupancy query is
+// cached per (kernel, shared-memory size): launches may sit inside a CUDA-graph capture.
+template <typename K>
+int resident_grid(helios_ctx* ctx, K kern, int threads, size_t smem, long long work_ctas) {
+    static std::mutex mu;
+    static std::unordered_map<size_t, int> cache;
+    const size_t key = reinterpret_cast<size_t>(kern) ^ (smem * 0x9E3779B97F4A7C15ull) ^ ((size_t)ctx->device << 56);
+    int per_sm = 0;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) per_sm = it->second;
+    }
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        std::lock_guard<std::mutex> lk(mu);
+        cache[key] = per_sm;
+    }
+    const long long cap = (long long)ctx->num_sms * per_sm;
+    return (int)(work_ctas < cap ? work_ctas : cap);
+}
+
+template <int CH, int LPC, bool NOBEAM, bool HOIST>
+int launch_sweep_iso(helios_ctx* ctx, double* F_down, double* F_up, const double* planck_lay, const double* plan,
+                     const double* albedo, PlanScalars s, const IsoGeom& g) {
+    constexpr int WARPS = 4;
+    constexpr int MINB = 4;
+    auto kern = k_sweep_iso<CH, LPC, NOBEAM, HOIST, WARPS, MINB>;
+    using TS = TileShape<CH, NOBEAM ? 3 : 5, 1, CH>;
+    const size_t smem = (size_t)WARPS * TS::stage_doubles(g.rs, g.cpw) * sizeof(double);
+    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total = (long long)g.ntw * s.nbatch;
+    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, (total + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, planck_lay, plan, albedo, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+int tune_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e != nullptr ? atoi(e) : dflt;
+}
+
+template <int CH, bool NOBEAM, int WARPS, int MINB>
+int launch_sweep_noniso_cfg(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                            const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
+                            PlanScalars s, const NonisoGeom& g, int ncol) {
+    auto kern = k_sweep_noniso<CH, NOBEAM, WARPS, MINB>;
+    using TS = TileShape<CH, NOBEAM ? 8 : 12, 2, 2 * CH + 1>;
+    const size_t smem = (size_t)WARPS * TS::stage_doubles(g.rs, 1) * sizeof(double);
+    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total = (long long)ncol * s.nbatch;
+    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, (total + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
+}
+
+template <int CH, bool NOBEAM>
+int launch_sweep_noniso(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
+                        const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
+                        PlanScalars s, const NonisoGeom& g, int ncol) {
+    // All step constants live in registers (no shared-memory reads inside the passes): ~157 registers per lane at CH = 4.
+    // CTAs of 2 warps; 7 per SM (144 registers, a few spills on the load path) keep a single 100-layer x 7,700-column
+    // atmosphere at 4 rounds of 14 columns per SM, 6 per SM (168 registers, no spills) would need 5.
+#define NI_ARGS ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s, g, ncol
+    if constexpr (CH >= 4) {
+        static const int minb = tune_int("HELIOS_NONISO_MINB", 7);
+        if (minb == 6) return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 6>(NI_ARGS);
+        if (minb == 8) return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 8>(NI_ARGS);
+        return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 7>(NI_ARGS);
+    } else {
+        return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 8>(NI_ARGS);
+    }
+#undef NI_ARGS
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- entry points (called from fband.cu)
+size_t plan2_iso_size(int nint, int ncol, int nbatch) {
+    IsoGeom g;
+    if (!iso_geom(nint - 1, ncol, false, g)) return 0;
+    return g.pb * (size_t)g.ntw * nbatch;
+}
+
+size_t plan2_noniso_size(int nint, int ncol, int nbatch) {
+    NonisoGeom g;
+    if (!noniso_geom(nint - 1, false, g)) return 0;
+    return g.pb * (size_t)ncol * nbatch;
+}
+
+int plan2_iso_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* w_0, const double* M,
+                    const double* N, const double* P, const double* Gp, const double* Gm, const double* albedo,
+                    const double* g0tot, double g_0, double mu_star, double epsi, int nint, int nbin, int ny,
+                    int dir_beam, int clouds, int scat_corr, double i2s) {
+    const int nlay = nint - 1, ncol = nbin * ny;
+    const bool nobeam = dir_beam == 0 && ctx->zero_beam[0] == F_dir;
+    IsoGeom g;
+    if (!iso_geom(nlay, ncol, nobeam, g)) return -1;
+    BuildScalars s{g_0, mu_star, epsi, 0.0, i2s, nint, nbin, ny, clouds, scat_corr, nobeam ? 1 : 0, g.nch, g.rs,
+                   ctx->batch.nbatch};
+    const int tpb = ISO_TC / g.cpw;
+    const size_t smem = (size_t)tpb * g.pb * sizeof(double);
+    const long long nblk = (long long)((g.ntw + tpb - 1) / tpb) * s.nbatch;
+#define X(CH_, LPC_)                                                                                              \
+    {                                                                                                             \
+        auto kern = k_plan_build_iso<CH_, LPC_, ISO_TC>;                                                          \
+        HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+        const int grid = resident_grid(ctx, kern, 256, smem, nblk);                                               \
+        kern<<<grid, 256, smem, ctx->stream>>>(plan, F_dir, w_0, M, N, P, Gp, Gm, albedo, g0tot, s);               \
+    }
+    ISO_SHAPES(X)
+#undef X
+    HLAUNCHED(ctx);
+    helios_plan_record(ctx, plan, g.pb * (size_t)g.ntw * s.nbatch * sizeof(double), 1, nobeam ? 1 : 0, nint, ncol);
+    return HELIOS_OK;
+}
+
+int plan2_iso_sweep(helios_ctx* ctx, double* F_down, double* F_up, const double* plan, const double* planck_lay,
+                    const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
+                    int dir_beam, int npass) {
+    const int nlay = nint - 1, ncol = nbin * ny;
+    const helios_plan_info* info = helios_plan_lookup(ctx, plan, 1, nint, ncol);
+    if (info == nullptr) return -2;
+    const bool nobeam = info->nobeam != 0;
+    IsoGeom g;
+    if (!iso_geom(nlay, ncol, nobeam, g)) return -1;
+    PlanScalars s{Rstar, a, f_factor, nint, nbin, ny, dir_beam, npass, g.nch, g.rs, ctx->batch.nbatch,
+                  ctx->batch.active ? ctx->batch.done : nullptr};
+    const bool hoist = npass >= 8;  // one extra scan per tile buys B-only scans in every pass
+#define X(CH_, LPC_)                                                                                                   \
+    {                                                                                                                  \
+        if (nobeam) return hoist ? launch_sweep_iso<CH_, LPC_, true, true>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g)   \
+                                 : launch_sweep_iso<CH_, LPC_, true, false>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g); \
+        return hoist ? launch_sweep_iso<CH_, LPC_, false, true>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g)              \
+                     : launch_sweep_iso<CH_, LPC_, false, false>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g);            \
+    }
+    ISO_SHAPES(X)
+#undef X
+    return -1;
+}
+
+int plan2_noniso_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, const double* const* coef,
+                       const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
+                       double epsi, double delta_tau_limit, int nint, int nbin, int ny, int dir_beam, int clouds,
+                       int scat_corr, double i2s) {
+    const int nlay = nint - 1, ncol = nbin * ny;
+    const bool nobeam = dir_beam == 0 && ctx->zero_beam[0] == F_dir && ctx->zero_beam[1] == Fc_dir;
+    NonisoGeom g;
+    if (!noniso_geom(nlay, nobeam, g)) return -1;
+    BuildScalars s{g_0, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, clouds, scat_corr, nobeam ? 1 : 0, g.nch, g.rs,
+                   ctx->batch.nbatch};
+    NonisoCoefP c{coef[0], coef[1], coef[2], coef[3], coef[4], coef[5], coef[6], coef[7], coef[8], coef[9], coef[10],
+                  coef[11], coef[12], coef[13], coef[14], coef[15]};
+    const size_t smem = (size_t)NONISO_TC * g.pb * sizeof(double);
+    const long long nblk = (long long)((ncol + NONISO_TC - 1) / NONISO_TC) * s.nbatch;
+#define X(CH_)                                                                                               \
+    {                                                                                                        \
+        auto kern = k_plan_build_noniso<CH_, NONISO_TC>;                                                     \
+        HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        const int grid = resident_grid(ctx, kern, 256, smem, nblk);                                          \
+        kern<<<grid, 256, smem, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);           \
+    }
+    NONISO_SHAPES(X)
+#undef X
+    HLAUNCHED(ctx);
+    helios_plan_record(ctx, plan, g.pb * (size_t)ncol * s.nbatch * sizeof(double), 2, nobeam ? 1 : 0, nint, ncol);
+    return HELIOS_OK;
+}
+
+int plan2_noniso_sweep(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up, const double* plan,
+                       const double* planck_lay, const double* planck_int, const double* albedo, double Rstar, double a,
+                       int nint, int nbin, double f_factor, int ny, int dir_beam, int npass) {
+    const int nlay = nint - 1, ncol = nbin * ny;
+    const helios_plan_info* info = helios_plan_lookup(ctx, plan, 2, nint, ncol);
+    if (info == nullptr) return -2;
+    const bool nobeam = info->nobeam != 0;
+    NonisoGeom g;
+    if (!noniso_geom(nlay, nobeam, g)) return -1;
+    PlanScalars s{Rstar, a, f_factor, nint, nbin, ny, dir_beam, npass, g.nch, g.rs, ctx->batch.nbatch,
+                  ctx->batch.active ? ctx->batch.done : nullptr};
+#define X(CH_)                                                                                                          \
+    {                                                                                                                   \
+        if (nobeam) return launch_sweep_noniso<CH_, true>(ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s, g, ncol); \
+        return launch_sweep_noniso<CH_, false>(ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s, g, ncol);            \
+    }
+    NONISO_SHAPES(X)
+#undef X
+    return -1;
+}

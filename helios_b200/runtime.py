@@ -11,7 +11,11 @@ _default = None
 
 
 def default_device() -> int:
-    for key in ("HELIOS_DEVICE", "LOCAL_RANK"):
+    # LOCAL_RANK first: under torchrun every rank must bind its own GPU even when HELIOS_DEVICE is exported
+    if "LOCAL_RANK" in os.environ and "HELIOS_DEVICE" in os.environ and os.environ["LOCAL_RANK"] != os.environ["HELIOS_DEVICE"]:
+        import warnings
+        warnings.warn("both LOCAL_RANK and HELIOS_DEVICE are set; using LOCAL_RANK=%s" % os.environ["LOCAL_RANK"])
+    for key in ("LOCAL_RANK", "HELIOS_DEVICE"):
         if key in os.environ:
             return int(os.environ[key])
     return 0

@@ -318,6 +318,19 @@ int helios_fband_noniso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up
                                 const double* planckband_int, const double* surf_albedo, double Rstar, double a,
                                 int numinterfaces, int nbin, double f_factor, int ny, int dir_beam, int npass);
 
+/* The same for isothermal layers (one step per layer: a, b, the Planck factor and the two beam sources per cell).
+ * Call helios_fband_iso_plan_build after calc_trans_iso and fdir_iso; when the beam is known to be zero (fdir_iso
+ * ran with dir_beam == 0 and F_dir_wg was not written since) the sweep does not read the beam sources. */
+int helios_fband_iso_plan_size(helios_ctx* ctx, int numinterfaces, int nbin, int ny, size_t* ndoubles);
+int helios_fband_iso_plan_build(helios_ctx* ctx, double* plan, const double* F_dir_wg, const double* w_0,
+                                const double* M_term, const double* N_term, const double* P_term,
+                                const double* G_plus, const double* G_minus, const double* surf_albedo,
+                                const double* g_0_tot_lay, double g_0, int numinterfaces, int nbin, double mu_star,
+                                int ny, double epsi, int dir_beam, int clouds, int scat_corr, double i2s_transition);
+int helios_fband_iso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up_wg, const double* plan,
+                             const double* planckband_lay, const double* surf_albedo, double Rstar, double a,
+                             int numinterfaces, int nbin, double f_factor, int ny, int dir_beam, int npass);
+
 /* K:1803 fband_matrix_iso, C:630-668.  alpha/beta/source_term_* are accepted for signature
  * compatibility but not touched: the Thomas coefficients are formed on the fly; c_prime/d_prime
  * (2*ninterface*ny*nbin doubles each) hold the forward elimination. */

@@ -148,3 +148,45 @@ def test_random_overlap_rejects_unsupported_ny(ctx):
     one = ctx.to_device(np.ones(4))
     with pytest.raises(HeliosError):
         ctx.call("add_to_mixed_opac", one, d, d, one, one, one, 1.0, 1, 1, 8, 4, 1)
+
+
+@pytest.mark.parametrize("iso", [1, 0])
+def test_real_species_loop_h2o_between_other_scatterers(ctx, iso):
+    """Compute.calculate_total_opacity_and_scat_cross_sections_from_species itself (C:1454-1501), called twice as the
+    radiation loop does every 10th iteration, with H2O Rayleigh scattering AFTER one table-based scatterer and BEFORE
+    another: the H2O cross sections must never be written into another species' resident table (the reference
+    allocates fresh zeros for H2O on every call, C:1483-1486).  Expected values: the hand-driven stage-by-stage loop
+    above (held to the oracle and to the reference's kernels by the other tests), on a second store."""
+    def build():
+        q = synthetic.make_store("C3", ctx=ctx, kcoeff_mixing="correlated-k", n_species=5, **SMALL)
+        q.iso = np.int32(iso)
+        sp = {s.name: s for s in q.species_list}
+        co = sp["CO"]
+        co.scattering = "yes"
+        sig = 3e-27 * (q.opac_wave / 1e-4) ** -4.0
+        co.scat_cross_sect_layer = np.tile(sig, int(q.nlayer))
+        co.scat_cross_sect_interface = np.tile(sig, int(q.nlayer) + 1)
+        q.species_list = [sp["H2"], sp["H2O"], sp["CO"], sp["He"], sp["CO2"]]
+        n = int(q.nlayer)
+        q.T_lay = np.concatenate([np.linspace(2200.0, 800.0, n), [2300.0]])
+        return synthetic.upload(q)
+
+    q, qe = build(), build()
+    comp, comp_e = Compute(ctx, verbose=False), Compute(ctx, verbose=False)
+    names = ["scat_cross_lay", "opac_wg_lay"] + ([] if iso == 1 else ["scat_cross_int", "opac_wg_int"])
+
+    def plain(m, outs, args):
+        getattr(comp_e, m)(qe, *args)
+
+    _species_loop(qe, comp_e, plain)
+    want = {n: getattr(qe, "dev_" + n).get() for n in names}
+    for call in range(2):
+        comp.interpolate_temperatures(q)
+        host.calculate_meanmolecularmass(q)
+        host.nullify_opac_scat_arrays(q)
+        comp.calculate_total_opacity_and_scat_cross_sections_from_species(q)
+        for n in names:
+            assert_close(getattr(q, "dev_" + n).get(), want[n], "call %d: %s" % (call + 1, n), rtol=1e-13)
+    # the resident tables of the table-based scatterers are untouched
+    for key, sp in ((("sl", 0), q.species_list[0]), (("sl", 2), q.species_list[2])):
+        assert np.array_equal(comp._species_cache[key][1].get(), np.asarray(sp.scat_cross_sect_layer, np.float64))

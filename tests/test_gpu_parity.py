@@ -459,7 +459,7 @@ def test_unusual_layer_counts(ctx, config, nlayer):
     stage_vs_oracle(q, comp, oc, "calculate_transmission", ["w_0"] if iso else ["w_0_upper", "w_0_lower"], soft=bad)
     stage_vs_oracle(q, comp, oc, "calculate_direct_beamflux", ["F_dir_wg"], soft=bad)
     comp.build_flux_plan(q)
-    assert getattr(q, "_flux_plan_valid", False) == (not iso and n <= 128)
+    assert getattr(q, "_flux_plan_valid", False) == (n <= (256 if iso else 128))
     fl = ["F_down_wg", "F_up_wg"] + ([] if iso else ["Fc_down_wg", "Fc_up_wg"])
     q._flux_plan_valid = False  # the oracle comparison is for the generic entry point
     for _ in range(2):
@@ -471,21 +471,27 @@ def test_unusual_layer_counts(ctx, config, nlayer):
     bad.check()
 
 SHAPES = [("C1", 16), ("C1", 30), ("C1", 31), ("C1", 47), ("C1", 48), ("C1", 77), ("C1", 80), ("C1", 100), ("C1", 112),
-          ("C1", 120), ("C1", 128), ("C1", 200), ("C1", 203), ("C1", 256),
+          ("C1", 120), ("C1", 128), ("C1", 150), ("C1", 192), ("C1", 200), ("C1", 203), ("C1", 256),
           ("C2", 32), ("C2", 33), ("C2", 64), ("C2", 70), ("C2", 96), ("C2", 98), ("C2", 100), ("C2", 127), ("C2", 128),
           ("C2", 129), ("C2", 256)]
+# the other beam setting (C1 with a beam, C2 without): the plan drops / carries its beam rows
+FLIPPED = [("C1", 31), ("C1", 100), ("C1", 128), ("C1", 203), ("C2", 33), ("C2", 100), ("C2", 128)]
 
 
-@pytest.mark.parametrize("config,nlayer", SHAPES)
-def test_sweep_tile_shapes(ctx, config, nlayer):
+@pytest.mark.parametrize("config,nlayer,flip", [(c, n, False) for c, n in SHAPES] + [(c, n, True) for c, n in FLIPPED])
+def test_sweep_tile_shapes(ctx, config, nlayer, flip):
     """every instantiation of the layer-parallel sweeps (layers per lane 1..8, 16 / 32 lanes per column), with and
     without a partial top chunk and with every lane of a column in use (128 / 256 layers): two consecutive flux solves
-    against the reference's kernel (1e-10), and for non-isothermal columns of <= 128 layers the planned sweep against
-    the unplanned one from the same state (1e-12).  5 bins x 20 Gauss points = 100 columns: the last tile is partial."""
+    against the reference's kernel (1e-10); where a sweep plan exists (isothermal <= 256 layers, non-isothermal <= 128)
+    the planned sweep (fband_plan.cu) from the same state against the reference's kernel (1e-10) and against the
+    unplanned sweep (1e-12), with and without beam rows in the plan, for one pass sequence and for two consecutive
+    solves.  5 bins x 20 Gauss points = 100 columns: the last column tile of the builders is partial."""
     from util import HostMirror, restore
     q = synthetic.make_store(config, ctx=ctx, nbin=5, nlayer=nlayer, ntemp=12, npress=8, plancktable_dim=700,
                              plancktable_step=10)
     q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+    if flip:
+        q.dir_beam = np.int32(1 - int(q.dir_beam))
     n = int(q.nlayer)
     q.T_lay = np.concatenate([np.linspace(2300.0, 900.0, n), [2400.0]])
     synthetic.upload(q)
@@ -505,15 +511,49 @@ def test_sweep_tile_shapes(ctx, config, nlayer):
             stage_vs_ref(q, comp, ref, "populate_spectral_flux_iteratively", fl, soft=bad)
         else:
             comp.populate_spectral_flux_iteratively(q)
-    if not iso and n <= 128:
+    if n <= (256 if iso else 128):
         ctx.synchronize()
         before = HostMirror(q)
+        want_ref = None
+        if ref is not None:
+            ref.populate_spectral_flux_iteratively(q)
+            ref.populate_spectral_flux_iteratively(q)
+            want_ref = {name: getattr(q, "dev_" + name).get() for name in fl}
+            restore(q, before)
         comp.populate_spectral_flux_iteratively(q)
-        want = {name: getattr(q, "dev_" + name).get() for name in fl}
-        restore(q, before)
+        want1 = {name: getattr(q, "dev_" + name).get() for name in fl}
+        comp.populate_spectral_flux_iteratively(q)
+        want2 = {name: getattr(q, "dev_" + name).get() for name in fl}
+        restore(q, before)  # (also invalidates the library's record of any plan: it has to be rebuilt)
         comp.build_flux_plan(q)
         assert q._flux_plan_valid
         comp.populate_spectral_flux_iteratively(q)
         for name in fl:
-            assert_close(getattr(q, "dev_" + name).get(), want[name], "planned vs unplanned: " + name, rtol=1e-12, soft=bad)
+            assert_close(getattr(q, "dev_" + name).get(), want1[name], "planned vs unplanned: " + name, rtol=1e-12, soft=bad)
+        comp.populate_spectral_flux_iteratively(q)
+        for name in fl:
+            assert_close(getattr(q, "dev_" + name).get(), want2[name], "planned vs unplanned, 2nd solve: " + name,
+                         rtol=1e-12, soft=bad)
+            if want_ref is not None:
+                assert_close(getattr(q, "dev_" + name).get(), want_ref[name], "planned vs kernels.cu, 2nd solve: " + name,
+                             rtol=1e-10, soft=bad)
     bad.check()
+
+
+def test_planned_sweep_refuses_a_foreign_plan(ctx):
+    """the layout of a plan depends on how it was built; a buffer the library did not build (or that was written to
+    since) must be refused loudly, not interpreted"""
+    from helios_b200 import backend
+    q = synthetic.make_store("C1", ctx=ctx, **SMALL)
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    q.iter_value = np.int32(0)
+    for m in ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+              "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass",
+              "calculate_transmission", "calculate_direct_beamflux", "build_flux_plan"]:
+        getattr(comp, m)(q)
+    assert q._flux_plan_valid
+    comp.populate_spectral_flux_iteratively(q)
+    q.dev_fband_plan.set(q.dev_fband_plan.get())  # a write from outside: the record is dropped
+    with pytest.raises(backend.HeliosError):
+        comp.populate_spectral_flux_iteratively(q)
