@@ -32,6 +32,7 @@
 #include "sweep_math.cuh"
 #include "fband_plan.cuh"
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -80,37 +81,12 @@ __device__ __forceinline__ bool cleanup_candidate(double f) {
     return ((unsigned)__double2hiint(f) ^ 0x80000000u) <= 0x2B2BFF2Eu;
 }
 
-// affine maps x -> A x + B; Kogge-Stone scans inside segments of LPC lanes (one segment = one column)
-struct Aff {
-    double A, B;
-};
-template <int LPC>
-__device__ __forceinline__ Aff scan_from_top(Aff m, int sl, int n) {  // lane j: maps of lanes j..n-1, highest first
-#pragma unroll
-    for (int d = 1; d < LPC; d <<= 1) {
-        const double oA = __shfl_down_sync(0xffffffffu, m.A, d, LPC);
-        const double oB = __shfl_down_sync(0xffffffffu, m.B, d, LPC);
-        if (sl + d < n) {
-            m.B = m.A * oB + m.B;
-            m.A = m.A * oA;
-        }
-    }
-    return m;
-}
-template <int LPC>
-__device__ __forceinline__ Aff scan_from_bottom(Aff m, int sl) {  // lane j: maps of lanes j..0, lane 0 first
-#pragma unroll
-    for (int d = 1; d < LPC; d <<= 1) {
-        const double oA = __shfl_up_sync(0xffffffffu, m.A, d, LPC);
-        const double oB = __shfl_up_sync(0xffffffffu, m.B, d, LPC);
-        if (sl >= d) {
-            m.B = m.A * oB + m.B;
-            m.A = m.A * oA;
-        }
-    }
-    return m;
-}
-
+// ---------------------------------------------------------------- the passes -------------------
+// Scans.  The A parts of the affine maps (products of the a's of a chunk) do not depend on the fluxes, so everything the
+// Kogge-Stone scans need from them is formed ONCE per tile: the multiplier every step applies to the incoming B part
+// (0 where the step does not apply to this lane -- that replaces the guard and its selects) and the prefix product that
+// multiplies the boundary flux.  A pass then shuffles and multiply-adds the B parts only: 2 SHFL + 1 DFMA per step.
+// The multipliers live in warp-private shared memory, [step][down | up][lane].
 template <int LPC>
 struct Log2;
 template <>
@@ -122,95 +98,174 @@ struct Log2<32> {
     static constexpr int v = 5;
 };
 
-// Warp-private staging area (doubles): [mbarrier 2][plan block PB][previous fluxes NF*CH*RL][Planck NB*RL][column consts 8]
-template <int CH, int NR, int NF, int NB>
-struct TileShape {
-    __host__ __device__ static int rl(int rs, int cpw) { return rs * cpw; }
-    __host__ __device__ static int plan_doubles(int rs, int cpw) { return CH * NR * rs * cpw + 4; }
-    __host__ __device__ static int stage_doubles(int rs, int cpw) {
-        return 2 + plan_doubles(rs, cpw) + NF * CH * rs * cpw + NB * rs * cpw + 8;
+template <int LPC>
+__device__ __forceinline__ void scan_setup(double Adn, double Aup, int sl, int nch, int lane, volatile double* mult,
+                                           double& scA_dn, double& scA_up) {
+#pragma unroll
+    for (int r = 0, d = 1; d < LPC; r++, d <<= 1) {
+        const double odn = __shfl_down_sync(0xffffffffu, Adn, d, LPC);
+        const double oup = __shfl_up_sync(0xffffffffu, Aup, d, LPC);
+        const bool okd = sl + d < nch, oku = sl >= d;
+        mult[(2 * r) * 32 + lane] = okd ? Adn : 0.0;
+        mult[(2 * r + 1) * 32 + lane] = oku ? Aup : 0.0;
+        if (okd) Adn = Adn * odn;
+        if (oku) Aup = Aup * oup;
+    }
+    scA_dn = Adn;
+    scA_up = Aup;
+}
+template <int LPC>
+__device__ __forceinline__ double scan_dn(double mB, int lane, const volatile double* mult) {
+#pragma unroll
+    for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mult[(2 * r) * 32 + lane], __shfl_down_sync(0xffffffffu, mB, d, LPC), mB);
+    return mB;
+}
+template <int LPC>
+__device__ __forceinline__ double scan_up(double mB, int lane, const volatile double* mult) {
+#pragma unroll
+    for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mult[(2 * r + 1) * 32 + lane], __shfl_up_sync(0xffffffffu, mB, d, LPC), mB);
+    return mB;
+}
+
+// The reference cleans every new flux, fabs(f) < 1e-100 ? fabs(f) : f (K:1453 ...): 18 of the 26 cycles of a dependent
+// walk step, although it changes a value only if its sign bit is set (and |f| < 1e-100).  EXACT = false: no clean-up,
+// the sign bits of all results are OR-ed into `acc` (one LOP3, off the critical path); a tile whose `acc` stays positive
+// in every lane -- practically all of them -- is bit-identical to the cleaned evaluation.  Otherwise the tile is redone
+// with EXACT = true.
+template <bool EXACT>
+__device__ __forceinline__ double clean(double f, unsigned& acc) {
+    if (EXACT) return tiny_to_abs(f);
+    acc |= (unsigned)__double2hiint(f);
+    return f;
+}
+
+// Shared-memory map of a CTA (doubles).  A CTA of WARPS warps owns NC = WARPS * CPW consecutive columns (a CTA tile).
+//   per warp : [mbarrier 2][plan block PB][Planck values NB * rl][column constants 8]          rl = CPW * rs
+//   per CTA  : [scan multipliers WARPS * 2 * NST * 32 | results of the downward sweep]  [previous fluxes]  [results up]
+// The flux arrays are [interface][column] in HBM (K:1076): a warp that owns one column touches one 8-byte piece of a
+// different cache line with every lane -- 25 wavefronts per load/store instruction, and the LSU serialises them (that,
+// not HBM, bound the first build of this kernel: 16 of its 46 us were the stores, 8 us the flux loads).  So the fluxes
+// move COOPERATIVELY: all threads of the CTA copy the [layer][NC columns] block of the tile with lanes along the columns
+// (full 32 / 64-byte sectors), staged in shared memory in the order the lanes consume them, [array][k][column * (rs + 1) +
+// chunk].
+template <int CH, int NR, int NF, int NB, int NST, int CPW, int WARPS>
+struct CtaShape {
+    __host__ __device__ static int rl(int rs) { return rs * CPW; }
+    __host__ __device__ static int pb(int rs) { return CH * NR * rl(rs) + 4; }
+    __host__ __device__ static int warp_doubles(int rs) { return 2 + pb(rs) + NB * rl(rs) + 8; }
+    // staged flux rows: column pitch rs + 1 (odd), so that the cooperative copies -- lanes along the columns -- and the
+    // owners -- lanes along the chunks -- both spread over the banks
+    __host__ __device__ static int cpitch(int rs) { return rs + 1; }
+    __host__ __device__ static int frow(int rs) { return WARPS * CPW * cpitch(rs); }
+    __host__ __device__ static int flux_doubles(int rs) { return NF * CH * frow(rs); }
+    __host__ __device__ static int mult_doubles(int rs) {
+        const int m = WARPS * 2 * NST * 32, f = flux_doubles(rs);
+        return m > f ? m : f;
+    }
+    __host__ __device__ static int cta_doubles(int rs) {
+        return WARPS * warp_doubles(rs) + mult_doubles(rs) + 2 * flux_doubles(rs);
     }
 };
+
+// cooperative copy of one flux array block: global [nlay rows][NC columns at col0] <-> staged [k][c * rs + chunk]
+template <int CH, int NC, int THREADS, bool LOAD>
+__device__ __forceinline__ void flux_block(double* __restrict__ g, unsigned stage_s, double* stage, int nlay, int ncol,
+                                           int col0, int cp, int frow) {
+    const int c = threadIdx.x % NC;
+    const bool colok = col0 + c < ncol;
+    double* __restrict__ p = g + col0 + c + (size_t)(threadIdx.x / NC) * ncol;
+    for (int i = threadIdx.x / NC; i < nlay; i += THREADS / NC, p += (size_t)(THREADS / NC) * ncol) {
+        const int o = (i % CH) * frow + c * cp + i / CH;
+        if (colok) {
+            if (LOAD) cp_async8(stage_s + (unsigned)o * 8u, p);
+            else *p = stage[o];
+        }
+    }
+}
 
 // =================================================================================================
 // Isothermal layers: NR = 3 rows per layer [a, b, k1] (+ [k0d, k0u] with a beam), one previous flux, CH Planck values.
 // =================================================================================================
-template <int CH, int LPC, bool NOBEAM, bool HOIST, int WARPS, int MINB>
+template <int CH, int LPC, bool NOBEAM, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double* __restrict__ planck_lay,
             const double* __restrict__ plan, const double* __restrict__ albedo, PlanScalars s) {
     constexpr int NR = NOBEAM ? 3 : 5;
     constexpr int CPW = 32 / LPC;
+    constexpr int NC = WARPS * CPW;
     constexpr int NST = Log2<LPC>::v;
-    using TS = TileShape<CH, NR, 1, CH>;
+    constexpr int THREADS = WARPS * 32;
+    using CS = CtaShape<CH, NR, 1, CH, NST, CPW, WARPS>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rs = s.rs, rl = rs * CPW;
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rs = s.rs, rl = rs * CPW, cp = CS::cpitch(rs), frow = CS::frow(rs);
     const int ncol = s.nbin * s.ny;
-    const int ntw = (ncol + CPW - 1) / CPW;
-    const long long total = (long long)ntw * s.nbatch;
-    const int PB = TS::plan_doubles(rs, CPW);
-    double* stage = smem + (size_t)warp * TS::stage_doubles(rs, CPW);
-    double* pbuf = stage + 2;
-    double* fbuf = pbuf + PB;
-    double* bbuf = fbuf + CH * rl;
+    const unsigned ntw = (unsigned)(ncol + CPW - 1) / CPW;  // warp tiles per atmosphere (plan blocks)
+    const unsigned nct = (unsigned)(ncol + NC - 1) / NC;    // CTA tiles per atmosphere
+    const unsigned total = nct * (unsigned)s.nbatch;
+    const int PB = CS::pb(rs);
+    double* wst = smem + (size_t)warp * CS::warp_doubles(rs);
+    double* pbuf = wst + 2;
+    double* bbuf = pbuf + PB;
     double* cbuf = bbuf + CH * rl;
-    const unsigned bar = smem_u32(stage), pbuf_s = smem_u32(pbuf), fbuf_s = smem_u32(fbuf), bbuf_s = smem_u32(bbuf),
-                   cbuf_s = smem_u32(cbuf);
+    double* cta = smem + (size_t)WARPS * CS::warp_doubles(rs);
+    volatile double* mult = cta + warp * (2 * NST * 32);
+    double* fout_dn = cta;  // aliases the multipliers: written only after every warp has finished its passes
+    double* fin = cta + CS::mult_doubles(rs);
+    double* fout_up = fin + CS::flux_doubles(rs);
+    const unsigned bar = smem_u32(wst), pbuf_s = smem_u32(pbuf), bbuf_s = smem_u32(bbuf), cbuf_s = smem_u32(cbuf),
+                   fin_s = smem_u32(fin);
     const int cw = lane / LPC, sl = lane % LPC;
     const bool act = sl < nch;
     const int lo = sl * CH;
-    const int me = cw * rs + sl;  // my element of a staged row
-    // rows never written by the copies (layers beyond the column) must read as zeros
-    for (int k = lane; k < 2 * CH * rl + 8; k += 32) fbuf[k] = 0.0;
+    const int me = cw * rs + sl;                        // my element of a staged row of my warp
+    const int fme = (warp * CPW + cw) * cp + (act ? sl : 0);  // ... and of a staged flux row of the CTA
+    // slots never written by the copies (layers beyond the column) must read as zeros
+    for (int k = lane; k < CH * rl + 8; k += 32) bbuf[k] = 0.0;
+    for (int k = threadIdx.x; k < CS::flux_doubles(rs); k += THREADS) fin[k] = 0.0;
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    __syncwarp();
+    __syncthreads();
 
-    auto issue = [&](long long wt) {
-        const int atm = (int)(wt / ntw);
-        const int tile = (int)(wt - (long long)atm * ntw);
-        const int colc = min(tile * CPW + cw, ncol - 1);
+    auto issue = [&](unsigned ct) {
+        const unsigned atm = ct / nct;
+        const int ctile = (int)(ct - atm * nct);
+        const unsigned tile = min((unsigned)ctile * WARPS + warp, ntw - 1u);  // warps beyond the last column mirror it
+        const int colc = min((int)tile * CPW + cw, ncol - 1);
         const int x = colc / s.ny;
         if (lane == 0) {
             fence_proxy_async();  // the generic-proxy reads of the previous tile are ordered before the bulk write
             mbar_expect_tx(bar, (unsigned)PB * 8u);
-            bulk_g2s(pbuf_s, plan + (size_t)wt * PB, (unsigned)PB * 8u, bar);
+            bulk_g2s(pbuf_s, plan + ((size_t)atm * ntw + tile) * PB, (unsigned)PB * 8u, bar);
         }
         const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
-        const double* __restrict__ Fu = F_up + (size_t)atm * ncol * nint + colc;
         if (act) {
 #pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const int i = lo + k;
-                if (i < nlay) {
-                    cp_async8(fbuf_s + (unsigned)(k * rl + me) * 8u, Fu + (size_t)ncol * i);
-                    cp_async8(bbuf_s + (unsigned)(k * rl + me) * 8u, BL + i);
-                }
-            }
+            for (int k = 0; k < CH; k++)
+                if (lo + k < nlay) cp_async8(bbuf_s + (unsigned)(k * rl + me) * 8u, BL + lo + k);
         }
         if (sl < 3) cp_async8(cbuf_s + (unsigned)(cw * 4 + sl) * 8u, sl == 0 ? BL + nlay : (sl == 1 ? BL + nlay + 1 : albedo + x));
+        flux_block<CH, NC, THREADS, true>(F_up + (size_t)atm * ncol * nint, fin_s, nullptr, nlay, ncol, ctile * NC, cp, frow);
         cp_async_commit();
     };
 
-    const long long first = (long long)blockIdx.x * WARPS + warp, stride = (long long)gridDim.x * WARPS;
-    if (first < total) issue(first);
+    if (blockIdx.x < total) issue(blockIdx.x);
     unsigned phase = 0;
     const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
-    for (long long wt = first; wt < total; wt += stride) {
-        const int atm = (int)(wt / ntw);
-        const int tile = (int)(wt - (long long)atm * ntw);
-        const int col = tile * CPW + cw;
+    for (unsigned ct = blockIdx.x; ct < total; ct += gridDim.x) {
+        const unsigned atm = ct / nct;
+        const int ctile = (int)(ct - atm * nct);
+        const int col = (ctile * WARPS + warp) * CPW + cw;
         const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
         const int colc = live ? col : ncol - 1;
         // ---- lift the staged tile into registers
         cp_async_wait_all();
-        __syncwarp();
         mbar_wait(bar, phase);
         phase ^= 1u;
+        __syncthreads();  // everybody's flux copies have landed; the previous tile's cooperative stores are done
         double a[CH], b[CH], sd[CH], su[NOBEAM ? 1 : CH], Fu_reg[CH], Fd_reg[CH], cc[CH];
         const int mec = act ? me : cw * rs;  // idle lanes mirror chunk 0 of their column; nothing of theirs is consumed
 #pragma unroll
@@ -219,7 +274,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
             a[k] = pbuf[(k * NR + 0) * rl + mec];
             b[k] = pbuf[(k * NR + 1) * rl + mec];
             const double k1 = pbuf[(k * NR + 2) * rl + mec];
-            Fu_reg[k] = fbuf[k * rl + mec];
+            Fu_reg[k] = fin[k * frow + fme];
             Fd_reg[k] = 0.0;
             if (NOBEAM) {
                 sd[k] = __dmul_rn(k1, B);
@@ -232,138 +287,98 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         const double Fdir0 = pbuf[CH * NR * rl + cw * 2 + 1];
         const double toa = toa_scale * cbuf[cw * 4 + 0];
         const double A_s = cbuf[cw * 4 + 2];
-        __syncwarp();  // every lane has read the staging area: the next tile's copies may overwrite it
-        if (wt + stride < total) issue(wt + stride);
-        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per warp
+        __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
+        if (ct + gridDim.x < total) issue(ct + gridDim.x);
+        const bool skip = s.done != nullptr && s.done[atm] != 0;  // uniform per CTA
 
-        // Pass-invariant half of the scans (HOIST, long pass sequences): the A parts of the affine maps are products of
-        // the a's only; the multiplier each Kogge-Stone step applies to the incoming B (0 where the step does not apply
-        // to this lane) and the final prefix products are formed once per tile.
-        double mdn[HOIST ? NST : 1], mup[HOIST ? NST : 1], scA_dn = 1.0, scA_up = 1.0;
-        if constexpr (HOIST) {
-            double Adn = 1.0, Aup = 1.0;
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) Adn = a[k] * Adn;
-#pragma unroll
-            for (int k = 0; k < CH; k++) Aup = a[k] * Aup;
-#pragma unroll
-            for (int r = 0, d = 1; d < LPC; r++, d <<= 1) {
-                const double odn = __shfl_down_sync(0xffffffffu, Adn, d, LPC);
-                const double oup = __shfl_up_sync(0xffffffffu, Aup, d, LPC);
-                const bool okd = sl + d < nch, oku = sl >= d;
-                mdn[r] = okd ? Adn : 0.0;
-                mup[r] = oku ? Aup : 0.0;
-                if (okd) Adn = Adn * odn;
-                if (oku) Aup = Aup * oup;
-            }
-            scA_dn = Adn;
-            scA_up = Aup;
-        }
         double F_out = 0.0;
-        for (int pass = 0; pass < s.npass; pass++) {
-            // ---------------- downward sweep ----------------
-            Aff m{1.0, 0.0};
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) {
-                cc[k] = sd[k] - b[k] * Fu_reg[k];
-                m.B = a[k] * m.B + cc[k];
-                if (!HOIST) m.A = a[k] * m.A;
-            }
-            Aff sc;
-            if constexpr (HOIST) {
-                double mB = m.B;
-#pragma unroll
-                for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mdn[r], __shfl_down_sync(0xffffffffu, mB, d, LPC), mB);
-                sc = Aff{scA_dn, mB};
-            } else {
-                sc = scan_from_top<LPC>(m, sl, nch);
-            }
-            const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
-            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it
-            if (sl >= nch - 1) F = toa;
+        if (!skip) {
+            double scA_dn, scA_up;
             {
-                const double Fin = F;
-                bool flag = false;
+                double Adn = 1.0, Aup = 1.0;
 #pragma unroll
-                for (int k = CH - 1; k >= 0; k--) {
-                    F = __fma_rn(a[k], F, cc[k]);
-                    flag |= cleanup_candidate(F);
-                    Fd_reg[k] = F;
-                }
-                if (__any_sync(0xffffffffu, flag)) {  // rare: redo the walk with the reference's clean-up
-                    F = Fin;
+                for (int k = CH - 1; k >= 0; k--) Adn = a[k] * Adn;
+#pragma unroll
+                for (int k = 0; k < CH; k++) Aup = a[k] * Aup;
+                scan_setup<LPC>(Adn, Aup, sl, nch, lane, mult, scA_dn, scA_up);
+            }
+            const bool top = sl >= nch - 1, bottom = sl == 0;
+            auto passes = [&](auto exact_tag) -> unsigned {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                unsigned acc = 0u;
+                for (int pass = 0; pass < s.npass; pass++) {
+                    // ---------------- downward sweep ----------------
+                    double mB = 0.0;
 #pragma unroll
                     for (int k = CH - 1; k >= 0; k--) {
-                        F = tiny_to_abs(__fma_rn(a[k], F, cc[k]));
+                        cc[k] = sd[k] - b[k] * Fu_reg[k];
+                        mB = a[k] * mB + cc[k];
+                    }
+                    mB = scan_dn<LPC>(mB, lane, mult);
+                    const double Fbot = scA_dn * toa + mB;                   // flux leaving my chunk (interface lo)
+                    double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it
+                    F = top ? toa : F;
+#pragma unroll
+                    for (int k = CH - 1; k >= 0; k--) {
+                        F = clean<EXACT>(__fma_rn(a[k], F, cc[k]), acc);
                         Fd_reg[k] = F;
                     }
-                }
-            }
-            // the flux at my top interface as WALKED (and stored) by the lane above
-            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
-            if (sl >= nch - 1) Fd_hi = toa;
-            // ---------------- upward sweep ----------------
-            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
-            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
-            m = Aff{1.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                cc[k] = (NOBEAM ? sd[k] : su[NOBEAM ? 0 : k]) - b[k] * Fd_top;
-                m.B = a[k] * m.B + cc[k];
-                if (!HOIST) m.A = a[k] * m.A;
-            }
-            if constexpr (HOIST) {
-                double mB = m.B;
-#pragma unroll
-                for (int r = 0, d = 1; d < LPC; r++, d <<= 1) mB = __fma_rn(mup[r], __shfl_up_sync(0xffffffffu, mB, d, LPC), mB);
-                sc = Aff{scA_up, mB};
-            } else {
-                sc = scan_from_bottom<LPC>(m, sl);
-            }
-            const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
-            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
-            if (sl == 0) F = fu0;
-            {
-                const double Fin = F;
-                bool flag = false;
-                double Fu_new[CH];
-#pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    Fu_new[k] = F;  // interface lo+k: what the next pass's downward sweep reads
-                    F = __fma_rn(a[k], F, cc[k]);
-                    flag |= cleanup_candidate(F);
-                }
-                if (__any_sync(0xffffffffu, flag)) {
-                    F = Fin;
+                    // the flux at my top interface as WALKED (and stored) by the lane above
+                    double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+                    Fd_hi = top ? toa : Fd_hi;
+                    // ---------------- upward sweep ----------------
+                    double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+                    fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+                    mB = 0.0;
 #pragma unroll
                     for (int k = 0; k < CH; k++) {
-                        Fu_new[k] = F;
-                        F = tiny_to_abs(__fma_rn(a[k], F, cc[k]));
+                        const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                        cc[k] = (NOBEAM ? sd[k] : su[NOBEAM ? 0 : k]) - b[k] * Fd_top;
+                        mB = a[k] * mB + cc[k];
                     }
-                }
+                    mB = scan_up<LPC>(mB, lane, mult);
+                    const double Ftop = scA_up * fu0 + mB;          // flux leaving my chunk (interface hi)
+                    F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
+                    F = bottom ? fu0 : F;
 #pragma unroll
-                for (int k = 0; k < CH; k++) Fu_reg[k] = Fu_new[k];
+                    for (int k = 0; k < CH; k++) {
+                        Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
+                        F = clean<EXACT>(__fma_rn(a[k], F, cc[k]), acc);
+                    }
+                    const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+                    Fu_reg[0] = bottom ? fu0 : Fu_lo;  // as walked by the lane below: bit-identical to what F_up holds there
+                    F_out = F;
+                }
+                return acc;
+            };
+            const unsigned acc = passes(std::false_type{});
+            if (__any_sync(0xffffffffu, (int)acc < 0)) {
+                // a flux with its sign bit set appeared somewhere in the tile: redo it with the reference's clean-up, from
+                // the previous upward fluxes (still unmodified in HBM)
+                const double* __restrict__ Fu = F_up + (size_t)atm * ncol * nint + colc;
+#pragma unroll
+                for (int k = 0; k < CH; k++) Fu_reg[k] = (act && lo + k < nlay) ? Fu[(size_t)ncol * (lo + k)] : 0.0;
+                passes(std::true_type{});
             }
-            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
-            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;  // as walked by the lane below: bit-identical to what F_up holds there
-            F_out = F;
         }
-        // the fluxes of the last pass, from the registers
-        if (live && act) {
-            const size_t off = (size_t)atm * ncol * nint + colc + (size_t)ncol * lo;
+        // ---- the fluxes of the last pass: registers -> staged block -> cooperative full-sector stores
+        __syncthreads();  // every warp is done with its scan multipliers (fout_dn aliases them)
+        if (act) {
 #pragma unroll
             for (int k = 0; k < CH; k++) {
-                if (lo + k < nlay) {
-                    const size_t e = off + (size_t)k * ncol;
-                    F_down[e] = Fd_reg[k];
-                    F_up[e] = Fu_reg[k];
-                }
+                fout_dn[k * frow + fme] = Fd_reg[k];
+                fout_up[k * frow + fme] = Fu_reg[k];
             }
-            if (sl == nch - 1) {
-                const size_t e = (size_t)atm * ncol * nint + colc + (size_t)ncol * nlay;
-                F_down[e] = toa;
-                F_up[e] = F_out;
+        }
+        __syncthreads();
+        if (!skip) {
+            double* __restrict__ gd = F_down + (size_t)atm * ncol * nint;
+            double* __restrict__ gu = F_up + (size_t)atm * ncol * nint;
+            flux_block<CH, NC, THREADS, false>(gd, 0u, fout_dn, nlay, ncol, ctile * NC, cp, frow);
+            flux_block<CH, NC, THREADS, false>(gu, 0u, fout_up, nlay, ncol, ctile * NC, cp, frow);
+            if (live && sl == nch - 1) {  // interface nlayer (TOA)
+                gd[(size_t)ncol * nlay + colc] = toa;
+                gu[(size_t)ncol * nlay + colc] = F_out;
             }
         }
     }
@@ -381,51 +396,59 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
                const double* __restrict__ plan, const double* __restrict__ albedo, PlanScalars s) {
     constexpr int NR = NOBEAM ? 8 : 12;
     constexpr int LPC = 32;
+    constexpr int NC = WARPS;
     constexpr int NBV = 2 * CH + 1;
-    using TS = TileShape<CH, NR, 2, NBV>;
+    constexpr int THREADS = WARPS * 32;
+    using CS = CtaShape<CH, NR, 2, NBV, 5, 1, WARPS>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rl = s.rs;
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rl = s.rs, cp = CS::cpitch(rl), frow = CS::frow(rl);
     const int ncol = s.nbin * s.ny;
-    const long long total = (long long)ncol * s.nbatch;
-    const int PB = TS::plan_doubles(rl, 1);
-    double* stage = smem + (size_t)warp * TS::stage_doubles(rl, 1);
-    double* pbuf = stage + 2;
-    double* fbuf = pbuf + PB;            // [2*CH][rl]: F_up (k), Fc_up (CH + k)
-    double* bbuf = fbuf + 2 * CH * rl;   // [2*CH+1][rl]: B_layer (k), B_interface (CH + k), k = 0..CH
+    const unsigned nct = (unsigned)(ncol + NC - 1) / NC;  // CTA tiles per atmosphere
+    const unsigned total = nct * (unsigned)s.nbatch;
+    const int PB = CS::pb(rl);
+    double* wst = smem + (size_t)warp * CS::warp_doubles(rl);
+    double* pbuf = wst + 2;
+    double* bbuf = pbuf + PB;  // [2*CH+1][rl]: B_layer (k), B_interface (CH + k), k = 0..CH
     double* cbuf = bbuf + NBV * rl;
-    const unsigned bar = smem_u32(stage), pbuf_s = smem_u32(pbuf), fbuf_s = smem_u32(fbuf), bbuf_s = smem_u32(bbuf),
-                   cbuf_s = smem_u32(cbuf);
+    double* cta = smem + (size_t)WARPS * CS::warp_doubles(rl);
+    volatile double* mult = cta + warp * (2 * 5 * 32);
+    double* fout_dn = cta;  // [F_down | Fc_down]; aliases the multipliers
+    double* fin = cta + CS::mult_doubles(rl);  // [F_up | Fc_up] of the previous solve
+    double* fout_up = fin + CS::flux_doubles(rl);
+    const int fone = CH * frow;  // one staged flux array
+    const unsigned bar = smem_u32(wst), pbuf_s = smem_u32(pbuf), bbuf_s = smem_u32(bbuf), cbuf_s = smem_u32(cbuf),
+                   fin_s = smem_u32(fin);
     const int sl = lane;
     const bool act = sl < nch;
     const int lo = sl * CH;
-    for (int k = lane; k < (2 * CH + NBV) * rl + 8; k += 32) fbuf[k] = 0.0;
+    const int fme = warp * cp + (act ? sl : 0);  // my element of a staged flux row of the CTA
+    for (int k = lane; k < NBV * rl + 8; k += 32) bbuf[k] = 0.0;
+    for (int k = threadIdx.x; k < CS::flux_doubles(rl); k += THREADS) fin[k] = 0.0;
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         fence_proxy_async();
     }
-    __syncwarp();
+    __syncthreads();
 
-    auto issue = [&](long long wt) {
-        const int atm = (int)(wt / ncol);
-        const int col = (int)(wt - (long long)atm * ncol);
+    auto issue = [&](unsigned ct) {
+        const unsigned atm = ct / nct;
+        const int ctile = (int)(ct - atm * nct);
+        const int col = min(ctile * NC + warp, ncol - 1);  // warps beyond the last column mirror it
         const int x = col / s.ny;
         if (lane == 0) {
             fence_proxy_async();
             mbar_expect_tx(bar, (unsigned)PB * 8u);
-            bulk_g2s(pbuf_s, plan + (size_t)wt * PB, (unsigned)PB * 8u, bar);
+            bulk_g2s(pbuf_s, plan + ((size_t)atm * ncol + col) * PB, (unsigned)PB * 8u, bar);
         }
         const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
         const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
-        const size_t wgo = (size_t)atm * ncol * nint + col;
         if (act) {
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const int i = lo + k;
                 if (i < nlay) {
-                    cp_async8(fbuf_s + (unsigned)(k * rl + sl) * 8u, F_up + wgo + (size_t)ncol * i);
-                    cp_async8(fbuf_s + (unsigned)((CH + k) * rl + sl) * 8u, Fc_up + wgo + (size_t)ncol * i);
                     cp_async8(bbuf_s + (unsigned)(k * rl + sl) * 8u, BL + i);
                     cp_async8(bbuf_s + (unsigned)((CH + k) * rl + sl) * 8u, BI + i);
                     if (k == CH - 1 || i == nlay - 1) cp_async8(bbuf_s + (unsigned)((CH + k + 1) * rl + sl) * 8u, BI + i + 1);
@@ -433,28 +456,32 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
             }
         }
         if (sl < 3) cp_async8(cbuf_s + (unsigned)sl * 8u, sl == 0 ? BL + nlay : (sl == 1 ? BL + nlay + 1 : albedo + x));
+        const size_t ao = (size_t)atm * ncol * nint;
+        flux_block<CH, NC, THREADS, true>(F_up + ao, fin_s, nullptr, nlay, ncol, ctile * NC, cp, frow);
+        flux_block<CH, NC, THREADS, true>(Fc_up + ao, fin_s + (unsigned)fone * 8u, nullptr, nlay, ncol, ctile * NC, cp, frow);
         cp_async_commit();
     };
 
-    const long long first = (long long)blockIdx.x * WARPS + warp, stride = (long long)gridDim.x * WARPS;
-    if (first < total) issue(first);
+    if (blockIdx.x < total) issue(blockIdx.x);
     unsigned phase = 0;
     const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
-    for (long long wt = first; wt < total; wt += stride) {
-        const int atm = (int)(wt / ncol);
-        const int col = (int)(wt - (long long)atm * ncol);
+    for (unsigned ct = blockIdx.x; ct < total; ct += gridDim.x) {
+        const unsigned atm = ct / nct;
+        const int ctile = (int)(ct - atm * nct);
+        const int col = ctile * NC + warp;
+        const bool live = col < ncol;  // uniform per warp
+        const int colc = live ? col : ncol - 1;
         cp_async_wait_all();
-        __syncwarp();
         mbar_wait(bar, phase);
         phase ^= 1u;
+        __syncthreads();  // everybody's flux copies have landed; the previous tile's cooperative stores are done
         // step constants: [0] = upper half, [1] = lower half of the lane's k-th layer
         double a[2][CH], b[2][CH], sd[2][CH], su[2][CH], Fu_reg[CH], Fcu_reg[CH], Fd_reg[CH], Fcd_reg[CH], cc[2][CH];
         const int mec = act ? sl : 0;
 #pragma unroll
         for (int k = 0; k < CH; k++) {
             const double Blay = bbuf[k * rl + mec], Bint_lo = bbuf[(CH + k) * rl + mec];
-            // the interface above my k-th layer: my own next row, or -- at the top of the chunk -- row CH + k + 1
-            const double Bint_hi = bbuf[(CH + k + 1) * rl + mec];
+            const double Bint_hi = bbuf[(CH + k + 1) * rl + mec];  // the interface above my k-th layer
             const double* __restrict__ p = pbuf + (size_t)(k * NR) * rl + mec;
             a[0][k] = p[0];
             b[0][k] = p[rl];
@@ -473,120 +500,120 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
             su[0][k] = __fma_rn(k2u, Blay, __fma_rn(k1u, Bint_hi, k0u_u));
             sd[1][k] = __fma_rn(k1l, Blay, __fma_rn(k2l, Bint_lo, k0d_l));
             su[1][k] = __fma_rn(k2l, Blay, __fma_rn(k1l, Bint_lo, k0u_l));
-            Fu_reg[k] = fbuf[k * rl + mec];
-            Fcu_reg[k] = fbuf[(CH + k) * rl + mec];
+            Fu_reg[k] = fin[k * frow + fme];
+            Fcu_reg[k] = fin[fone + k * frow + fme];
             Fd_reg[k] = Fcd_reg[k] = 0.0;
         }
         const double emis = __dmul_rn(pbuf[CH * NR * rl], cbuf[1]);
         const double Fdir0 = pbuf[CH * NR * rl + 1];
         const double toa = toa_scale * cbuf[0];
         const double A_s = cbuf[2];
-        __syncwarp();
-        if (wt + stride < total) issue(wt + stride);
-        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per warp
+        __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
+        if (ct + gridDim.x < total) issue(ct + gridDim.x);
+        const bool skip = s.done != nullptr && s.done[atm] != 0;  // uniform per CTA
 
         double F_out = 0.0;
-        for (int pass = 0; pass < s.npass; pass++) {
-            // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
-            Aff m{1.0, 0.0};
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) {
-                cc[0][k] = sd[0][k] - b[0][k] * Fcu_reg[k];
-                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
-                cc[1][k] = sd[1][k] - b[1][k] * Fu_reg[k];
-                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
-            }
-            Aff sc = scan_from_top<LPC>(m, sl, nch);
-            const double Fbot = sc.A * toa + sc.B;
-            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);
-            if (sl >= nch - 1) F = toa;
+        if (!skip) {
+            double scA_dn, scA_up;
             {
-                const double Fin = F;
-                bool flag = false;
+                double Adn = 1.0, Aup = 1.0;
 #pragma unroll
-                for (int k = CH - 1; k >= 0; k--) {
-                    F = __fma_rn(a[0][k], F, cc[0][k]);
-                    flag |= cleanup_candidate(F);
-                    Fcd_reg[k] = F;
-                    F = __fma_rn(a[1][k], F, cc[1][k]);
-                    flag |= cleanup_candidate(F);
-                    Fd_reg[k] = F;
-                }
-                if (__any_sync(0xffffffffu, flag)) {
-                    F = Fin;
+                for (int k = CH - 1; k >= 0; k--) Adn = a[1][k] * (a[0][k] * Adn);
+#pragma unroll
+                for (int k = 0; k < CH; k++) Aup = a[0][k] * (a[1][k] * Aup);
+                scan_setup<LPC>(Adn, Aup, sl, nch, lane, mult, scA_dn, scA_up);
+            }
+            const bool top = sl >= nch - 1, bottom = sl == 0;
+            auto passes = [&](auto exact_tag) -> unsigned {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                unsigned acc = 0u;
+                for (int pass = 0; pass < s.npass; pass++) {
+                    // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
+                    double mB = 0.0;
 #pragma unroll
                     for (int k = CH - 1; k >= 0; k--) {
-                        F = tiny_to_abs(__fma_rn(a[0][k], F, cc[0][k]));
+                        cc[0][k] = sd[0][k] - b[0][k] * Fcu_reg[k];
+                        mB = a[0][k] * mB + cc[0][k];
+                        cc[1][k] = sd[1][k] - b[1][k] * Fu_reg[k];
+                        mB = a[1][k] * mB + cc[1][k];
+                    }
+                    mB = scan_dn<LPC>(mB, lane, mult);
+                    const double Fbot = scA_dn * toa + mB;
+                    double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);
+                    F = top ? toa : F;
+#pragma unroll
+                    for (int k = CH - 1; k >= 0; k--) {
+                        F = clean<EXACT>(__fma_rn(a[0][k], F, cc[0][k]), acc);
                         Fcd_reg[k] = F;
-                        F = tiny_to_abs(__fma_rn(a[1][k], F, cc[1][k]));
+                        F = clean<EXACT>(__fma_rn(a[1][k], F, cc[1][k]), acc);
                         Fd_reg[k] = F;
                     }
-                }
-            }
-            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
-            if (sl >= nch - 1) Fd_hi = toa;
-            // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
-            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
-            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
-            m = Aff{1.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                cc[1][k] = su[1][k] - b[1][k] * Fcd_reg[k];
-                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
-                cc[0][k] = su[0][k] - b[0][k] * Fd_top;
-                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
-            }
-            sc = scan_from_bottom<LPC>(m, sl);
-            const double Ftop = sc.A * fu0 + sc.B;
-            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);
-            if (sl == 0) F = fu0;
-            {
-                const double Fin = F;
-                bool flag = false;
-                double Fu_new[CH];
-#pragma unroll
-                for (int k = 0; k < CH; k++) {
-                    Fu_new[k] = F;
-                    // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
-                    F = __fma_rn(a[1][k], F, cc[1][k]);
-                    Fcu_reg[k] = F;
-                    F = __fma_rn(a[0][k], F, cc[0][k]);
-                    flag |= cleanup_candidate(F);
-                }
-                if (__any_sync(0xffffffffu, flag)) {
-                    F = Fin;
+                    double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
+                    Fd_hi = top ? toa : Fd_hi;
+                    // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
+                    double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
+                    fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
+                    mB = 0.0;
 #pragma unroll
                     for (int k = 0; k < CH; k++) {
-                        Fu_new[k] = F;
+                        const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
+                        cc[1][k] = su[1][k] - b[1][k] * Fcd_reg[k];
+                        mB = a[1][k] * mB + cc[1][k];
+                        cc[0][k] = su[0][k] - b[0][k] * Fd_top;
+                        mB = a[0][k] * mB + cc[0][k];
+                    }
+                    mB = scan_up<LPC>(mB, lane, mult);
+                    const double Ftop = scA_up * fu0 + mB;
+                    F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);
+                    F = bottom ? fu0 : F;
+#pragma unroll
+                    for (int k = 0; k < CH; k++) {
+                        Fu_reg[k] = F;
+                        // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
                         F = __fma_rn(a[1][k], F, cc[1][k]);
                         Fcu_reg[k] = F;
-                        F = tiny_to_abs(__fma_rn(a[0][k], F, cc[0][k]));
+                        F = clean<EXACT>(__fma_rn(a[0][k], F, cc[0][k]), acc);
                     }
+                    const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
+                    Fu_reg[0] = bottom ? fu0 : Fu_lo;
+                    F_out = F;
                 }
+                return acc;
+            };
+            const unsigned acc = passes(std::false_type{});
+            if (__any_sync(0xffffffffu, (int)acc < 0)) {
+                const size_t wgo = (size_t)atm * ncol * nint + colc;
 #pragma unroll
-                for (int k = 0; k < CH; k++) Fu_reg[k] = Fu_new[k];
+                for (int k = 0; k < CH; k++) {
+                    const bool in = act && lo + k < nlay;
+                    Fu_reg[k] = in ? F_up[wgo + (size_t)ncol * (lo + k)] : 0.0;
+                    Fcu_reg[k] = in ? Fc_up[wgo + (size_t)ncol * (lo + k)] : 0.0;
+                }
+                passes(std::true_type{});
             }
-            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
-            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
-            F_out = F;
         }
+        // ---- the fluxes of the last pass: registers -> staged block -> cooperative full-sector stores
+        __syncthreads();  // every warp is done with its scan multipliers (fout_dn aliases them)
         if (act) {
-            const size_t off = (size_t)atm * ncol * nint + col + (size_t)ncol * lo;
 #pragma unroll
             for (int k = 0; k < CH; k++) {
-                if (lo + k < nlay) {
-                    const size_t e = off + (size_t)k * ncol;
-                    F_down[e] = Fd_reg[k];
-                    Fc_down[e] = Fcd_reg[k];
-                    F_up[e] = Fu_reg[k];
-                    Fc_up[e] = Fcu_reg[k];
-                }
+                const int o = k * frow + fme;
+                fout_dn[o] = Fd_reg[k];
+                fout_dn[fone + o] = Fcd_reg[k];
+                fout_up[o] = Fu_reg[k];
+                fout_up[fone + o] = Fcu_reg[k];
             }
-            if (sl == nch - 1) {
-                const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * nlay;
-                F_down[e] = toa;
-                F_up[e] = F_out;
+        }
+        __syncthreads();
+        if (!skip) {
+            const size_t ao = (size_t)atm * ncol * nint;
+            flux_block<CH, NC, THREADS, false>(F_down + ao, 0u, fout_dn, nlay, ncol, ctile * NC, cp, frow);
+            flux_block<CH, NC, THREADS, false>(Fc_down + ao, 0u, fout_dn + fone, nlay, ncol, ctile * NC, cp, frow);
+            flux_block<CH, NC, THREADS, false>(F_up + ao, 0u, fout_up, nlay, ncol, ctile * NC, cp, frow);
+            flux_block<CH, NC, THREADS, false>(Fc_up + ao, 0u, fout_up + fone, nlay, ncol, ctile * NC, cp, frow);
+            if (live && sl == nch - 1) {  // interface nlayer (TOA)
+                F_down[ao + (size_t)ncol * nlay + colc] = toa;
+                F_up[ao + (size_t)ncol * nlay + colc] = F_out;
             }
         }
     }
@@ -824,7 +851,9 @@ inline int even_up(int v) { return (v + 1) & ~1; }
     else if (nlay <= 96) { X(3); }     \
     else if (nlay <= 128) { X(4); }
 
-constexpr int ISO_TC = 32;    // columns per CTA of the isothermal plan build (256-byte row segments)
+// columns per CTA of the isothermal plan build: 32 (256-byte row segments) for two-column warp tiles, 8 where a warp
+// tile is one column of up to 256 layers (the CTA's tile blocks have to fit into shared memory)
+constexpr int iso_tc(int lpc) { return lpc == 16 ? 32 : 8; }
 constexpr int NONISO_TC = 8;  // non-isothermal: a column's block is 4x larger, 8 columns fill the shared memory
 
 struct IsoGeom {
@@ -882,38 +911,24 @@ int resident_grid(helios_ctx* ctx, K kern, int threads, size_t smem, long long w
     return (int)(work_ctas < cap ? work_ctas : cap);
 }
 
-template <int CH, int LPC, bool NOBEAM, bool HOIST>
-int launch_sweep_iso(helios_ctx* ctx, double* F_down, double* F_up, const double* planck_lay, const double* plan,
-                     const double* albedo, PlanScalars s, const IsoGeom& g) {
-    constexpr int WARPS = 4;
-    constexpr int MINB = 4;
-    auto kern = k_sweep_iso<CH, LPC, NOBEAM, HOIST, WARPS, MINB>;
-    using TS = TileShape<CH, NOBEAM ? 3 : 5, 1, CH>;
-    const size_t smem = (size_t)WARPS * TS::stage_doubles(g.rs, g.cpw) * sizeof(double);
-    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long total = (long long)g.ntw * s.nbatch;
-    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, (total + WARPS - 1) / WARPS);
-    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, planck_lay, plan, albedo, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
-}
-
 int tune_int(const char* name, int dflt) {
     const char* e = getenv(name);
     return e != nullptr ? atoi(e) : dflt;
 }
 
-template <int CH, bool NOBEAM, int WARPS, int MINB>
-int launch_sweep_noniso_cfg(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
-                            const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
-                            PlanScalars s, const NonisoGeom& g, int ncol) {
-    auto kern = k_sweep_noniso<CH, NOBEAM, WARPS, MINB>;
-    using TS = TileShape<CH, NOBEAM ? 8 : 12, 2, 2 * CH + 1>;
-    const size_t smem = (size_t)WARPS * TS::stage_doubles(g.rs, 1) * sizeof(double);
+template <int CH, int LPC, bool NOBEAM>
+int launch_sweep_iso(helios_ctx* ctx, double* F_down, double* F_up, const double* planck_lay, const double* plan,
+                     const double* albedo, PlanScalars s, const IsoGeom& g) {
+    constexpr int WARPS = 4;
+    constexpr int MINB = 4;
+    constexpr int NC = WARPS * (32 / LPC);
+    auto kern = k_sweep_iso<CH, LPC, NOBEAM, WARPS, MINB>;
+    using CS = CtaShape<CH, NOBEAM ? 3 : 5, 1, CH, Log2<LPC>::v, 32 / LPC, WARPS>;
+    const size_t smem = (size_t)CS::cta_doubles(g.rs) * sizeof(double);
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long total = (long long)ncol * s.nbatch;
-    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, (total + WARPS - 1) / WARPS);
-    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);
+    const long long total = (long long)((s.nbin * s.ny + NC - 1) / NC) * s.nbatch;
+    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, total);
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, planck_lay, plan, albedo, s);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -922,19 +937,20 @@ template <int CH, bool NOBEAM>
 int launch_sweep_noniso(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
                         const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
                         PlanScalars s, const NonisoGeom& g, int ncol) {
-    // All step constants live in registers (no shared-memory reads inside the passes): ~157 registers per lane at CH = 4.
-    // CTAs of 2 warps; 7 per SM (144 registers, a few spills on the load path) keep a single 100-layer x 7,700-column
-    // atmosphere at 4 rounds of 14 columns per SM, 6 per SM (168 registers, no spills) would need 5.
-#define NI_ARGS ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s, g, ncol
-    if constexpr (CH >= 4) {
-        static const int minb = tune_int("HELIOS_NONISO_MINB", 7);
-        if (minb == 6) return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 6>(NI_ARGS);
-        if (minb == 8) return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 8>(NI_ARGS);
-        return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 7>(NI_ARGS);
-    } else {
-        return launch_sweep_noniso_cfg<CH, NOBEAM, 2, 8>(NI_ARGS);
-    }
-#undef NI_ARGS
+    // All step constants live in registers (~156 per lane at CH = 4).  The register file is split four ways (16 K
+    // registers per scheduler), so the occupancy points are 12 warps per SM at <= 168 registers and 16 at <= 128; 128
+    // spills inside the passes and was measured slower.  CTAs of 4 warps (4 columns = one 32-byte sector per flux row).
+    constexpr int WARPS = 4;
+    constexpr int MINB = (CH >= 4) ? 3 : 4;
+    auto kern = k_sweep_noniso<CH, NOBEAM, WARPS, MINB>;
+    using CS = CtaShape<CH, NOBEAM ? 8 : 12, 2, 2 * CH + 1, 5, 1, WARPS>;
+    const size_t smem = (size_t)CS::cta_doubles(g.rs) * sizeof(double);
+    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total = (long long)((ncol + WARPS - 1) / WARPS) * s.nbatch;
+    const int grid = resident_grid(ctx, kern, WARPS * 32, smem, total);
+    kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);
+    HLAUNCHED(ctx);
+    return HELIOS_OK;
 }
 
 }  // namespace
@@ -962,12 +978,12 @@ int plan2_iso_build(helios_ctx* ctx, double* plan, const double* F_dir, const do
     if (!iso_geom(nlay, ncol, nobeam, g)) return -1;
     BuildScalars s{g_0, mu_star, epsi, 0.0, i2s, nint, nbin, ny, clouds, scat_corr, nobeam ? 1 : 0, g.nch, g.rs,
                    ctx->batch.nbatch};
-    const int tpb = ISO_TC / g.cpw;
+    const int tpb = iso_tc(g.LPC) / g.cpw;
     const size_t smem = (size_t)tpb * g.pb * sizeof(double);
     const long long nblk = (long long)((g.ntw + tpb - 1) / tpb) * s.nbatch;
 #define X(CH_, LPC_)                                                                                              \
     {                                                                                                             \
-        auto kern = k_plan_build_iso<CH_, LPC_, ISO_TC>;                                                          \
+        auto kern = k_plan_build_iso<CH_, LPC_, iso_tc(LPC_)>;                                                       \
         HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
         const int grid = resident_grid(ctx, kern, 256, smem, nblk);                                               \
         kern<<<grid, 256, smem, ctx->stream>>>(plan, F_dir, w_0, M, N, P, Gp, Gm, albedo, g0tot, s);               \
@@ -990,13 +1006,10 @@ int plan2_iso_sweep(helios_ctx* ctx, double* F_down, double* F_up, const double*
     if (!iso_geom(nlay, ncol, nobeam, g)) return -1;
     PlanScalars s{Rstar, a, f_factor, nint, nbin, ny, dir_beam, npass, g.nch, g.rs, ctx->batch.nbatch,
                   ctx->batch.active ? ctx->batch.done : nullptr};
-    const bool hoist = npass >= 8;  // one extra scan per tile buys B-only scans in every pass
-#define X(CH_, LPC_)                                                                                                   \
-    {                                                                                                                  \
-        if (nobeam) return hoist ? launch_sweep_iso<CH_, LPC_, true, true>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g)   \
-                                 : launch_sweep_iso<CH_, LPC_, true, false>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g); \
-        return hoist ? launch_sweep_iso<CH_, LPC_, false, true>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g)              \
-                     : launch_sweep_iso<CH_, LPC_, false, false>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g);            \
+#define X(CH_, LPC_)                                                                                             \
+    {                                                                                                            \
+        if (nobeam) return launch_sweep_iso<CH_, LPC_, true>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g);  \
+        return launch_sweep_iso<CH_, LPC_, false>(ctx, F_down, F_up, planck_lay, plan, albedo, s, g);             \
     }
     ISO_SHAPES(X)
 #undef X

@@ -14,8 +14,8 @@ import json,sys
 d=json.load(open('gpurun_out/bench_${w}_$tag.json'))
 print('$w', 'ms/step', d['ms_per_step'], 'kernel_ms', d['roofline']['kernel_ms'], 'frac', round(d['roofline']['frac'],3), 'e2e ms', d['e2e']['ms_per_step'], d['e2e'].get('ms_per_step_with_rebuild'))"
 done
-for mb in 6 8; do
-  HELIOS_NONISO_MINB=$mb timeout 300 python bench.py --workload C2 $B > gpurun_out/bench_C2_minb${mb}_$tag.json 2> gpurun_out/bench_C2_minb${mb}_$tag.err
+for mb in 8; do
+  HELIOS_NONISO_CFG=$mb timeout 300 python bench.py --workload C2 $B > gpurun_out/bench_C2_minb${mb}_$tag.json 2> gpurun_out/bench_C2_minb${mb}_$tag.err
   python -c "
 import json
 d=json.load(open('gpurun_out/bench_C2_minb${mb}_$tag.json'))
