@@ -1,5 +1,5 @@
-// Planned two-stream sweeps (round 2): one warp owns a column (or a pair of columns), everything it needs for its NEXT
-// tile is staged into warp-private shared memory while it sweeps the current one, and the passes run from registers.
+// Planned two-stream sweeps (round 2): one warp owns a column (or a pair of columns), everything a CTA needs for its NEXT
+// tile is staged into shared memory while it sweeps the current one, and the passes run from registers.
 //
 // Why a plan.  Between two opacity refreshes (10 RT iterations, C:860) only the Planck terms change.  The sweep of
 // K:1366-1799 is, per (half-)layer, the affine step
@@ -15,19 +15,20 @@
 // Plan layout = the shared-memory image of a warp's tile.  A warp tile is CPW = 32/LPC columns; lane = (column, chunk of
 // CH layers).  Its block is NR*CH rows of RL = CPW*RS doubles (RS = active lanes per column, rounded to even; a lane's
 // element sits at column*RS + chunk), row (k*NR + j) = constant j of the lane's k-th layer, followed by 4 doubles of
-// per-column surface constants.  The block is contiguous in HBM, so ONE cp.async.bulk (TMA, SASS UBLKCP) per tile brings
-// it in, completion on a warp-private mbarrier; the previous upward fluxes and the Planck values of the tile come by
-// 8-byte cp.async (LDGSTS) into rows of the same shape.  The copies for tile n+1 are issued as soon as tile n has been
-// lifted into registers, so the memory round trip overlaps the ~thousands of cycles of dependent sweep arithmetic:
-// no block barrier anywhere, warps of a CTA drift freely.
+// per-column surface constants.  The block is contiguous in HBM, so ONE cp.async.bulk (TMA, SASS UBLKCP) per warp and tile
+// brings it in, completion on a warp-private mbarrier.  The flux arrays keep the reference's [interface][column] layout
+// (K:1076) -- one 8-byte piece per cache line for a lane that owns a column -- so the CTA (4 warps = 4 or 8 adjacent
+// columns) moves them cooperatively, lanes along the columns, full 32 / 64-byte sectors, through a staged block in shared
+// memory (see CtaShape).  The copies for tile n+1 are issued as soon as tile n has been lifted into registers, so the memory
+// round trip overlaps the dependent sweep arithmetic.
 //
-// The passes (phase B of k_fband_wp, operation for operation): every lane composes the affine map of its chunk, a
-// Kogge-Stone shuffle scan over the lanes of the column hands it the flux entering the chunk, the lane walks its layers.
-// Cells outside the column are identity steps BY DATA (a = 1, b = 0, s = 0: 1*F + 0 == F exactly), so there is no
-// "inside" select.  The reference's tiny-value clean-up (fabs(f) < 1e-100 ? fabs(f) : f, K:1453) costs 18 of the 26 cycles
-// of a dependent walk step, yet it changes a value only when the sign bit is set and |f| < 1e-100: the walk runs
-// WITHOUT it, tests the high word of every result with integer instructions off the critical path, and only if any lane
-// saw such a value (warp vote) redoes the walk with the exact clean-up -- bit-identical results, 8-cycle steps.
+// The passes (phase B of k_fband_wp): every lane composes the affine map of its chunk, a Kogge-Stone shuffle scan over
+// the lanes of the column hands it the flux entering the chunk, the lane walks its layers.  Cells outside the column are
+// identity steps BY DATA (a = 1, b = 0, s = 0: 1*F + 0 == F exactly), so there is no "inside" select.  The A parts of the
+// scans are pass-invariant and hoisted (scan_setup); the reference's tiny-value clean-up is replaced by a sign-bit vote
+// per tile with an exact redo (clean<>).  Measured on B200: the first build of this file, one warp per
+// column with per-lane 8-byte copies, spent 16 of its 46 us per C2 solve in the flux stores and 8 us in the flux loads
+// (25 wavefronts per LSU instruction); the cooperative staging brought the solve to 44 us.
 #include "common.cuh"
 #include "sweep_math.cuh"
 #include "fband_plan.cuh"
@@ -74,12 +75,6 @@ __device__ __forceinline__ void cp_async8(unsigned dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// would tiny_to_abs change f?  (sign bit set and |f| < 1e-100, or f == -0.0.)  Conservative on the low word: the exact
-// test decides in the slow path.  1e-100 = 0x2B2BFF2EE48E0530.
-__device__ __forceinline__ bool cleanup_candidate(double f) {
-    return ((unsigned)__double2hiint(f) ^ 0x80000000u) <= 0x2B2BFF2Eu;
-}
 
 // ---------------------------------------------------------------- the passes -------------------
 // Scans.  The A parts of the affine maps (products of the a's of a chunk) do not depend on the fluxes, so everything the
@@ -909,11 +904,6 @@ int resident_grid(helios_ctx* ctx, K kern, int threads, size_t smem, long long w
     }
     const long long cap = (long long)ctx->num_sms * per_sm;
     return (int)(work_ctas < cap ? work_ctas : cap);
-}
-
-int tune_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e != nullptr ? atoi(e) : dflt;
 }
 
 template <int CH, int LPC, bool NOBEAM>
