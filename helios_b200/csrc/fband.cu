@@ -509,26 +509,7 @@ int fband_noniso_cp_try(helios_ctx* ctx, double* F_down, double* F_up, double* F
                         const double* g0_int, double g_0, double Rstar, double a, int nint, int nbin,
                         double f_factor, double mu_star, int ny, double epsi, double delta_tau_limit,
                         int dir_beam, int clouds, int scat_corr, double i2s, int npass);
-int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
-                     const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
-                     double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
-                     double i2s);
-size_t fband_plan_size(int nint, int ncol, int nbatch);
-int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
-                         const double* plan, const double* planck_lay, const double* planck_int,
-                         const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
-                         int dir_beam, int npass);
 
-
-// HELIOS_PLAN_V1=1: the round-1 planned sweep (k_plan_build + k_fband_lane of fband_cp.cu) instead of fband_plan.cu --
-// kept for A/B measurements only
-static bool plan_v1() {
-    static const bool v = [] {
-        const char* e = getenv("HELIOS_PLAN_V1");
-        return e != nullptr && e[0] == '1';
-    }();
-    return v;
-}
 
 static int fband_grid(helios_ctx* ctx, int ncol) {
     const int ntile = (ncol + FB_THREADS - 1) / FB_THREADS;
@@ -656,23 +637,14 @@ int helios_fband_noniso_plan_build(
     HARG(clouds == 0 || (g_0_tot_lay != nullptr && g_0_tot_int != nullptr));
     HARG(numinterfaces > 1 && nbin > 0 && ny > 0);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
-    CpNonisoCoef cc{w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
-                    delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
-                    G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
-    int rc;
-    if (plan_v1()) {
-        rc = fband_plan_build(ctx, plan, F_dir_wg, Fc_dir_wg, cc, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0, mu_star, epsi,
-                              delta_tau_limit, numinterfaces, nbin, ny, clouds == 1, scat_corr == 1, i2s_transition);
-    } else {
-        const double* coef[16] = {w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
-                                  delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
-                                  G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
-        // dir_beam is not an argument of this entry point: the beam rows are dropped only when both beam arrays are
-        // known to hold zeros (fdir_noniso ran with dir_beam == 0 and nothing wrote to them since)
-        rc = plan2_noniso_build(ctx, plan, F_dir_wg, Fc_dir_wg, coef, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0, mu_star,
-                                epsi, delta_tau_limit, numinterfaces, nbin, ny, 0, clouds == 1, scat_corr == 1,
-                                i2s_transition);
-    }
+    const double* coef[16] = {w_0_upper, w_0_lower, delta_tau_wg_upper, delta_tau_wg_lower, delta_tau_all_clouds_upper,
+                              delta_tau_all_clouds_lower, M_upper, M_lower, N_upper, N_lower, P_upper, P_lower,
+                              G_plus_upper, G_plus_lower, G_minus_upper, G_minus_lower};
+    // dir_beam is not an argument of this entry point: the beam rows are dropped only when both beam arrays are
+    // known to hold zeros (fdir_noniso ran with dir_beam == 0 and nothing wrote to them since)
+    const int rc = plan2_noniso_build(ctx, plan, F_dir_wg, Fc_dir_wg, coef, surf_albedo, g_0_tot_lay, g_0_tot_int, g_0,
+                                      mu_star, epsi, delta_tau_limit, numinterfaces, nbin, ny, 0, clouds == 1,
+                                      scat_corr == 1, i2s_transition);
     if (rc < 0) {
         helios_set_error("helios_fband_noniso_plan_build: more than 128 layers are not supported by the planned sweep");
         return HELIOS_ERR_ARG;
@@ -683,9 +655,7 @@ int helios_fband_noniso_plan_build(
 int helios_fband_noniso_plan_size(helios_ctx* ctx, int numinterfaces, int nbin, int ny, size_t* ndoubles) {
     HCTX(ctx);
     HARG(ndoubles != nullptr && numinterfaces > 1 && nbin > 0 && ny > 0);
-    const size_t v1 = fband_plan_size(numinterfaces, nbin * ny, ctx->batch.nbatch);
-    const size_t v2 = plan2_noniso_size(numinterfaces, nbin * ny, ctx->batch.nbatch);
-    *ndoubles = plan_v1() ? (v1 > v2 ? v1 : v2) : v2;
+    *ndoubles = plan2_noniso_size(numinterfaces, nbin * ny, ctx->batch.nbatch);
     return HELIOS_OK;
 }
 
@@ -697,12 +667,8 @@ int helios_fband_noniso_planned(helios_ctx* ctx, double* F_down_wg, double* F_up
     HARG(F_down_wg && F_up_wg && Fc_down_wg && Fc_up_wg && plan && planckband_lay && planckband_int && surf_albedo);
     HARG(numinterfaces > 1 && nbin > 0 && ny > 0 && npass > 0);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
-    const int rc = plan_v1() ? fband_noniso_planned(ctx, F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, plan, planckband_lay,
-                                                    planckband_int, surf_albedo, Rstar, a, numinterfaces, nbin, f_factor,
-                                                    ny, dir_beam, npass)
-                             : plan2_noniso_sweep(ctx, F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, plan, planckband_lay,
-                                                  planckband_int, surf_albedo, Rstar, a, numinterfaces, nbin, f_factor, ny,
-                                                  dir_beam, npass);
+    const int rc = plan2_noniso_sweep(ctx, F_down_wg, F_up_wg, Fc_down_wg, Fc_up_wg, plan, planckband_lay, planckband_int,
+                                      surf_albedo, Rstar, a, numinterfaces, nbin, f_factor, ny, dir_beam, npass);
     if (rc == -2) {
         helios_set_error("helios_fband_noniso_planned: `plan` was not built by helios_fband_noniso_plan_build for this shape "
                          "(or was overwritten since)");

@@ -20,10 +20,9 @@
 //     handed over by shuffle).  The passes are branch-free (cells outside the column are identity steps) and
 //     store nothing; the fluxes of the last pass are stored from the registers afterwards.
 //
-//   Non-isothermal layers between two opacity refreshes take the PLANNED form further down (k_plan_build +
-//   k_fband_lane): the Planck-independent part of the step constants is formed once per refresh and stored in
-//   the order the sweep lanes consume it, so the sweep has no phase A at all -- one warp per column, loads by
-//   cp.async into thread-private shared-memory rows, then the same passes.
+//   Between two opacity refreshes the PLANNED sweeps of fband_plan.cu take over: the Planck-independent part of the
+//   step constants is formed once per refresh and stored in the order the sweep lanes consume it, so the sweep has no
+//   phase A at all.  This file remains the unplanned form (any call without a plan, > 128 / 256 layers).
 //
 // Arithmetic: a F - b F_opp + s is the reference's 1/M (P F - N F_opp + ...) with the division by M
 // distributed, and the chunk-entry flux comes from composed maps: both reorder a few multiply-adds.
@@ -38,11 +37,6 @@
 #ifndef ISO_NCOLS
 #define ISO_NCOLS 8  // columns per tile of the isothermal sweep at 81..112 layers: 128-thread CTAs, 4 per SM (measured
                      // 1-2 % faster than 16 columns / 256 threads / 2 per SM: more CTAs in different phases overlap better)
-#endif
-#ifndef PLAN_NCOLS
-#define PLAN_NCOLS 4  // columns per tile of the planned sweep: 128-thread CTAs, 4 per SM; a single C2 atmosphere is
-                      // 1925 tiles on 592 CTA slots instead of 963 on 296 -- the same 3.25 waves but half as long a tail
-                      // (measured 65.1 -> 61.9 us)
 #endif
 
 struct CpScalars {
@@ -116,129 +110,6 @@ __device__ __forceinline__ void beam_pair(double Fa, double Fb, double neg_mu, d
     if (Fa != 0.0 || Fb != 0.0) {
         Dd = beam_source(Fa, Fb, neg_mu, M, G_min, N, G_pl, m1d, m2d);
         Du = beam_source(Fb, Fa, neg_mu, N, G_min, M, G_pl, P, G_pl);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Sweep plan (non-isothermal layers).  Between two opacity refreshes (10 RT iterations, C:860) only the Planck
-// terms change; everything else phase A derives from the coefficient arrays -- 1/M, P/M, N/M, the source factor,
-// the gradient factor, the direct-beam sources with their four divisions -- is the same every iteration.  The
-// source terms are affine in the Planck values of a half-layer,
-//      s = k0 + k1 * B_layer + k2 * B_interface,
-// so k_plan_build evaluates, once per refresh and with the same building blocks as phase A, the 8 constants
-// [a, b, k0d, k1d, k2d, k0u, k1u, k2u] of every half-layer; the planned sweep (k_fband_lane) then reads 16 + 2 values
-// per cell instead of 24 and does 8 multiply-adds instead of ~650 instructions with 12 divisions.  Per column the plan
-// also carries the surface constants (emission factor of K:1704, direct beam at BOA).  Rounding differs from the
-// reference's operation
-// order by a few ulp of the source terms (measured against the unplanned kernel: <= 1e-13 on the fluxes).
-// ------------------------------------------------------------------------------------------------
-struct PlanHalf {
-    double a, b, k0d, k1d, k2d, k0u, k1u, k2u;
-};
-
-// lay_first: the half-layer's "B1" of the downward form is the layer value (upper half) or the interface (lower)
-__device__ __forceinline__ PlanHalf plan_half(double w0, double M, double N, double P, double Gp, double Gm, double dt,
-                                              double g0, double Fa_d, double Fb_d, double m1d, double m2d,
-                                              bool upper, double neg_mu, const CpScalars& s, double& E_out) {
-    const double E = s.scat_corr ? E_parameter(w0, g0, s.i2s_transition) : 1.0;
-    E_out = E;
-    const double invM = 1.0 / M;
-    const double fac = source_factor(s.epsi, w0, E);
-    double Dd, Du;
-    beam_pair(Fa_d, Fb_d, neg_mu, M, N, P, Gp, Gm, m1d, m2d, Dd, Du);
-    double lay_d, int_d, lay_u, int_u;  // coefficients of B_layer / B_interface in the Planck terms
-    if (dt < s.delta_tau_limit) {
-        lay_d = int_d = lay_u = int_u = 0.5 * ((M + N) - P);
-    } else {
-        const double pre = gradient_factor(s.epsi, w0, g0, E);
-        const double cd = (N + (P - M)) * pre / dt;
-        const double cu = ((M - P) - N) * pre / dt;
-        if (upper) {  // down: B1 = layer, B2 = interface above; up: B1 = interface above, B2 = layer
-            lay_d = (M + N) + cd;  int_d = -P - cd;
-            lay_u = cu - P;        int_u = (M + N) - cu;
-        } else {      // down: B1 = interface below, B2 = layer; up: B1 = layer, B2 = interface below
-            lay_d = -P - cd;       int_d = (M + N) + cd;
-            lay_u = (M + N) - cu;  int_u = cu - P;
-        }
-    }
-    PlanHalf h;
-    h.a = invM * P;
-    h.b = invM * N;
-    const double f = invM * fac;
-    h.k0d = invM * Dd;  h.k1d = f * lay_d;  h.k2d = f * int_d;
-    h.k0u = invM * Du;  h.k1u = f * lay_u;  h.k2u = f * int_u;
-    return h;
-}
-
-// Plan layout.  The plan is private to k_plan_build and k_fband_lane, so it is stored in exactly the order the sweep
-// lanes consume it: a tile is NCOLS columns, sweep thread t = column * LPC + chunk owns layers chunk * CH + k
-// (k = 0..CH-1), and the 16 constants of its slot-k layer are 8 double2 values at
-//      plan2[((tile * CH + k) * 8 + j) * THREADS + t],   j = 0..7,
-// i.e. every warp-level load is one contiguous 512-byte run (the coefficient arrays themselves can only be read
-// as 64-byte row segments by an 8-column tile, which caps at 2.3 TB/s on B200: scripts/stream_bench.cu).
-// Behind the tiles: per (tile, column) the two surface constants (emission factor of K:1704, direct beam at BOA).
-template <int CH, int LPC, int NCOLS>
-__host__ __device__ inline size_t plan_cells_doubles(size_t ntiles_total) {
-    return ntiles_total * CH * 16 * (size_t)(NCOLS * LPC);
-}
-
-template <int CH, int LPC, int NCOLS>
-__global__ void __launch_bounds__(NCOLS * LPC)
-k_plan_build(double* __restrict__ plan, const double* __restrict__ F_dir, const double* __restrict__ Fc_dir,
-             CpNonisoCoef cfg, const double* __restrict__ albedo, const double* __restrict__ g0_lay,
-             const double* __restrict__ g0_int, CpScalars s) {
-    constexpr int THREADS = NCOLS * LPC;
-    const int nint = s.nint, nlay = nint - 1, ncol = s.nbin * s.ny;
-    const int ntile = (ncol + NCOLS - 1) / NCOLS;
-    const double neg_mu = -s.mu_star;
-    double2* __restrict__ plan2 = reinterpret_cast<double2*>(plan);
-    double* __restrict__ extras = plan + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
-    const int c = threadIdx.x % NCOLS;
-    const int r = threadIdx.x / NCOLS;
-    for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
-        const int atm = gtile / ntile;
-        const int tile = gtile - atm * ntile;
-        const int col = min(tile * NCOLS + c, ncol - 1);
-        const int x = col / s.ny;
-#pragma unroll
-        for (int m = 0; m < CH; m++) {
-            const int i = r + LPC * m;
-            if (i >= nlay) continue;
-            const size_t e = (size_t)atm * ncol * nint + col + (size_t)ncol * i;
-            const size_t bl = (size_t)atm * s.nbin * nlay + (size_t)x + (size_t)s.nbin * i;
-            const size_t bi = (size_t)atm * s.nbin * nint + (size_t)x + (size_t)s.nbin * i;
-            double g0_up = s.g_0, g0_low = s.g_0;
-            if (s.clouds) {
-                const double gl = g0_lay[bl];
-                g0_up = (gl + g0_int[bi + s.nbin]) / 2.0;
-                g0_low = (g0_int[bi] + gl) / 2.0;
-            }
-            const double Fdir_i = F_dir[e], Fdir_ip1 = F_dir[e + ncol], Fcdir = Fc_dir[e];
-            double E_u, E_l;
-            const double P_u = cfg.P_u[e], Gm_u = cfg.Gm_u[e];
-            const PlanHalf u = plan_half(cfg.w0_u[e], cfg.M_u[e], cfg.N_u[e], P_u, cfg.Gp_u[e], Gm_u,
-                                         cfg.dtau_u[e] + cfg.dtc_u[bl], g0_up, Fcdir, Fdir_ip1, Gm_u, P_u, true, neg_mu, s, E_u);
-            const double w0_l = cfg.w0_l[e], P_l = cfg.P_l[e], Gm_l = cfg.Gm_l[e];
-            const PlanHalf l = plan_half(w0_l, cfg.M_l[e], cfg.N_l[e], P_l, cfg.Gp_l[e], Gm_l,
-                                         cfg.dtau_l[e] + cfg.dtc_l[bl], g0_low, Fdir_i, Fcdir, P_l, Gm_l, false, neg_mu, s, E_l);
-            // lane order: the cell of layer i, column c belongs to sweep thread c * LPC + i / CH, slot i % CH
-            double2* __restrict__ p = plan2 + ((size_t)gtile * CH + (i % CH)) * 8 * THREADS + (c * LPC + i / CH);
-            p[0] = make_double2(u.a, u.b);
-            p[THREADS] = make_double2(u.k0d, u.k1d);
-            p[2 * THREADS] = make_double2(u.k2d, u.k0u);
-            p[3 * THREADS] = make_double2(u.k1u, u.k2u);
-            p[4 * THREADS] = make_double2(l.a, l.b);
-            p[5 * THREADS] = make_double2(l.k0d, l.k1d);
-            p[6 * THREADS] = make_double2(l.k2d, l.k0u);
-            p[7 * THREADS] = make_double2(l.k1u, l.k2u);
-            if (i == 0) {  // surface constants (K:1704: w0 and E of layer 0's lower half)
-                const double A_s = albedo[x];
-                double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + c) * 2;
-                ex[0] = __ddiv_rn(__dmul_rn(__dmul_rn(__dsub_rn(1.0, A_s), 3.141592653589793), __dsub_rn(1.0, w0_l)),
-                                  __dsub_rn(E_l, w0_l));
-                ex[1] = Fdir_i;
-            }
-        }
     }
 }
 
@@ -621,207 +492,6 @@ k_fband_wp(double* __restrict__ F_down, double* __restrict__ F_up, double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Planned sweep, lane-ordered plan.  The plan is private to k_plan_build and this kernel, so it is stored
-// per SWEEP LANE: thread t = column * LPC + chunk of a tile finds the 16 constants of its slot-k layer as 8 double2 at
-//      plan2[((tile * CH + k) * 8 + j) * THREADS + t],   j = 0..7
-// (512 contiguous bytes per warp and load).  Each lane derives the source terms of its own CH layers from the Planck
-// values, parks them in its private shared-memory slots and runs the chunk-parallel sweeps of k_fband_wp's phase B:
-// there is no phase A, no transposition through shared memory and no block-wide barrier -- a warp is one column and
-// the warps of a CTA drift freely, loads of one overlapping the shuffle scans of another.  The sweep arithmetic is
-// phase B of k_fband_wp operation for operation (an earlier build that staged the plan through phase A and shared
-// memory gave bit-identical fluxes at 62 us per C2 solve; this form takes 56 us).
-// ------------------------------------------------------------------------------------------------
-template <int CH, int LPC, int NCOLS, bool FULL>
-__global__ void __launch_bounds__(NCOLS * LPC, (NCOLS * LPC <= 128) ? 4 : 2)
-k_fband_lane(double* __restrict__ F_down, double* __restrict__ F_up, double* __restrict__ Fc_down,
-             double* __restrict__ Fc_up, const double* __restrict__ planck_lay, const double* __restrict__ planck_int,
-             const double* __restrict__ plan, const double* __restrict__ albedo, CpScalars s) {
-    extern __shared__ double sm[];  // [CH * 6][THREADS] double2, thread-private columns (see the load phase)
-    constexpr int THREADS = NCOLS * LPC;
-    const int nint = s.nint, nlay = nint - 1, nch = s.nchunk;
-    const int ncol = s.nbin * s.ny;
-    const int ntile = (ncol + NCOLS - 1) / NCOLS;
-    const int t = threadIdx.x;
-    const int cw = t / LPC;  // column of this lane segment
-    const int sl = t % LPC;  // chunk index
-    const int lo = sl * CH;
-    const bool act = sl < nch;
-    const int hi = min(lo + CH, nlay);
-    const double2* __restrict__ plan2 = reinterpret_cast<const double2*>(plan);
-    const double* __restrict__ extras = plan + plan_cells_doubles<CH, LPC, NCOLS>((size_t)ntile * s.nbatch);
-    double2* __restrict__ my2 = reinterpret_cast<double2*>(sm) + t;  // my private rows: [CH * 6][THREADS] double2
-    const unsigned my_s = (unsigned)__cvta_generic_to_shared(my2);
-    for (int gtile = blockIdx.x; gtile < ntile * s.nbatch; gtile += gridDim.x) {
-        const int atm = gtile / ntile;
-        const int tile = gtile - atm * ntile;
-        if (s.done != nullptr && s.done[atm] != 0) continue;  // uniform per block
-        const size_t wgo = (size_t)atm * ncol * nint;          // [i][x][y] arrays
-        const int col = tile * NCOLS + cw;
-        const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
-        const int colc = live ? col : ncol - 1;
-        const int x = colc / s.ny;
-        const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
-        const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
-        double a[2][CH], b[2][CH], Fu_reg[CH], Fd_reg[CH], Fcu_reg[CH], Fcd_reg[CH], cc[2][CH];
-        // Load phase.  Everything a tile needs is requested at once, so the lane waits ONE memory round trip per tile
-        // instead of one per slot (registers allow only one slot of plan constants in flight, and with 16 warps per SM
-        // those round trips were 40 % of the stall samples): a, b (they live in registers for all passes anyway) and
-        // the previous upward fluxes go straight to their registers; the 12 Planck-term constants of each slot go
-        // from global to the lane's private shared-memory rows with 16-byte cp.async -- no registers involved.
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const bool in = act && (FULL || lo + k < hi);
-            a[0][k] = a[1][k] = 1.0;  // identity step outside the column
-            b[0][k] = b[1][k] = 0.0;
-            Fu_reg[k] = Fcu_reg[k] = Fd_reg[k] = Fcd_reg[k] = 0.0;
-            if (in) {
-                const double2* __restrict__ p = plan2 + ((size_t)gtile * CH + k) * 8 * THREADS + t;
-                constexpr int JJ[6] = {1, 2, 3, 5, 6, 7};
-#pragma unroll
-                for (int jj = 0; jj < 6; jj++)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(my_s + (unsigned)((k * 6 + jj) * THREADS * 16)),
-                                 "l"(p + JJ[jj] * THREADS)
-                                 : "memory");
-                const double2 u = p[0], l = p[4 * THREADS];
-                a[0][k] = u.x;
-                b[0][k] = u.y;
-                a[1][k] = l.x;
-                b[1][k] = l.y;
-                const size_t e = wgo + colc + (size_t)ncol * (lo + k);
-                Fu_reg[k] = F_up[e];
-                Fcu_reg[k] = Fc_up[e];
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        const double* __restrict__ ex = extras + ((size_t)gtile * NCOLS + cw) * 2;
-        const double A_s = albedo[x], Fdir0 = ex[1], emis = __dmul_rn(ex[0], BL[nlay + 1]);
-        const double toa = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI * BL[nlay];
-        asm volatile("cp.async.wait_group 0;" ::: "memory");  // my own copies have landed (nobody else reads them)
-        // source terms from the Planck values, written over the head of each slot's rows:
-        // row 0 = (sd upper half, sd lower half) for the downward sweep, row 1 = (su upper, su lower) for the upward
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            const bool in = act && (FULL || lo + k < hi);
-            double2 sd = make_double2(0.0, 0.0), su = make_double2(0.0, 0.0);
-            if (in) {
-                const int i = lo + k;
-                const double Blay = BL[i], Bint_lo = BI[i], Bint_hi = BI[i + 1];
-                double2 q[6];
-#pragma unroll
-                for (int jj = 0; jj < 6; jj++) q[jj] = my2[(k * 6 + jj) * THREADS];
-                // q[0] = (k0d, k1d), q[1] = (k2d, k0u), q[2] = (k1u, k2u) of the upper half; q[3..5] of the lower half
-                sd.x = __fma_rn(q[0].y, Blay, __fma_rn(q[1].x, Bint_hi, q[0].x));
-                su.x = __fma_rn(q[2].x, Blay, __fma_rn(q[2].y, Bint_hi, q[1].y));
-                sd.y = __fma_rn(q[3].y, Blay, __fma_rn(q[4].x, Bint_lo, q[3].x));
-                su.y = __fma_rn(q[5].x, Blay, __fma_rn(q[5].y, Bint_lo, q[4].y));
-            }
-            my2[(k * 6 + 0) * THREADS] = sd;
-            my2[(k * 6 + 1) * THREADS] = su;
-        }
-        // One pass = downward sweep + upward sweep.  Branch-free: cells outside the column are identity steps
-        // (a = 1, b = 0, s = 0), so the arithmetic runs unconditionally and only the stores of the LAST pass
-        // (WRITE) are predicated -- for this kernel measured faster than storing from the registers after the last
-        // pass, which is what k_fband_wp does.  FULL (nlay == nchunk * CH): every active lane owns CH real cells and the
-        // per-cell "inside" selects vanish; otherwise the identity cells of the top lane pass the flux through.
-        const bool st_ok = live && act;
-        const size_t off = wgo + colc + (size_t)ncol * lo;
-        auto one_pass = [&](auto write_tag) {
-            constexpr bool WRITE = decltype(write_tag)::value;
-            // ---------------- downward sweep (per layer: upper half, then lower half) ----------------
-            Aff m{1.0, 0.0};
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) {
-                const double2 sd = my2[(k * 6 + 0) * THREADS];
-                cc[0][k] = sd.x - b[0][k] * Fcu_reg[k];
-                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
-                cc[1][k] = sd.y - b[1][k] * Fu_reg[k];
-                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
-            }
-            Aff sc = scan_from_top<LPC>(m, sl, nch);
-            const double Fbot = sc.A * toa + sc.B;                   // flux leaving my chunk (interface lo)
-            double F = __shfl_down_sync(0xffffffffu, Fbot, 1, LPC);  // = flux entering it (interface hi)
-            if (sl >= nch - 1) F = toa;
-            if (WRITE && live && sl == nch - 1) F_down[wgo + colc + (size_t)ncol * nlay] = toa;
-#pragma unroll
-            for (int k = CH - 1; k >= 0; k--) {
-                const bool in = FULL || lo + k < hi;
-                double Fn = tiny_to_abs(a[0][k] * F + cc[0][k]);
-                if (!FULL) Fn = in ? Fn : F;
-                Fcd_reg[k] = Fn;
-                if (WRITE) { if (st_ok && in) Fc_down[off + (size_t)(k * ncol)] = Fn; }
-                double Fm = tiny_to_abs(a[1][k] * Fn + cc[1][k]);
-                if (!FULL) Fm = in ? Fm : F;
-                Fd_reg[k] = Fm;
-                if (WRITE) { if (st_ok && in) F_down[off + (size_t)(k * ncol)] = Fm; }
-                F = Fm;
-            }
-            // the flux at my top interface as WALKED (and stored) by the lane above
-            double Fd_hi = __shfl_down_sync(0xffffffffu, Fd_reg[0], 1, LPC);
-            if (sl >= nch - 1) Fd_hi = toa;
-            // ---------------- upward sweep (per layer: lower half, then upper half) ----------------
-            double fu0 = __fma_rn(A_s, __dadd_rn(Fdir0, Fd_reg[0]), emis);  // surface, valid in lane 0 (K:1469-1474)
-            fu0 = __shfl_sync(0xffffffffu, fu0, 0, LPC);
-            m = Aff{1.0, 0.0};
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                // identity cells above the column carry the entering flux (toa) unchanged, so no "inside" test
-                const double Fd_top = (k + 1 < CH) ? Fd_reg[(k + 1) % CH] : Fd_hi;
-                const double2 su = my2[(k * 6 + 1) * THREADS];
-                cc[1][k] = su.y - b[1][k] * Fcd_reg[k];
-                m = Aff{a[1][k] * m.A, a[1][k] * m.B + cc[1][k]};
-                cc[0][k] = su.x - b[0][k] * Fd_top;
-                m = Aff{a[0][k] * m.A, a[0][k] * m.B + cc[0][k]};
-            }
-            sc = scan_from_bottom<LPC>(m, sl);
-            const double Ftop = sc.A * fu0 + sc.B;          // flux leaving my chunk (interface hi)
-            F = __shfl_up_sync(0xffffffffu, Ftop, 1, LPC);  // = flux entering it (interface lo)
-            if (sl == 0) F = fu0;
-            if (WRITE && live && sl == 0) F_up[wgo + colc] = fu0;
-#pragma unroll
-            for (int k = 0; k < CH; k++) {
-                const bool in = FULL || lo + k < hi;
-                Fu_reg[k] = F;  // interface lo+k: what the next pass's downward sweep reads
-                // no tiny-value clean-up on Fc_up: the reference applies it to index i, not i-1 (K:1763)
-                double Fn = a[1][k] * F + cc[1][k];
-                if (!FULL) Fn = in ? Fn : F;
-                Fcu_reg[k] = Fn;
-                if (WRITE) { if (st_ok && in) Fc_up[off + (size_t)(k * ncol)] = Fn; }
-                double Fm = tiny_to_abs(a[0][k] * Fn + cc[0][k]);
-                if (!FULL) Fm = in ? Fm : F;
-                if (WRITE) { if (st_ok && in) F_up[off + (size_t)((k + 1) * ncol)] = Fm; }
-                F = Fm;
-            }
-            // next pass: the flux at my bottom interface as walked by the lane below
-            const double Fu_lo = __shfl_up_sync(0xffffffffu, F, 1, LPC);
-            Fu_reg[0] = (sl == 0) ? fu0 : Fu_lo;
-        };
-        for (int pass = 0; pass + 1 < s.npass; pass++) one_pass(std::false_type{});
-        one_pass(std::true_type{});  // only the last pass writes the flux arrays
-    }
-}
-
-template <int CH, int LPC, int NCOLS>
-static int launch_lane(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
-                       const double* planck_lay, const double* planck_int, const double* plan, const double* albedo,
-                       CpScalars s, int ncol) {
-    const int nlay = s.nint - 1;
-    s.nchunk = (nlay + CH - 1) / CH;
-    if (s.nchunk > LPC) return -1;
-    constexpr int THREADS = NCOLS * LPC;
-    const size_t smem = (size_t)CH * 6 * THREADS * sizeof(double2);
-    const int ntile = (ncol + NCOLS - 1) / NCOLS * ctx->batch.nbatch;
-    s.nbatch = ctx->batch.nbatch;
-    s.done = ctx->batch.active ? ctx->batch.done : nullptr;
-    const int per_sm = (THREADS <= 128) ? 4 : 2;  // __launch_bounds__
-    const int grid = ntile < ctx->num_sms * per_sm ? ntile : ctx->num_sms * per_sm;
-    auto kern = (nlay == s.nchunk * CH) ? k_fband_lane<CH, LPC, NCOLS, true> : k_fband_lane<CH, LPC, NCOLS, false>;
-    HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, THREADS, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
-}
-
-// ------------------------------------------------------------------------------------------------
 // launch planning: LPC = 16 lanes per column (two columns per warp) while nlay <= 128, else 32
 // ------------------------------------------------------------------------------------------------
 template <bool NONISO, int CH, int LPC, int NCOLS>
@@ -885,79 +555,6 @@ static int dispatch_wp(helios_ctx* ctx, double* F_down, double* F_up, double* Fc
     }
 #undef WP_ARGS
     return -1;
-}
-
-// planned non-isothermal sweep: one warp per column, CH = ceil(nlay / 32) layers per lane
-static int dispatch_wp_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
-                               const double* planck_lay, const double* planck_int, CpNonisoCoef c,
-                               const double* albedo, CpScalars s, int ncol) {
-    const int nlay = s.nint - 1;
-#define LN_ARGS ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, c.w0_u, albedo, s, ncol
-    if (nlay <= 32) return launch_lane<1, 32, PLAN_NCOLS>(LN_ARGS);
-    if (nlay <= 64) return launch_lane<2, 32, PLAN_NCOLS>(LN_ARGS);
-    if (nlay <= 96) return launch_lane<3, 32, PLAN_NCOLS>(LN_ARGS);
-    if (nlay <= 128) return launch_lane<4, 32, PLAN_NCOLS>(LN_ARGS);
-#undef LN_ARGS
-    return -1;
-}
-
-template <int CH, int LPC, int NCOLS>
-static size_t plan_doubles(int ncol, int nbatch) {
-    const size_t ntiles = (size_t)((ncol + NCOLS - 1) / NCOLS) * nbatch;
-    return plan_cells_doubles<CH, LPC, NCOLS>(ntiles) + ntiles * NCOLS * 2;
-}
-
-// number of doubles a plan needs (0: more than 128 layers, not supported by the planned sweep)
-size_t fband_plan_size(int nint, int ncol, int nbatch) {
-    const int nlay = nint - 1;
-    if (nlay <= 32) return plan_doubles<1, 32, PLAN_NCOLS>(ncol, nbatch);
-    if (nlay <= 64) return plan_doubles<2, 32, PLAN_NCOLS>(ncol, nbatch);
-    if (nlay <= 96) return plan_doubles<3, 32, PLAN_NCOLS>(ncol, nbatch);
-    if (nlay <= 128) return plan_doubles<4, 32, PLAN_NCOLS>(ncol, nbatch);
-    return 0;
-}
-
-template <int CH, int LPC, int NCOLS>
-static int launch_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
-                             const double* albedo, const double* g0_lay, const double* g0_int, CpScalars s) {
-    const int ntile = (s.nbin * s.ny + NCOLS - 1) / NCOLS * s.nbatch;
-    // as many resident CTAs as the register file allows (the kernel strides over the tiles): 3 of 256 threads, 5 of 128
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_plan_build<CH, LPC, NCOLS>, NCOLS * LPC, 0) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = 3;
-    }
-    const int cap = ctx->num_sms * per_sm;
-    k_plan_build<CH, LPC, NCOLS><<<ntile < cap ? ntile : cap, NCOLS * LPC, 0, ctx->stream>>>(plan, F_dir, Fc_dir, c, albedo,
-                                                                                         g0_lay, g0_int, s);
-    HLAUNCHED(ctx);
-    return HELIOS_OK;
-}
-
-int fband_plan_build(helios_ctx* ctx, double* plan, const double* F_dir, const double* Fc_dir, CpNonisoCoef c,
-                     const double* albedo, const double* g0_lay, const double* g0_int, double g_0, double mu_star,
-                     double epsi, double delta_tau_limit, int nint, int nbin, int ny, int clouds, int scat_corr,
-                     double i2s) {
-    CpScalars s{g_0, 0.0, 0.0, 0.0, mu_star, epsi, delta_tau_limit, i2s, nint, nbin, ny, 0, clouds, scat_corr, 1, 0, 0,
-                0, 0, ctx->batch.nbatch, nullptr};
-    const int nlay = nint - 1;
-    // the plan is laid out for the tile shape the planned sweep uses at this layer count (dispatch_wp_planned)
-    if (nlay <= 32) return launch_plan_build<1, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 64) return launch_plan_build<2, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 96) return launch_plan_build<3, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    if (nlay <= 128) return launch_plan_build<4, 32, PLAN_NCOLS>(ctx, plan, F_dir, Fc_dir, c, albedo, g0_lay, g0_int, s);
-    return -1;
-}
-
-int fband_noniso_planned(helios_ctx* ctx, double* F_down, double* F_up, double* Fc_down, double* Fc_up,
-                         const double* plan, const double* planck_lay, const double* planck_int,
-                         const double* albedo, double Rstar, double a, int nint, int nbin, double f_factor, int ny,
-                         int dir_beam, int npass) {
-    CpScalars s{0.0, Rstar, a, f_factor, 0.0, 0.0, 0.0, 0.0, nint, nbin, ny, dir_beam, 0, 0, npass, 0, 0, 0, 0, 1, nullptr};
-    CpNonisoCoef c{plan, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                   nullptr, nullptr, nullptr, nullptr, nullptr};
-    return dispatch_wp_planned(ctx, F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, c, albedo, s, nbin * ny);
 }
 
 // return HELIOS_OK when launched, -1 when the shape does not fit this scheme (the caller then falls back to
