@@ -8,32 +8,7 @@
 // ends up with bitwise-identical totals (fixed summation order), so the replicated temperature update
 // cannot drift between ranks.  The reference has no counterpart (single GPU).
 #include "common.cuh"
-
-#define COMM_MAX_WORLD 16
-
-struct helios_comm_state {
-    int rank = 0, world = 1, slot = 0;
-    unsigned long long seq = 0;
-    // own mailbox: [2 banks][world][slot] doubles, then [world] flags (u64), flags padded to 128 B
-    void* own = nullptr;
-    void* peers[COMM_MAX_WORLD] = {nullptr};
-    bool opened[COMM_MAX_WORLD] = {false};
-    void** peers_dev = nullptr;
-    size_t data_bytes = 0;
-};
-
-struct CommPeers {
-    void* p[COMM_MAX_WORLD];
-};
-
-__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
+#include "comm.cuh"
 
 // vec_a[0..n) and (optionally) vec_b[0..n) are reduced in one exchange; `net` (optional) receives a - b.
 __global__ void __launch_bounds__(256)
@@ -104,7 +79,47 @@ static int comm_launch(helios_ctx* ctx, const char* who, double* a, double* b, d
     return HELIOS_OK;
 }
 
+int helios_comm_fused_next(helios_ctx* ctx, int n, FusedComm* fc) {
+    helios_comm_state* c = ctx->comm;
+    if (!c || !c->fused) {
+        fc->world = 0;
+        return HELIOS_OK;
+    }
+    if (2 * n > c->slot) {
+        helios_set_error("fused flux all-reduce: %d interfaces do not fit the mailbox slot (%d doubles)", n, c->slot);
+        return HELIOS_ERR_ARG;
+    }
+    for (int r = 0; r < c->world; r++) {
+        if (c->peers[r] == nullptr) {
+            helios_set_error("fused flux all-reduce: peer %d not connected", r);
+            return HELIOS_ERR_STATE;
+        }
+    }
+    if (c->fused_ticket == nullptr) {
+        HCUDA(cudaMalloc((void**)&c->fused_ticket, sizeof(unsigned)));
+        HCUDA(cudaMemsetAsync(c->fused_ticket, 0, sizeof(unsigned), ctx->stream));
+    }
+    for (int r = 0; r < COMM_MAX_WORLD; r++) fc->peers.p[r] = c->peers[r];
+    fc->rank = c->rank;
+    fc->world = c->world;
+    fc->slot = c->slot;
+    fc->data_bytes = c->data_bytes;
+    fc->seq = ++c->seq;
+    fc->ticket = c->fused_ticket;
+    return HELIOS_OK;
+}
+
 extern "C" {
+
+int helios_comm_set_fused(helios_ctx* ctx, int on) {
+    HCTX(ctx);
+    if (!ctx->comm) {
+        helios_set_error("helios_comm_set_fused: no communicator");
+        return HELIOS_ERR_STATE;
+    }
+    ctx->comm->fused = on != 0;
+    return HELIOS_OK;
+}
 
 int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles, unsigned char* handle_out) {
     HCTX(ctx);
@@ -180,6 +195,7 @@ int helios_comm_destroy(helios_ctx* ctx) {
     for (int r = 0; r < c->world; r++)
         if (c->opened[r] && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
     if (c->own) cudaFree(c->own);
+    if (c->fused_ticket) cudaFree(c->fused_ticket);
     delete c;
     ctx->comm = nullptr;
     return HELIOS_OK;

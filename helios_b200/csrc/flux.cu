@@ -1,6 +1,7 @@
 // Band / Gauss-point flux integration, temperature stepping and the post-processing diagnostics.
 // From-scratch sm_100a kernels for K:2428-3139 of the reference.
 #include "common.cuh"
+#include "comm.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // integrate_flux (K:2428-2513).  The reference runs ONE 1024-thread block that funnels every cell
@@ -31,7 +32,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                  double* __restrict__ F_up_band, double* __restrict__ F_dir_band,
                  const double* __restrict__ gauss_weight, int nbin, int ny, int xb,
                  const double* __restrict__ deltalambda, double* __restrict__ partial, unsigned* __restrict__ ticket,
-                 double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net) {
+                 double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net, FusedComm fc) {
     extern __shared__ double sm[];
     const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
     double* s_dn = sm;
@@ -114,6 +115,54 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         F_down_tot[slot] = dn;
         F_net[slot] = up - dn;
         ticket[slot] = 0u;
+    }
+    // Wavelength sharding, fused form (helios_comm_set_fused): the sum over ranks of the per-interface totals runs in THIS
+    // launch.  The block that finishes an interface stores this rank's two partial totals straight into slot `rank` of
+    // every peer's mailbox over NVLink; the block that finishes the LAST interface raises this rank's flag in every
+    // mailbox, waits for the peers' flags and adds the world's slots in rank order -- every rank obtains bitwise the same
+    // totals.  One launch instead of integration + exchange kernel.
+    if (fc.world > 0) {
+        __shared__ bool all_done;
+        if (threadIdx.x == 0) {
+            all_done = false;
+            if (last) {
+                const int bank = (int)(fc.seq & 1ull);
+                const double up = F_up_tot[i], dn = F_down_tot[i];
+                for (int r = 0; r < fc.world; r++) {
+                    double* data = reinterpret_cast<double*>(fc.peers.p[r]) + ((size_t)bank * fc.world + fc.rank) * fc.slot;
+                    data[i] = up;
+                    data[nint + i] = dn;
+                }
+                __threadfence_system();
+                all_done = atomicAdd(fc.ticket, 1u) == (unsigned)nint - 1;
+            }
+        }
+        __syncthreads();
+        if (all_done) {
+            if ((int)threadIdx.x < fc.world) {
+                unsigned long long* flags = reinterpret_cast<unsigned long long*>(
+                    reinterpret_cast<char*>(fc.peers.p[threadIdx.x]) + fc.data_bytes);
+                st_flag(flags + 16 * fc.rank, fc.seq);
+                const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
+                    reinterpret_cast<char*>(fc.peers.p[fc.rank]) + fc.data_bytes);
+                while (ld_flag(mine + 16 * threadIdx.x) < fc.seq) __nanosleep(64);
+            }
+            __syncthreads();
+            __threadfence_system();
+            const int bank = (int)(fc.seq & 1ull);
+            const volatile double* box = reinterpret_cast<const volatile double*>(fc.peers.p[fc.rank]);
+            for (int t = threadIdx.x; t < nint; t += blockDim.x) {
+                double a = 0.0, b = 0.0;
+                for (int r = 0; r < fc.world; r++) {
+                    a += box[((size_t)bank * fc.world + r) * fc.slot + t];
+                    b += box[((size_t)bank * fc.world + r) * fc.slot + nint + t];
+                }
+                F_up_tot[t] = a;
+                F_down_tot[t] = b;
+                F_net[t] = a - b;
+            }
+            if (threadIdx.x == 0) *fc.ticket = 0u;
+        }
     }
 }
 
@@ -476,10 +525,17 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
         HCUDA(cudaMemsetAsync(ctx->integ_ticket, 0, nticket * sizeof(unsigned), ctx->stream));
         ctx->integ_ticket_n = nticket;
     }
+    FusedComm fc;
+    rc = helios_comm_fused_next(ctx, numinterfaces, &fc);
+    if (rc) return rc;
+    if (fc.world > 0 && nb != 1) {
+        helios_set_error("helios_integrate_flux_double: the fused flux all-reduce is not available in batch mode");
+        return HELIOS_ERR_STATE;
+    }
     k_band_integrate<<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band,
                                                               F_up_band, F_dir_band, gauss_weight, nbin,
                                                               ny, xb, deltalambda, scratch + 8, ctx->integ_ticket,
-                                                              F_down_tot, F_up_tot, F_net);
+                                                              F_down_tot, F_up_tot, F_net, fc);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }

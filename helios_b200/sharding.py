@@ -94,9 +94,14 @@ def exchange_handles(my_handle, rank, world, pg=None):
     return b"".join(bytes(r.cpu().numpy().tobytes()) for r in rows)
 
 
-def attach_flux_allreduce(q, ctx, rank, world, pg=None):
-    """Create this rank's NVLink mailbox, connect the peers', and install the per-iteration exchange that
-    `Compute.integrate_flux` calls (`q.flux_allreduce`)."""
+def attach_flux_allreduce(q, ctx, rank, world, pg=None, fused=True):
+    """Create this rank's NVLink mailbox, connect the peers', and install the per-iteration exchange.
+
+    fused (default): `helios_integrate_flux_double` itself performs the exchange -- the block that finishes the last
+    interface pushes this rank's totals into the peers' mailboxes, waits for theirs and sums in rank order
+    (helios_comm_set_fused; csrc/flux.cu) -- so a sharded flux solve is two launches (sweep, integration).
+    fused=False: a separate one-block kernel after the integration (`q.flux_allreduce`, called by
+    `Compute.integrate_flux`)."""
     import ctypes
     n = int(q.ninterface)
     handle = (ctypes.c_ubyte * 64)()
@@ -108,7 +113,9 @@ def attach_flux_allreduce(q, ctx, rank, world, pg=None):
     def flux_allreduce(quant):
         ctx.call("comm_allreduce_flux_totals", quant.dev_F_up_tot, quant.dev_F_down_tot, quant.dev_F_net, n)
 
-    q.flux_allreduce = flux_allreduce
+    ctx.call("comm_set_fused", 1 if fused else 0)
+    q.flux_allreduce = None if fused else flux_allreduce
+    q.flux_allreduce_fused = bool(fused)
     return flux_allreduce
 
 

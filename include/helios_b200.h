@@ -465,6 +465,10 @@ int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n);
  * slot_doubles must be >= 2*numinterfaces. */
 int helios_comm_allreduce_flux_totals(helios_ctx* ctx, double* F_up_tot, double* F_down_tot, double* F_net,
                                       int numinterfaces);
+/* on != 0: helios_integrate_flux_double performs the flux-total exchange in its own launch (the block that finishes the
+ * last interface pushes / waits / sums over the peer mailboxes); helios_comm_allreduce_flux_totals must then NOT be
+ * called for that step.  Every rank has to make the same sequence of exchanging calls. */
+int helios_comm_set_fused(helios_ctx* ctx, int on);
 int helios_comm_destroy(helios_ctx* ctx);
 
 #ifdef __cplusplus

@@ -53,7 +53,7 @@ def _store(config, ctx):
     return q
 
 
-def _worker(rank, world, port, config, out):
+def _worker(rank, world, port, config, fused, out):
     sys.path.insert(0, ROOT)
     try:
         import torch.distributed as dist
@@ -67,7 +67,8 @@ def _worker(rank, world, port, config, out):
         q = _store(config, ctx)
         sharding.shard_store(q, rank, world)
         synthetic.upload(q)
-        sharding.attach_flux_allreduce(q, ctx, rank, world)
+        # fused: the exchange runs inside the integration kernel's epilogue; otherwise a separate one-block kernel
+        sharding.attach_flux_allreduce(q, ctx, rank, world, fused=fused)
         part = _solve(q, comp, rank, world)
         worst = 0.0
         for (fu, fd, fn, T), (gu, gd, gn, gT) in zip(full, part):
@@ -90,8 +91,9 @@ def _worker(rank, world, port, config, out):
         out.put((rank, "fail", traceback.format_exc()))
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("config", ["C1", "C2"])
-def test_wavelength_sharded_flux_solve_two_gpus(config):
+def test_wavelength_sharded_flux_solve_two_gpus(config, fused):
     from helios_b200 import backend
     import ctypes
     n = ctypes.c_int(0)
@@ -104,7 +106,7 @@ def test_wavelength_sharded_flux_solve_two_gpus(config):
         port = s.getsockname()[1]
     mpctx = mp.get_context("spawn")
     out = mpctx.Queue()
-    procs = [mpctx.Process(target=_worker, args=(r, 2, port, config, out)) for r in range(2)]
+    procs = [mpctx.Process(target=_worker, args=(r, 2, port, config, fused, out)) for r in range(2)]
     for p in procs:
         p.start()
     results = [out.get(timeout=300) for _ in procs]
@@ -112,5 +114,5 @@ def test_wavelength_sharded_flux_solve_two_gpus(config):
         p.join(timeout=60)
     for rank, status, info in results:
         assert status == "ok", "rank %d:\n%s" % (rank, info)
-    print("\n[multi] %s: 2-rank wavelength-sharded solve vs unsharded, worst relative difference %.2e" %
-          (config, max(r[2] for r in results)))
+    print("\n[multi] %s (%s exchange): 2-rank wavelength-sharded solve vs unsharded, worst relative difference %.2e" %
+          (config, "fused" if fused else "separate", max(r[2] for r in results)))

@@ -1,7 +1,9 @@
 """GPU: end-to-end parity of the converged state.  The same host loop (Compute.radiation_loop /
 convection_loop) is driven once through the product's C-ABI kernels and once through the reference's own
 kernels.cu (RefBacked below re-points every launch site at the verbatim cubin).  BASELINE.json's bar: converged
-T-P profile within 0.01 K, TOA emission spectrum within 1e-8 relative."""
+T-P profile within 0.01 K, TOA emission spectrum within 1e-8 relative -- asserted without any allowance, on the
+deterministic form of the reference trajectory.  (The reference's own LOOPS, with its nondeterministic atomics, are
+run by tests/test_gpu_refloop.py.)"""
 import numpy as np
 import pytest
 
@@ -23,10 +25,16 @@ _SITES = ["construct_planck_table", "correct_incident_energy", "interpolate_temp
 class RefBacked(Compute):
     """Compute's loops with every kernel launch site served by the reference's kernels.cu"""
 
-    def __init__(self, ctx):
+    def __init__(self, ctx, deterministic_integration=False):
+        """deterministic_integration: keep the product's fixed-order band / wavelength sums for `integrate_flux` only.
+        The reference's integrate_flux_double adds with CAS atomics in whatever order the hardware schedules (K:2474), so
+        its trajectory is not reproducible run to run; with this one launch site swapped the reference-kernel trajectory
+        is deterministic and can be compared at the north-star bars without any allowance for run-to-run spread."""
         super().__init__(ctx, verbose=False)
         self._ref = ref_gpu.RefCompute(ctx.device)
         for name in _SITES:
+            if deterministic_integration and name == "integrate_flux":
+                continue
             setattr(self, name, self._bind(name))
 
     def prepare_iteration(self, q):  # Compute fuses the two launch sites; the reference has them separately
@@ -43,7 +51,7 @@ class RefBacked(Compute):
         return int(q.dev_abort.get().sum())  # C:927-932
 
 
-def _run(ctx, config, backed, perturb=0.0, T_intern=None):
+def _run(ctx, config, backed, perturb=0.0, T_intern=None, det=False, limit=None):
     q = synthetic.make_store(config, ctx=ctx, **SMALL)
     if config == "C2":
         q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
@@ -53,8 +61,10 @@ def _run(ctx, config, backed, perturb=0.0, T_intern=None):
         host.calc_F_intern(q)
     if perturb:
         q.T_lay = np.asarray(q.T_lay, np.float64) + perturb
+    if limit is not None:
+        q.rad_convergence_limit = np.float64(limit)
     synthetic.upload(q)
-    comp = RefBacked(ctx) if backed else Compute(ctx, verbose=False)
+    comp = RefBacked(ctx, deterministic_integration=det) if backed else Compute(ctx, verbose=False)
     comp.construct_planck_table(q)
     comp.correct_incident_energy(q)
     comp.radiation_loop(q, None, None, None)
@@ -98,51 +108,30 @@ def _lockstep(ctx, config, steps=25):
 
 
 @pytest.mark.parametrize("config", ["C1", "C2"])
-def test_converged_profile_and_spectrum_match_reference_kernels(ctx, config):
-    """Converged state, ours vs the reference's kernels behind the same host loop.
-
-    The pseudo-time stepping branches on comparisons and the reference's band integration adds in a
-    nondeterministic order (CAS atomics, K:2474), so two runs stop at two different points INSIDE the
-    convergence basin |dF| / F < rad_convergence_limit.  Where the profile is well determined by that
-    criterion (C1) the two agree to ~1e-6 K.  In C2 the deep, optically thick layers are only weakly
-    constrained by it (dF/dT is ~1e-4 of the optically thin value), so the honest yardstick is the reference's
-    own spread: the same loop driven by the reference's kernels from three start profiles 1e-9 K apart (the
-    reference's trajectory is not even reproducible run to run; its iteration count varies by tens of percent).
-    Bars (BASELINE.json): T-P within 0.01 K and TOA spectrum within 1e-8 of the nearest reference run -- or
-    within 2x the reference's own run-to-run spread where that spread exceeds them."""
+def test_converged_state_at_the_north_star_bars(ctx, config):
+    """BASELINE.json's bars with no allowance: converged T-P within 0.01 K, TOA spectrum within 1e-8 relative.
+    The reference's kernels behind the same loop, with ONE launch site made deterministic (the band / wavelength sums:
+    the reference's CAS-atomic order is the only source of its run-to-run spread), against the product's kernels.  Both
+    trajectories then differ only through the <= 1e-10 differences of the kernels; the pseudo-time controller
+    (K:2717-2724 branches on comparisons) does not amplify those beyond the bars, and the two runs stop after the same
+    number of iterations."""
     if not ref_gpu.available():
         pytest.skip("reference cubin not built")
-    lock = _lockstep(ctx, config)
-    ours = _run(ctx, config, backed=False)
-    refs = [_run(ctx, config, backed=True, perturb=p) for p in (0.0, 1e-9, -1e-9)]
-
-    def spec_diff(a, b):
-        return float(np.max(np.abs(a["toa"] - b["toa"]) / np.maximum(np.abs(b["toa"]), 1e-6 * np.max(np.abs(b["toa"])))))
-
-    def t_diff(a, b, key="T"):
-        return float(np.max(np.abs(a[key] - b[key])))
-
-    pairs = [(0, 1), (0, 2), (1, 2)]
-    spread_T = max(t_diff(refs[i], refs[j]) for i, j in pairs)
-    spread_spec = max(spec_diff(refs[i], refs[j]) for i, j in pairs)
-    # ours is as close to SOME run of the reference as the reference's runs are to each other
-    dT = min(t_diff(ours, r) for r in refs)
-    dT_rad = min(t_diff(ours, r, "T_rad") for r in refs)
-    spec = min(spec_diff(ours, r) for r in refs)
-    print("\n[rce] %s: lock-step 25 iterations max rel dT %.1e; radiation loop %d (ours) / %s (kernels.cu, three starts "
-          "1e-9 K apart) iterations, convection loop %d / %d; max |dT| ours-vs-nearest-ref %.2e K (after the radiation "
-          "loop %.2e K), ref-vs-ref spread %.2e K; TOA spectrum rel. diff %.2e (ref-vs-ref %.2e)" %
-          (config, lock, ours["rad_iters"], [r["rad_iters"] for r in refs], ours["conv_iters"], refs[0]["conv_iters"],
-           dT, dT_rad, spread_T, spec, spread_spec))
+    lock = _lockstep(ctx, config)  # fully reference-backed (atomics included): 25 iterations agree to rounding
     assert lock < 1e-9, lock
-    assert ours["rad_iters"] > 50, "the loop did not iterate"
-    # Three runs are a small sample of the reference's spread.  Over the runs of this round the reference's own
-    # run-to-run differences on the C2 case were 2.4e-2 .. 6.0e-2 K and 1.8e-7 .. 2.0e-7 (spectrum); those measured
-    # values are the floor of the yardstick, so that a lucky trio of close reference runs cannot fail a correct backend.
-    floor_T, floor_spec = (0.1, 5e-7) if config == "C2" else (0.0, 0.0)
-    assert dT <= max(0.01, 2 * spread_T, floor_T), (dT, spread_T)
-    assert dT_rad <= max(0.01, 2 * spread_T, floor_T), (dT_rad, spread_T)
-    assert spec <= max(1e-8, 2 * spread_spec, floor_spec), (spec, spread_spec)
+    ours = _run(ctx, config, backed=False)
+    ref = _run(ctx, config, backed=True, det=True)
+    dT = float(np.max(np.abs(ours["T"] - ref["T"])))
+    dT_rad = float(np.max(np.abs(ours["T_rad"] - ref["T_rad"])))
+    spec = float(np.max(np.abs(ours["toa"] - ref["toa"]) / np.maximum(np.abs(ref["toa"]), 1e-6 * np.max(np.abs(ref["toa"])))))
+    print("\n[rce-det] %s: radiation loop %d / %d iterations, convection loop %d / %d; max |dT| %.2e K (after the radiation "
+          "loop %.2e K); TOA spectrum rel. diff %.2e" % (config, ours["rad_iters"], ref["rad_iters"], ours["conv_iters"],
+                                                          ref["conv_iters"], dT, dT_rad, spec))
+    assert ours["rad_iters"] > 50
+    assert dT_rad <= 0.01, dT_rad
+    assert dT <= 0.01, dT
+    assert spec <= 1e-8, spec
+    assert abs(ours["rad_iters"] - ref["rad_iters"]) <= max(2, ours["rad_iters"] // 100), (ours["rad_iters"], ref["rad_iters"])
     # radiative equilibrium: F_net == F_intern at every interface of the radiative zone (K:2751, known-answer iii)
     if ours["conv"] == 0:
         scale = ours["Fdn_top"] + ours["F_intern"]

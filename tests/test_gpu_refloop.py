@@ -1,0 +1,89 @@
+"""GPU: the reference's OWN loops.  `source/computation.py` + `quantities.py` + `host_functions.py`, unmodified
+(byte-compiled in place from /root/reference into oracle/_ref/helios_py), run `radiation_loop` / `convection_loop`
+(C:827-1174) over the test-only PyCUDA stand-in of oracle/refshim on the reference's own kernels -- in a child process,
+because it brings its own `pycuda` / `astropy` / `source` modules.  That pins what no per-kernel test can: the loop
+control flow of helios_b200.Compute (refresh schedule, convergence test, hand-over to the convection loop, iteration
+counts) against the code it mirrors."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helios_b200 import synthetic
+from helios_b200.computation import Compute
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = dict(nbin=37, nlayer=24, ntemp=12, npress=8, plancktable_dim=700, plancktable_step=10)
+
+
+def _reference_runs(tmp_path, config, n, **kw):
+    from oracle.refshim import runner
+    if not runner.available():
+        pytest.skip("oracle/_ref/helios_py or the reference cubin is missing (make -C oracle ref refpy)")
+    out = []
+    for k in range(n):
+        pkl, npz = str(tmp_path / ("in_%s_%d.pkl" % (config, k))), str(tmp_path / ("out_%s_%d.npz" % (config, k)))
+        host = runner.dump_host_store(config, pkl, **kw)
+        if config == "C2":  # the regular (non-singular) beam angle of the parity tests
+            import pickle
+            host["mu_star"] = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+            pickle.dump(host, open(pkl, "wb"), protocol=4)
+        env = dict(os.environ, PYTHONPATH=ROOT)
+        r = subprocess.run([sys.executable, "-m", "oracle.refshim.runner", "run", pkl, npz], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, "reference run failed:\n%s\n%s" % (r.stdout[-2000:], r.stderr[-4000:])
+        out.append(dict(np.load(npz, allow_pickle=True)))
+    return out
+
+
+def _ours(ctx, config, **kw):
+    q = synthetic.make_store(config, ctx=ctx, **kw)
+    if config == "C2":
+        q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+    synthetic.upload(q)
+    comp = Compute(ctx, verbose=False)
+    comp.construct_planck_table(q)
+    comp.correct_incident_energy(q)
+    comp.radiation_loop(q, None, None, None)
+    rad = int(q.iter_value)
+    conv = 0
+    if q.convection == 1:
+        comp.convection_loop(q, None, None, None)
+        conv = int(q.iter_value)
+    nl, nb = int(q.nlayer), int(q.nbin)
+    return dict(T=q.dev_T_lay.get(), toa=q.dev_F_up_band.get()[nl * nb:(nl + 1) * nb], rad=rad, conv=conv)
+
+
+@pytest.mark.parametrize("config", ["C1", "C2"])
+def test_loops_against_the_references_own_computation_py(ctx, tmp_path, config):
+    """Iteration counts and the converged state of helios_b200.Compute's loops against the reference's own loops.  The
+    reference is not reproducible run to run (CAS-atomic summation order feeds a controller that branches on
+    comparisons), so it runs three times and the yardstick is max(north-star bar, 2 x its own spread)."""
+    refs = _reference_runs(tmp_path, config, 3, **SMALL)
+    ours = _ours(ctx, config, **SMALL)
+    nl, nb = SMALL["nlayer"], SMALL["nbin"]
+
+    def toa(r):
+        return np.asarray(r["F_up_band"])[nl * nb:(nl + 1) * nb]
+
+    def spec(a, b):
+        return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6 * np.max(np.abs(b)))))
+
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    spread_T = max(float(np.max(np.abs(refs[i]["T_lay"] - refs[j]["T_lay"]))) for i, j in pairs)
+    spread_s = max(spec(toa(refs[i]), toa(refs[j])) for i, j in pairs)
+    dT = min(float(np.max(np.abs(ours["T"] - r["T_lay"]))) for r in refs)
+    ds = min(spec(ours["toa"], toa(r)) for r in refs)
+    rad_ref = [int(r["radiation_iterations"]) for r in refs]
+    conv_ref = [int(r["convection_iterations"]) for r in refs]
+    print("\n[refloop] %s: radiation loop %d (ours) vs %s (reference computation.py), convection loop %d vs %s; max |dT| to "
+          "the nearest reference run %.2e K (reference run-to-run %.2e K), TOA spectrum %.2e (run-to-run %.2e)" %
+          (config, ours["rad"], rad_ref, ours["conv"], conv_ref, dT, spread_T, ds, spread_s))
+    assert all(str(r["status"]) == "converged" for r in refs)
+    assert min(rad_ref) * 0.7 <= ours["rad"] <= max(rad_ref) * 1.3, (ours["rad"], rad_ref)
+    assert (ours["conv"] > 0) == (max(conv_ref) > 0), (ours["conv"], conv_ref)
+    assert dT <= max(0.01, 2 * spread_T), (dT, spread_T)
+    assert ds <= max(1e-8, 2 * spread_s), (ds, spread_s)

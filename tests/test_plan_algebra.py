@@ -1,4 +1,4 @@
-"""CPU check of the algebra behind the sweep plan (helios_b200/csrc/fband_cp.cu: plan_half / k_plan_build).
+"""CPU check of the algebra behind the sweep plan (helios_b200/csrc/fband_plan.cu: plan_half / k_plan_build_noniso).
 
 Between two opacity refreshes only the Planck values of a half-layer change, and the source term of the two-stream
 recurrence (K:1640-1691 downward, K:1744-1795 upward) is affine in them:
@@ -150,3 +150,15 @@ def test_hoisted_scan_equals_guarded_scan():
                 for i in range(nch - 1, j - 1, -1):
                     a_, b_ = A[i] * a_, A[i] * b_ + B[i]
                 assert abs(hA[j] - a_) <= 1e-13 * abs(a_) and abs(hB[j] - b_) <= 1e-12 * (abs(b_) + np.abs(B).max())
+
+
+def test_upward_weights_are_the_downward_ones_swapped_bit_for_bit():
+    """fband_plan.cu stores SIX constants per half-layer [a, b, k0d, k0u, k1, k2] instead of eight: the weights of
+    (B_layer, B_interface) in the upward source term are the downward ones swapped -- not just mathematically but bit for
+    bit in IEEE arithmetic ((M - P) - N == -(N + (P - M)) exactly, and negation commutes with rounding), in the gradient
+    form and in the thin-layer fallback, for both halves."""
+    rng = np.random.default_rng(20260115)
+    w0, M, N, P, dt, g0, E, Dd, Du, _, _ = _random_cells(rng, 50000)
+    for upper in (True, False):
+        _, _, _, k1d, k2d, _, k1u, k2u = plan_half(w0, M, N, P, dt, g0, E, Dd, Du, upper, 0.5, 1e-4)
+        assert np.array_equal(k1u, k2d) and np.array_equal(k2u, k1d)
