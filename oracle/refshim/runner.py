@@ -1,5 +1,5 @@
 """Drive the reference's UNMODIFIED Python (source/computation.py, quantities.py, host_functions.py -- byte-compiled from
-/root/reference into oracle/_ref/helios_py by `make -C oracle refpy`) over the PyCUDA stand-in of this directory.
+/root/reference into oracle/_ref/helios_py/source/*.bin by `make -C oracle refpy`) over the PyCUDA stand-in of this directory.
 TEST INFRASTRUCTURE: used by tests/test_gpu_refloop.py and by `bench.py --impl reference`; never by the product.
 Nothing here imports helios_b200 or loads libhelios_b200.so.
 
@@ -8,6 +8,9 @@ Host-side inputs come as a plain dict of the attributes `read.py` would have put
     python -m oracle.refshim.runner run <inputs.pkl> <out.npz> [--max-iter N]      one RCE run, results to out.npz
 """
 import contextlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import io
 import os
 import pickle
@@ -22,8 +25,26 @@ REF_PY = os.path.join(os.path.dirname(HERE), "_ref", "helios_py")
 
 
 def available():
-    return os.path.exists(os.path.join(REF_PY, "source", "computation.pyc")) and \
+    return os.path.exists(os.path.join(REF_PY, "source", "computation.bin")) and \
         os.path.exists(os.path.join(os.path.dirname(HERE), "_ref", "helios_ref.cubin"))
+
+
+class _ByteCodeFinder(importlib.abc.MetaPathFinder):
+    """`source` and `source.X` from oracle/_ref/helios_py/source/X.bin (byte code of the unmodified reference modules)"""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname != "source" and not fullname.startswith("source."):
+            return None
+        pkg = os.path.join(REF_PY, "source")
+        leaf = "__init__" if fullname == "source" else fullname.split(".", 1)[1]
+        if "." in leaf:
+            return None
+        f = os.path.join(pkg, leaf + ".bin")
+        if not os.path.exists(f):
+            return None
+        loader = importlib.machinery.SourcelessFileLoader(fullname, f)
+        return importlib.util.spec_from_file_location(fullname, f, loader=loader,
+                                                      submodule_search_locations=[pkg] if fullname == "source" else None)
 
 
 def load_reference():
@@ -33,9 +54,10 @@ def load_reference():
         if mod is not None and not (getattr(mod, "__file__", "") or "").startswith((HERE, REF_PY)):
             raise RuntimeError("a foreign `%s` is already imported (%s): run the reference in its own process" %
                                (name, getattr(mod, "__file__", "?")))
-    for p in (REF_PY, HERE):
-        if p not in sys.path:
-            sys.path.insert(0, p)
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    if not any(isinstance(f, _ByteCodeFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _ByteCodeFinder())
     import source.computation as computation
     import source.quantities as quantities
     import source.host_functions as host_functions
