@@ -86,6 +86,28 @@ def _traffic_from_profile(workload, nbatch=None):
     return best
 
 
+def _fp64_peaks():
+    """measured pipe peaks of this pool's B200 (scripts/peaks_bench.cu -> profiles/r2_measured_fp64_peaks.json)"""
+    path = os.path.join(ROOT, "profiles", "r2_measured_fp64_peaks.json")
+    if os.path.exists(path):
+        return json.load(open(path)), "measured (profiles/r2_measured_fp64_peaks.json, scripts/peaks_bench.cu)"
+    return {"fp64_fma_tflops": 36.4, "dfma_per_clk_per_sm": 62.5, "ddiv_rn_gops": 1245.0, "exp_f64_gops": 875.0,
+            "sqrt_f64_gops": 1222.0, "sms": 148, "sm_clock_ghz_nominal": 1.965}, "fallback (round-2 measurement)"
+
+
+def _fp64_roofline(kernel, ops, t_ms, what):
+    """compute-bound launches: `ops` = {"fma": n, "div": n, "exp": n, "sqrt": n, "cmp": n} algorithmic fp64 operations per
+    launch; the bound is the time the measured pipe rates need for them, frac = bound / measured time"""
+    pk, src = _fp64_peaks()
+    fma_rate = pk["fp64_fma_tflops"] * 0.5e12  # FMA (or MUL / ADD / compare) instructions per second
+    t_bound = (ops.get("fma", 0) + ops.get("cmp", 0)) / fma_rate + ops.get("div", 0) / (pk["ddiv_rn_gops"] * 1e9) + \
+        ops.get("exp", 0) / (pk["exp_f64_gops"] * 1e9) + ops.get("sqrt", 0) / (pk["sqrt_f64_gops"] * 1e9)
+    flops = 2.0 * ops.get("fma", 0) + ops.get("cmp", 0) + ops.get("div", 0) + ops.get("exp", 0) + ops.get("sqrt", 0)
+    return {"bound": "fp64", "kernel": kernel, "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": pk["fp64_fma_tflops"],
+            "unit": "TFLOP/s", "frac": t_bound / (t_ms * 1e-3), "traffic": None, "kernel_ms": t_ms, "operations": ops,
+            "peak_source": src, "what": what}
+
+
 class ClockSampler(object):
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -356,6 +378,7 @@ def bench_c4(ctx, rank, world, steps, warmup, flush, nbin=100000, scat=1, dim=80
 
     t_solve, t_fband = _timed(ctx, step, steps, warmup, flush)
     return dict(q=q, comp=comp, npass=npass, cells=cells, points=cells * npass, t_solve=t_solve, t_fband=t_fband,
+                totals=(q.dev_F_up_tot.get(), q.dev_F_down_tot.get()),
                 bpc=_bytes_per_cell(q), sbpc=_survey_bytes_per_cell(q), kernel=_sweep_kernel_name(q),
                 workload="C4: post-processing spectrum, %d layers x %d bins x 1 point (this rank: %d bins), %d fused "
                          "flux passes (scat=%d), wavelength-sharded over %d GPU(s)" %
@@ -395,10 +418,104 @@ def bench_mixing(ctx, flush, reps=5):
         out[mixing] = {"ms_per_species_loop": ms, "species": nspec, "cells_x_i": cells,
                        "mixed_cells_per_s": cells * nspec / (ms * 1e-3),
                        "k_combinations_sorted_per_s": (cells * (nspec - 1) * 400 / (ms * 1e-3)) if mixing == "RO" else None}
+        if mixing == "RO":
+            # per (x, i) cell and species: 400 k-sums + 400 weights, a 512-wide bitonic network = 256 * 45 = 11,520
+            # compare-exchanges (one fp64 compare each), a 400-long weight scan and 20 interpolations of ~4 FMA
+            per_cell = {"fma": 400 + 400 + 80, "cmp": 11520}
+            out[mixing]["roofline"] = _fp64_roofline(
+                "k_add_to_mixed_opac (random overlap) + k_pt_gather, %d species" % nspec,
+                {k: v * cells * (nspec - 1) for k, v in per_cell.items()}, ms,
+                "fp64-pipe operations of the sort network and the rebinning; the loop also interpolates every species' table")
     out["workload"] = ("C3: %d species, %d layers x %d bins x %d gauss points, isothermal layers; one full species loop "
                        "(interpolation + mixing + scattering cross sections), tables resident in HBM" %
                        (nspec, q.nlayer, q.nbin, q.ny))
     return out
+
+
+def sharded_self_check(ctx, rank, world):
+    """N >= 2: the wavelength-sharded flux solve with the fused NVLink exchange against the unsharded solve of the same
+    (small) spectrum, both run by every rank; returns the largest relative difference of the per-interface totals"""
+    from helios_b200 import backend, synthetic, sharding
+    from helios_b200.computation import Compute
+    kw = dict(nbin=4096, nlayer=100, ntemp=12, npress=8, plancktable_dim=700, plancktable_step=10)
+    out = []
+    for sharded in (False, True):
+        q = synthetic.make_store("C4", ctx=ctx, **kw)
+        q.scat = np.int32(1)
+        q.singlewalk = np.int32(0)  # 4 passes
+        n = int(q.nlayer)
+        q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+        if sharded:
+            sharding.shard_store(q, rank, world)
+        synthetic.upload(q)
+        if sharded:
+            sharding.attach_flux_allreduce(q, ctx, rank, world)
+        comp = Compute(ctx, verbose=False)
+        comp.construct_planck_table(q)
+        q.iter_value = np.int32(0)
+        refresh(comp, q)
+        for _ in range(2):
+            comp.populate_spectral_flux_iteratively(q)
+            comp.integrate_flux(q)
+        out.append((q.dev_F_up_tot.get(), q.dev_F_down_tot.get()))
+        ctx.synchronize()
+        if sharded:
+            backend._check(backend.lib().helios_comm_destroy(ctx.handle), "helios_comm_destroy")
+    worst = 0.0
+    for a, b in zip(out[0], out[1]):
+        worst = max(worst, float(np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-300))))
+    return worst
+
+
+def multi_gpu_workloads(ctx, rank, world, args, flush, barrier, reduce_max):
+    """the two partitioned configurations of BASELINE.json at N > 1, every rank taking part:
+      C4  the 1e5-bin spectrum sharded by wavelength (strong scaling), exchange fused into the integration kernel
+      C5  the batched grid, 128 atmospheres per GPU (weak scaling, no collective)"""
+    from helios_b200 import backend
+    steps = max(5, args.steps // 5)
+    extra = {}
+    barrier()
+    check = sharded_self_check(ctx, rank, world)
+    check = reduce_max([check])[0]
+    extra["sharded_self_check"] = {"max_rel_diff_vs_unsharded": check, "what": "4096-bin spectrum, 100 layers, 2 flux solves "
+                                   "of 4 passes: per-interface flux totals, wavelength-sharded over %d GPUs with the "
+                                   "fused exchange vs unsharded" % world}
+    r = None
+    for scat in (0, 1):
+        key = "C4_spectrum_1e5_bins_scat%d" % scat
+        barrier()
+        r = bench_c4(ctx, rank, world, max(3, steps // 2) if scat else steps, 3, flush, scat=scat, reuse=r)
+        barrier()
+        t_solve, t_fband = reduce_max([r["t_solve"], r["t_fband"]])
+        total_points = 100 * 100000 * r["npass"]
+        extra[key] = {"workload": r["workload"], "value": total_points / (t_solve * 1e-3), "unit": UNIT, "n_gpus": world,
+                      "scaling": "strong", "ms_per_step": t_solve, "sweep_kernel_ms": t_fband,
+                      "launches_per_step": 2,
+                      "exchange": "fused into k_band_integrate's epilogue: peer stores + flags over NVLink, rank-order sum"}
+    backend._check(backend.lib().helios_comm_destroy(ctx.handle), "helios_comm_destroy")
+    del r
+    gc.collect()
+    barrier()
+    r = bench_batch(ctx, rank, world, args.batch, steps, 3, flush)
+    barrier()
+    t_solve, t_fband, t_e2e = reduce_max([r["t_solve"], r["t_fband"], r["t_e2e"]])
+    extra["C5_batched_grid"] = {"workload": r["workload"], "value": world * r["points"] / (t_solve * 1e-3), "unit": UNIT,
+                                "n_gpus": world, "scaling": "weak", "ms_per_step": t_solve, "sweep_kernel_ms": t_fband,
+                                "e2e": {"value": world * r["points"] / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e,
+                                        "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]}}
+    return extra
+
+
+def _sweep_roofline(r, tag, nbatch=None):
+    """HBM roofline for a flux solve of a few fused passes; for long pass sequences (post-processing: 1001 passes run from
+    registers) the launch is bound by the fp64 pipe instead: 4 multiply-adds per cell and pass (cc and the walk step, both
+    sweeps) are the recurrence's own arithmetic"""
+    if r["npass"] >= 8:
+        return _fp64_roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), {"fma": 4.0 * r["cells"] * r["npass"]},
+                              r["t_fband"], "the two-stream recurrence itself: 2 FMA per cell, sweep and pass (source term, "
+                              "flux step); the layer-parallel evaluation executes ~3x that (composition + scan)")
+    return _roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), r["bpc"], r["cells"], r["t_fband"], r["npass"], tag,
+                     nbatch, r["sbpc"])
 
 
 def _quiesce(ctx):
@@ -492,6 +609,68 @@ def rce_batch(ctx, nbatch=32):
                     "to the reference's convergence criterion, converged ones frozen by the on-device latch" % nbatch}
 
 
+def e2e_leg(ctx, workload, flush, steps, rank, barrier):
+    """the metric measured end to end: one RT iteration per step through the public API with HOST buffers.  The
+    temperature profile comes from pinned host memory every iteration and the per-interface fluxes, the new profile and
+    the convergence flags go back to the host every iteration; the copies are part of the recorded iteration."""
+    from helios_b200 import backend, synthetic
+    from helios_b200.batch import make_batch
+    q1 = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + rank)
+    n = int(q1.nlayer)
+    q1.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+    qb, bc = make_batch([q1], ctx)
+    bc.construct_planck_table(qb)
+    bc.correct_incident_energy(qb)
+    qb.enter()
+    lib = backend.lib()
+    backend._check(lib.helios_ctx_batch_device_iteration(ctx.handle, 1), "helios_ctx_batch_device_iteration")
+    qb.state(reset=True)
+    qb.iter_value = np.int32(0)  # the kernels read the device counter; the argument is ignored
+    nint = int(qb.ninterface)
+    T_host = backend.PinnedArray(n + 1)
+    T_host.array[:] = qb.dev_T_lay.get()
+    outs = [("F_net", nint, np.float64), ("F_up_tot", nint, np.float64), ("F_down_tot", nint, np.float64),
+            ("T_lay", n + 1, np.float64), ("abort", n + 1, np.int32)]
+    hosts = [backend.PinnedArray(size, dt) for _, size, dt in outs]
+
+    def body(refresh):
+        T_host.h2d_async(ctx, qb.dev_T_lay)
+        bc._iteration(qb, refresh=refresh, heights=False, fused=True)
+        for (name, _, _), h in zip(outs, hosts):
+            h.d2h_async(ctx, getattr(qb, "dev_" + name))
+
+    for k in range(10):  # eager first block: sizes the library's scratch buffers, builds the plan buffer
+        body(k == 0)
+    ctx.synchronize()
+    graphs = {}
+    for refresh in (True, False):
+        with ctx.capture() as g:
+            body(refresh)
+        graphs[refresh] = g
+    for k in range(10):
+        graphs[k == 0].launch()
+    ctx.synchronize()
+    barrier()
+    e0, e1 = ctx.event(), ctx.event()
+    e2e_steps = 10 * max(2, steps // 10)  # whole blocks of the reference's 10-iteration schedule
+    t_total = t_refresh = 0.0
+    for k in range(e2e_steps):
+        flush()
+        e0.record()
+        graphs[k % 10 == 0].launch()
+        e1.record()
+        e1.synchronize()
+        dt = e0.time_till(e1)
+        t_total += dt
+        if k % 10 == 0:
+            t_refresh += dt
+    barrier()
+    backend._check(lib.helios_ctx_batch_device_iteration(ctx.handle, 0), "helios_ctx_batch_device_iteration")
+    qb.leave()
+    return {"t_total": t_total, "t_refresh": t_refresh, "steps": e2e_steps, "h2d": T_host.nbytes,
+            "d2h": sum(h.nbytes for h in hosts), "calls": 1}
+
+
 def _roofline(kernel, bpc, cells, t_kernel_ms, npass, workload, nbatch=None, survey_bpc=None):
     peak, peak_src = _peaks()
     traffic = _traffic_from_profile(workload, nbatch)
@@ -547,7 +726,13 @@ def run_ours(args):
     l2 = ("flushed between timed steps, outside the event bracket: a 256 MiB buffer (2x L2) is overwritten and then "
           "read back, so the timed kernels start on a cold L2 that holds no dirty lines of the flusher")
 
-    if args.workload == "C5":
+    if args.workload == "C3":
+        m = bench_mixing(ctx, flush)
+        ro = m["RO"]
+        line = dict(base, metric="mixed_cells_per_s", unit="cells/s", value=ro["mixed_cells_per_s"],
+                    ms_per_step=ro["ms_per_species_loop"], scaling="weak", config={"workload": m["workload"]},
+                    e2e=None, gpu_launches=None, roofline=ro.get("roofline"), mixing=m)
+    elif args.workload == "C5":
         barrier()
         r = bench_batch(ctx, rank, world, args.batch, steps, warmup, flush)
         barrier()
@@ -573,8 +758,7 @@ def run_ours(args):
                             "sharding": "contiguous wavelength ranges per rank; one fused NVLink peer-memory all-reduce of "
                                         "the per-interface flux totals per step"},
                     e2e=None, gpu_launches=None,
-                    roofline=_roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), r["bpc"], r["cells"], t_fband,
-                                       r["npass"], "C4", None, r["sbpc"]))
+                    roofline=_sweep_roofline(dict(r, t_fband=t_fband), "C4"))
         del pts
     else:
         line = _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max)
@@ -610,9 +794,8 @@ def run_ours(args):
                 try:
                     r = bench_c4(ctx, 0, 1, max(3, steps // 10), 3, flush, scat=scat, reuse=r)
                     extra[key] = {"workload": r["workload"], "value": r["points"] / (r["t_solve"] * 1e-3), "unit": UNIT,
-                                  "ms_per_step": r["t_solve"],
-                                  "roofline": _roofline("%s, %d passes fused" % (r["kernel"], r["npass"]), r["bpc"], r["cells"],
-                                                        r["t_fband"], r["npass"], "C4", None, r["sbpc"])}
+                                  "n_gpus": 1, "scaling": "strong", "ms_per_step": r["t_solve"], "sweep_kernel_ms": r["t_fband"],
+                                  "roofline": _sweep_roofline(r, "C4")}
                 except Exception as e:  # noqa: BLE001
                     extra[key] = {"error": repr(e)}
             try:
@@ -620,6 +803,12 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 extra["C3_on_the_fly_mixing"] = {"error": repr(e)}
             line["workloads"] = extra
+        elif world > 1 and not args.only_main:
+            # every N: the wavelength-sharded spectrum (strong scaling, with the NVLink exchange) and the batched grid
+            # (weak scaling) ride along, so that the scaling run measures the partitioned configurations as well
+            extra = multi_gpu_workloads(ctx, rank, world, args, flush, barrier, reduce_max)
+            if rank == 0:
+                line["workloads"] = extra
     clocks = sampler.stop() if sampler else None
     if rank == 0:
         line["clocks"] = clocks
@@ -662,50 +851,8 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     t_fband = sum(e[0].time_till(e[1]) for e in ev)
 
     # ---- end to end through the public API, host buffers, pinned staging
-    T_host = backend.PinnedArray(int(q.nlayer) + 1)
-    T_host.array[:] = q.dev_T_lay.get()
-    nint = int(q.ninterface)
-    res_host = backend.PinnedArray(3 * nint + int(q.nlayer) + 1)
-    abort_host = backend.PinnedArray(int(q.nlayer) + 1, np.int32)
-    d2h = res_host.nbytes + abort_host.nbytes
-    h2d = T_host.nbytes
-    res_dev = ctx.zeros(3 * nint + int(q.nlayer) + 1)
-
-    def iteration(k):
-        """iteration k of the radiation loop as the reference schedules it (C:851-984): the temperature-dependent
-        opacities, transmission functions and direct beam are rebuilt every 10th iteration (C:860), the Planck
-        terms, the flux solve and the temperature step run every iteration"""
-        T_host.h2d_async(ctx, q.dev_T_lay)
-        if k % 10 == 0:
-            refresh(comp, q)
-        else:
-            comp.prepare_iteration(q)  # interpolate_temperatures + interpolate_planck (C:856-857), one launch
-        flux_solve()
-        comp.rad_temp_iteration(q)
-        for j, name in enumerate(("F_net", "F_up_tot", "F_down_tot")):
-            res_dev.view(j * nint, nint).copy_from(getattr(q, "dev_" + name))
-        res_dev.view(3 * nint, int(q.nlayer) + 1).copy_from(q.dev_T_lay)
-        res_host.d2h_async(ctx, res_dev)
-        abort_host.d2h_async(ctx, q.dev_abort)
-        ctx.synchronize()
-
-    for k in range(10):
-        iteration(k)
-    barrier()
-    e0, e1 = ctx.event(), ctx.event()
-    e2e_steps = 10 * max(2, args.steps // 10)  # whole blocks of the reference's 10-iteration schedule
-    t_e2e = t_e2e_refresh = 0.0
-    for k in range(e2e_steps):
-        flush()
-        e0.record()
-        iteration(k)
-        e1.record()
-        e1.synchronize()
-        dt = e0.time_till(e1)
-        t_e2e += dt
-        if k % 10 == 0:
-            t_e2e_refresh += dt
-    barrier()
+    e2e = e2e_leg(ctx, args.workload, flush, args.steps, rank, barrier)
+    t_e2e, t_e2e_refresh, e2e_steps, h2d, d2h = (e2e["t_total"], e2e["t_refresh"], e2e["steps"], e2e["h2d"], e2e["d2h"])
     rce = None
     if not args.no_rce:
         legs = rce_leg(ctx, args.workload, seed_offset=rank)
@@ -730,11 +877,15 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                 e2e={"value": world * points * e2e_steps / (t_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e / e2e_steps,
                      "ms_per_step_with_rebuild": t_e2e_refresh / (e2e_steps // 10), "steps": e2e_steps,
-                     "what": "one RT iteration through Compute.* with host buffers, averaged over whole blocks of the "
-                             "reference's schedule (C:851-984): every iteration = T profile H2D from pinned memory, Planck "
-                             "terms, flux solve (all passes), band integration, temperature step, fluxes + profile + "
-                             "convergence flags D2H; every 10th iteration additionally rebuilds opacities, transmission "
-                             "functions and the direct beam (C:860)"},
+                     "launch_calls_per_iteration": e2e["calls"],
+                     "what": "one RT iteration through the public API (BatchCompute with nbatch = 1: iteration counter on "
+                             "the device, the iteration recorded once with ctx.capture() and replayed as a CUDA graph) with "
+                             "host buffers, averaged over whole blocks of the reference's schedule (C:851-984): every "
+                             "iteration = T profile H2D from pinned memory, Planck terms, flux solve (all passes), band "
+                             "integration, temperature step + convergence latch, fluxes + profile + convergence flags D2H; "
+                             "every 10th iteration additionally rebuilds opacities, transmission functions, the direct beam "
+                             "and the sweep plan (C:860).  Same kernels as the eager Compute.* path (bit-identical, "
+                             "tests/test_gpu_batch.py), one host call per iteration instead of ~12"},
                 gpu_launches=int(launches),
                 roofline=_roofline("%s, all %d passes fused" % (_sweep_kernel_name(q), npass),
                                    _bytes_per_cell(q), cells, t_fband / args.steps, npass, args.workload, None,
@@ -745,73 +896,192 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
     return line
 
 
-def cpu_baseline(q_dev, workload):
-    """the NumPy oracle's flux solve on this box's host cores (single process: NumPy ufuncs are single-threaded)"""
-    from oracle.pipeline import HostMirror, OracleCompute
-    m = HostMirror(q_dev)
+def _cpu_worker(job):
+    """one host process of the lambda-sharded CPU baseline: the NumPy oracle's flux solve on this process's share of the
+    wavelength bins (NumPy ufuncs are single-threaded, so the host cores are used by sharding the spectrum)"""
+    workload, rank, world, seconds = job
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from helios_b200 import synthetic, sharding
+    from oracle.pipeline import mirror_from_host, OracleCompute
+    # the Planck table only has to cover the profile: a coarse one keeps the untimed set-up short
+    q = synthetic.make_store(workload, plancktable_dim=800, plancktable_step=10)
+    n = int(q.nlayer)
+    q.T_lay = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+    if world > 1:
+        sharding.shard_store(q, rank, world)
+    m = mirror_from_host(q)
     oc = OracleCompute()
+    m.iter_value = np.int32(0)
+    for stage in ("construct_planck_table", "interpolate_temperatures", "interpolate_planck",
+                  "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass"):
+        getattr(oc, stage)(m)
+    if m.clouds == 1:
+        oc.calc_total_g_0_of_gas_and_clouds(m)
+    oc.calculate_transmission(m)
+    m.dev_z_lay = np.zeros(n)
+    oc.calculate_direct_beamflux(m)
     npass = (3 if m.singlewalk == 0 else 1000) * int(m.scat) + 1
     points = int(m.nlayer) * int(m.nbin) * int(m.ny) * npass
+    oc.populate_spectral_flux_iteratively(m)  # warm-up
     reps, t0 = 0, time.perf_counter()
     while True:
         oc.populate_spectral_flux_iteratively(m)
         oc.integrate_flux(m)
         reps += 1
-        if time.perf_counter() - t0 > 10.0 or reps >= 20:
+        if time.perf_counter() - t0 > seconds:
             break
-    dt = time.perf_counter() - t0
-    return {"value": points * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "%d full %s flux solves (fband x%d + integrate_flux), NumPy fp64 oracle, %.1f s" % (reps, workload, npass, dt)}
+    return points, reps, time.perf_counter() - t0
+
+
+def cpu_baseline(q_dev, workload):
+    """the NumPy oracle's flux solve on this box's host cores: wavelength-sharded over os.cpu_count() processes (each a
+    single-threaded NumPy process on its share of the bins), plus the single-process figure"""
+    import multiprocessing as mp
+    ncores = max(1, min(os.cpu_count() or 1, int(q_dev.nbin)))
+    pts, reps, dt = _cpu_worker((workload, 0, 1, 5.0))
+    single = pts * reps / dt
+    out = {"value": single, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": "%d full %s flux solves, NumPy fp64 oracle, one process, %.1f s" % (reps, workload, dt)}
+    if ncores > 1:
+        try:
+            with mp.get_context("spawn").Pool(ncores) as pool:
+                res = pool.map(_cpu_worker, [(workload, r, ncores, 8.0) for r in range(ncores)])
+            total = sum(p * k for p, k, _ in res) / max(t for _, _, t in res)
+            out = {"value": total, "unit": UNIT, "cores": ncores, "kind": "port", "single_core_value": single,
+                   "sample": "%s flux solve (fband x passes + integrate_flux), NumPy fp64 oracle, wavelength-sharded over %d "
+                             "host processes, %d..%d solves of a %d-bin share each in ~8 s; single process: %.3g points/s"
+                             % (workload, ncores, min(k for _, k, _ in res), max(k for _, k, _ in res),
+                                int(q_dev.nbin) // ncores, single)}
+        except Exception as e:  # noqa: BLE001 -- the single-process figure stands
+            out["multi_process_error"] = repr(e)
+    return out
+
+
+def _ref_inputs(workload, **kw):
+    """host-side inputs of a synthetic run as a plain dict, made in a CHILD process: the reference arm itself never
+    imports helios_b200 (whose synthetic-input generator the child uses) and never maps libhelios_b200.so"""
+    import pickle
+    fd, path = tempfile.mkstemp(suffix=".pkl")
+    os.close(fd)
+    code = ("import sys; sys.path.insert(0, %r); from oracle.refshim import runner; runner.dump_host_store(%r, %r, **%r)"
+            % (ROOT, workload, path, kw))
+    subprocess.run([sys.executable, "-c", code], check=True, stdout=subprocess.DEVNULL)
+    host = pickle.load(open(path, "rb"))
+    os.unlink(path)
+    return host
+
+
+def _reference_mixing(run, driver, local):
+    """C3 through the reference's own species loop (C:1454-1501), as it runs every 10th iteration: per species an H2D of
+    its full k-table, interpolation, random overlap with a single-thread bubble sort per cell (K:3263)"""
+    q, hs = run.q, run.hsfunc
+    sampler = ClockSampler(local)
+    q.iter_value = np.int32(0)
+    run.comp.interpolate_temperatures(q)
+    times = []
+    for k in range(3):
+        hs.calculate_meanmolecularmass(q)
+        hs.nullify_opac_scat_arrays(q)
+        driver.Context.synchronize()
+        t0 = time.perf_counter()
+        run.comp.calculate_total_opacity_and_scat_cross_sections_from_species(q)
+        driver.Context.synchronize()
+        times.append(time.perf_counter() - t0)
+    ms = 1e3 * min(times)
+    cells, nspec = int(q.nlayer) * int(q.nbin), len(q.species_list)
+    emit({"impl": "reference", "metric": "mixed_cells_per_s", "value": cells * nspec / (ms * 1e-3), "unit": "cells/s",
+          "n_gpus": 1, "steps": 3, "warmup": 0, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "config": {"workload": "C3: %d species, %d layers x %d bins x %d gauss points, %s; one species loop of the reference's "
+                                 "computation.py (table H2D + interpolation + mixing per species)" %
+                                 (nspec, q.nlayer, q.nbin, q.ny, q.kcoeff_mixing)},
+          "clocks": sampler.stop()})
 
 
 def run_reference(args):
-    """the reference's kernels.cu on one B200, launch shapes + per-launch syncs of computation.py"""
+    """The reference's stock code path on ONE B200: its unmodified source/computation.py + quantities.py +
+    host_functions.py (byte code in oracle/_ref/helios_py) driving its unmodified kernels.cu (oracle/_ref/helios_ref.cubin)
+    over the PyCUDA stand-in of oracle/refshim -- launch shapes, per-launch device syncs and host round trips exactly as
+    the reference has them.  The reference has no CPU path, so this is "the reference run on the same box" of
+    BASELINE.json:north_star.  This process imports neither helios_b200 nor its shared library."""
     world, rank, local = _dist()
     if rank != 0:
         return
-    from oracle import ref_gpu
-    if not ref_gpu.available():
-        emit({"impl": "reference", "unavailable": "oracle/_ref/helios_ref.cubin was not built (needs /root/reference at build time)"})
+    os.environ.setdefault("REFSHIM_DEVICE", str(local))
+    from oracle.refshim import runner
+    if not runner.available():
+        emit({"impl": "reference", "unavailable": "oracle/_ref (reference cubin + byte-compiled computation.py) was not "
+                                                  "built: needs /root/reference at build time (make -C oracle ref refpy)"})
         return
-    from helios_b200 import backend, runtime
-    ctx = runtime.set_default_context(backend.Context(local))
-    q, comp = _prepare(args.workload, ctx)
-    ref = ref_gpu.RefCompute(local)
-    npass = comp.n_scat_passes(q)
+    workload = args.workload if args.workload in ("C1", "C2", "C3") else "C2"
+    host = _ref_inputs(workload)
+    n = int(host["nlayer"])
+    host["T_lay"] = np.concatenate([2300.0 - 1200.0 * (np.arange(n) / (n - 1.0)) ** 1.5, [2350.0]])
+    run = runner.RefRun(host)
+    from pycuda import driver  # the stand-in (oracle/refshim/pycuda)
+    run.setup()
+    if workload == "C3":
+        return _reference_mixing(run, driver, local)
+    run.prepare_flux_solve()
+    q = run.q
+    npass = (3 if q.singlewalk == 0 else 1000) * int(q.scat) + 1
     points = int(q.nlayer) * int(q.nbin) * int(q.ny) * npass
-    def flush():
-        ctx.call("l2_flush", 1)
+    flush_buf = driver.mem_alloc(256 << 20)
+
+    def flush():  # 2x L2 overwritten; the reference's 6-7 ms step does not notice the write-back of the dirty lines
+        driver.memset_d8(flush_buf, 0, 256 << 20)
+        driver.Context.synchronize()
 
     sampler = ClockSampler(local)
-
-    def flux_solve():
-        ref.populate_spectral_flux_iteratively(q)
-        ref.integrate_flux(q)
-
     for _ in range(max(args.warmup, 3)):
-        flux_solve()
+        run.flux_solve()
     t = 0.0
-    n0 = ref.mod.launches
+    n0 = driver.launches
     for _ in range(args.steps):
         flush()
-        ctx.synchronize()
-        t0 = time.perf_counter()  # the reference syncs the device after every launch, so wall clock == device time
-        flux_solve()
+        t0 = time.perf_counter()  # the reference syncs the device after every launch, so wall clock == its step time
+        run.flux_solve()
         t += time.perf_counter() - t0
+    launches = driver.launches - n0
+    # where the time goes: CUDA events around every launch of two more steps
+    driver.PROFILE = True
+    driver.per_kernel_ms.clear()
+    for _ in range(2):
+        flush()
+        run.flux_solve()
+    driver.PROFILE = False
+    split = {k: {"launches_per_step": c // 2, "ms_per_step": ms / 2} for k, (c, ms) in driver.per_kernel_ms.items()}
     clocks = sampler.stop()
     value = points * args.steps / t
-    emit({
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: %d layers x %d bins x %d gauss points, %d fband launches + integrate_flux_double, "
+        "config": {"workload": "%s: %d layers x %d bins x %d gauss points, %d fband launches + integrate_flux_double through "
+                               "the reference's own computation.py (populate_spectral_flux_iteratively + integrate_flux), "
                                "reference kernels.cu on one B200 (the reference is single-GPU, no CPU path)" %
-                               (args.workload, q.nlayer, q.nbin, q.ny, npass),
-                   "l2": "flushed between timed steps"},
+                               (workload, q.nlayer, q.nbin, q.ny, npass),
+                   "l2": "flushed between timed steps (256 MiB device memset)"},
+        "kernel_split": split,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 0, "kind": "reference",
-                         "sample": "reference kernels.cu (verbatim cubin) on GPU 0; %d launches per step" % ((ref.mod.launches - n0) // args.steps)},
+                         "sample": "reference computation.py + kernels.cu (verbatim cubin) on GPU 0; %d launches per step"
+                                   % (launches // args.steps)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": int(ref.mod.launches - n0), "clocks": clocks})
+        "gpu_launches": int(launches), "clocks": clocks}
+    if not args.no_rce and workload in ("C1", "C2"):
+        # converged atmospheres per hour through the reference's own radiation_loop + convection_loop (C:827-1174)
+        del run
+        gc.collect()
+        rce = runner.RefRun(_ref_inputs(workload))
+        rce.setup()
+        res = rce.rce()
+        line["rce"] = {"atmospheres_per_hour": 3600.0 / res["seconds"], "seconds": res["seconds"], "status": res["status"],
+                       "radiation_iterations": res["radiation_iterations"],
+                       "convection_iterations": res["convection_iterations"], "launches": res["launches"],
+                       "what": "one %s atmosphere from the isothermal start to the reference's convergence criterion through "
+                               "the reference's own radiation_loop + convection_loop, wall clock" % workload}
+    emit(line)
 
 
 _REAL_STDOUT = None
@@ -839,7 +1109,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C4", "C5"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-rce", action="store_true", help="skip the converged-atmospheres-per-hour leg")
     ap.add_argument("--only-main", action="store_true", help="skip the extra workloads (C5 batch, C4 spectrum)")

@@ -71,7 +71,7 @@ def dump_host_store(config, path, **kw):
     q = synthetic.make_store(config, **kw)
     d = {}
     for k, v in vars(q).items():
-        if k.startswith("dev_") or k.startswith("_") or callable(v):
+        if k.startswith("dev_") or k.startswith("_") or isinstance(v, (types.FunctionType, types.MethodType)):
             continue
         if k == "species_list":
             v = [{kk: vv for kk, vv in vars(sp).items()} for sp in v]
