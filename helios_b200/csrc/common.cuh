@@ -77,7 +77,7 @@ struct helios_ctx {
     size_t zero_beam_bytes = 0;
     // sweep plans built by this context (fband_plan.cu): the layout of a plan depends on how it was built (beam rows
     // present or not), so the planned sweeps only accept plans recorded here and not overwritten since
-    helios_plan_info plans[4];
+    std::unordered_map<const void*, helios_plan_info> plans;
     unsigned* integ_ticket = nullptr;  // integrate_flux: blocks finished per (atmosphere, interface)
     size_t integ_ticket_n = 0;
     void* flush_buf = nullptr;  // helios_l2_flush
@@ -153,37 +153,31 @@ static inline void helios_note_write(helios_ctx* ctx, const void* p, size_t nbyt
         const char* z = static_cast<const char*>(ctx->zero_beam[k]);
         if (z != nullptr && lo < z + ctx->zero_beam_bytes && z < lo + nbytes) ctx->zero_beam[k] = nullptr;
     }
-    for (auto& pi : ctx->plans) {
-        const char* z = static_cast<const char*>(pi.ptr);
-        if (z != nullptr && lo < z + pi.bytes && z < lo + nbytes) pi.ptr = nullptr;
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end();) {
+        const char* z = static_cast<const char*>(it->second.ptr);
+        if (lo < z + it->second.bytes && z < lo + nbytes) it = ctx->plans.erase(it);
+        else ++it;
     }
 }
 
 static inline void helios_plan_record(helios_ctx* ctx, const void* ptr, size_t bytes, int kind, int nobeam, int nint,
                                       int ncol) {
-    helios_plan_info* slot = nullptr;
-    for (auto& pi : ctx->plans)
-        if (pi.ptr == ptr) slot = &pi;
-    if (slot == nullptr)
-        for (auto& pi : ctx->plans)
-            if (pi.ptr == nullptr) slot = &pi;
-    if (slot == nullptr) slot = &ctx->plans[0];
-    slot->ptr = ptr;
-    slot->bytes = bytes;
-    slot->kind = kind;
-    slot->nobeam = nobeam;
-    slot->nint = nint;
-    slot->ncol = ncol;
-    slot->nbatch = ctx->batch.nbatch;
+    helios_plan_info& pi = ctx->plans[ptr];
+    pi.ptr = ptr;
+    pi.bytes = bytes;
+    pi.kind = kind;
+    pi.nobeam = nobeam;
+    pi.nint = nint;
+    pi.ncol = ncol;
+    pi.nbatch = ctx->batch.nbatch;
 }
 
 static inline const helios_plan_info* helios_plan_lookup(const helios_ctx* ctx, const void* ptr, int kind, int nint,
                                                          int ncol) {
-    for (const auto& pi : ctx->plans)
-        if (pi.ptr == ptr && ptr != nullptr && pi.kind == kind && pi.nint == nint && pi.ncol == ncol &&
-            pi.nbatch == ctx->batch.nbatch)
-            return &pi;
-    return nullptr;
+    auto it = ctx->plans.find(ptr);
+    if (it == ctx->plans.end()) return nullptr;
+    const helios_plan_info& pi = it->second;
+    return (pi.kind == kind && pi.nint == nint && pi.ncol == ncol && pi.nbatch == ctx->batch.nbatch) ? &pi : nullptr;
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -39,38 +39,54 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     double* s_up = sm + (size_t)xb * pitch;
     double* s_dr = sm + (size_t)2 * xb * pitch;
     const int i = blockIdx.y;
-    const int x0 = blockIdx.x * xb;
-    const int nx = min(xb, nbin - x0);
     {   // batch (blockIdx.z = atmosphere): [i][x][y] and [i][x] arrays both hold gridDim.y = ninterface rows
         const size_t wg = (size_t)blockIdx.z * gridDim.y * nbin * ny, bd = (size_t)blockIdx.z * gridDim.y * nbin;
         F_down_wg += wg; F_up_wg += wg; F_dir_wg += wg;
         F_down_band += bd; F_up_band += bd; F_dir_band += bd;
     }
-    const size_t base = ((size_t)i * nbin + x0) * ny;
-    const int n = nx * ny;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const int xl = k / ny, y = k - xl * ny;
-        const int d = xl * pitch + y;
-        s_dn[d] = F_down_wg[base + k];
-        s_up[d] = F_up_wg[base + k];
-        s_dr[d] = F_dir_wg[base + k];
-    }
-    __syncthreads();
-    double t_up = 0.0, t_dn = 0.0;  // this thread's bin in the sum over wavelength (xb <= blockDim.x: one bin each)
-    for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
-        double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
-        for (int y = 0; y < ny; y++) {
-            const double hw = 0.5 * gauss_weight[y];
-            a_dr += hw * s_dr[xl * pitch + y];
-            a_up += hw * s_up[xl * pitch + y];
-            a_dn += hw * s_dn[xl * pitch + y];
+    // A block walks the x-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its interface (wide spectra: 1e5 bins are
+    // ~400 tiles; a block per tile would be ~40,000 blocks of two barriers-and-a-ticket each) and keeps its share of the
+    // wavelength integral in registers across them.
+    double t_up = 0.0, t_dn = 0.0;  // this thread's bins in the sum over wavelength
+    const int ntiles = (nbin + xb - 1) / xb;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int x0 = tile * xb;
+        const int nx = min(xb, nbin - x0);
+        const size_t base = ((size_t)i * nbin + x0) * ny;
+        if (ny > 1) {
+            const int n = nx * ny;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int xl = k / ny, y = k - xl * ny;
+                const int d = xl * pitch + y;
+                s_dn[d] = F_down_wg[base + k];
+                s_up[d] = F_up_wg[base + k];
+                s_dr[d] = F_dir_wg[base + k];
+            }
+            __syncthreads();
         }
-        const size_t o = (size_t)i * nbin + x0 + xl;
-        F_dir_band[o] = a_dr;
-        F_up_band[o] = a_up;
-        F_down_band[o] = a_dn;
-        t_up += a_up * deltalambda[x0 + xl];
-        t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
+        for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
+            double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
+            if (ny > 1) {
+                for (int y = 0; y < ny; y++) {
+                    const double hw = 0.5 * gauss_weight[y];
+                    a_dr += hw * s_dr[xl * pitch + y];
+                    a_up += hw * s_up[xl * pitch + y];
+                    a_dn += hw * s_dn[xl * pitch + y];
+                }
+            } else {  // opacity sampling: one point per bin, consecutive threads read consecutive bins
+                const double hw = 0.5 * gauss_weight[0];
+                a_dr += hw * F_dir_wg[base + xl];
+                a_up += hw * F_up_wg[base + xl];
+                a_dn += hw * F_down_wg[base + xl];
+            }
+            const size_t o = (size_t)i * nbin + x0 + xl;
+            F_dir_band[o] = a_dr;
+            F_up_band[o] = a_up;
+            F_down_band[o] = a_dn;
+            t_up += a_up * deltalambda[x0 + xl];
+            t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
+        }
+        if (ny > 1) __syncthreads();  // the next tile overwrites the staging area
     }
     // Sum over wavelength in the same launch (K:2484-2509): fixed tree over this block's bins, then the LAST block
     // of the interface to finish adds the per-block partial sums in block order -- a fixed summation order, bitwise
@@ -505,8 +521,13 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
     }
     const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
-    const int ntile = ceil_div(nbin, xb);
     const int nb = ctx->batch.nbatch;
+    // blocks per (atmosphere, interface): one per x-tile while that keeps a single atmosphere's grid within ~8 blocks per
+    // SM, else a block walks several tiles.  Independent of the batch size: the summation order of an atmosphere is the
+    // same alone and in a batch (bit-for-bit equality of the two paths, tests/test_gpu_batch.py).
+    int ntile = ceil_div(nbin, xb);
+    const int cap = ctx->num_sms * 8 / numinterfaces;
+    if (ntile > cap) ntile = cap < 1 ? 1 : cap;
     dim3 grid(ntile, numinterfaces, nb);
     // per-block partial sums (transient, scratch) and one ticket per (atmosphere, interface) (persistent, zeroed)
     double* scratch = nullptr;

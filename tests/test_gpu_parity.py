@@ -557,3 +557,38 @@ def test_planned_sweep_refuses_a_foreign_plan(ctx):
     q.dev_fband_plan.set(q.dev_fband_plan.get())  # a write from outside: the record is dropped
     with pytest.raises(backend.HeliosError):
         comp.populate_spectral_flux_iteratively(q)
+
+
+@pytest.mark.parametrize("kernel", ["rad_temp_iteration", "conv_temp_iteration"])
+def test_temperature_step_with_smoothing(ctx, kernel):
+    """smooth == 1 (K:2656-2669, K:2806): the smoothing force pow(T_mid - T, 7) and its running sum.  The reference sums
+    F_smooth across its 16-thread blocks without a grid sync (a race once nlayer > 16); with <= 16 layers its
+    kernel is one block and well defined, which is where it is compared (1e-10).  For more layers the product's one-block
+    kernel is held to the NumPy oracle, which follows the source's intended order."""
+    from util import HostMirror
+    for nlayer, use_ref in ((14, True), (24, False)):
+        q = synthetic.make_store("C2", ctx=ctx, **dict(SMALL, nlayer=nlayer))
+        q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
+        q.smooth = np.int32(1)
+        rng = np.random.default_rng(5)
+        n = int(q.nlayer)
+        q.T_lay = np.concatenate([np.linspace(2300.0, 900.0, n) + rng.uniform(-60, 60, n), [2400.0]])
+        synthetic.upload(q)
+        comp, oc = Compute(ctx, verbose=False), OracleCompute()
+        q.iter_value = np.int32(0)
+        for m in ["construct_planck_table", "correct_incident_energy", "interpolate_temperatures", "interpolate_planck",
+                  "interpolate_opacities_and_scattering_cross_sections", "interpolate_meanmolmass",
+                  "calc_total_g_0_of_gas_and_clouds", "calculate_transmission", "calculate_direct_beamflux",
+                  "populate_spectral_flux_iteratively", "integrate_flux"]:
+            getattr(comp, m)(q)
+        if kernel == "conv_temp_iteration":
+            marked = np.zeros(n + 1, np.int32)
+            marked[n // 2] = 1
+            comp._upload(q, "marked_red", marked)
+            comp._upload(q, "conv_layer", np.zeros(n + 1, np.int32))
+        outs = ["T_lay", "F_smooth", "F_smooth_sum", "F_net_diff"] + (["abort"] if kernel == "rad_temp_iteration" else [])
+        q.iter_value = np.int32(3)
+        if use_ref and ref_gpu.available():
+            stage_vs_ref(q, comp, ref_gpu.RefCompute(ctx.device), kernel, outs)
+        stage_vs_oracle(q, comp, oc, kernel, outs)
+        assert np.any(q.dev_F_smooth.get() != 0.0), "the smoothing branch did not run"
