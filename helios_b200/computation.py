@@ -31,6 +31,12 @@ class Compute(object):
         # (helios_fband_noniso_plan_build) and run the planned sweep in the iterations in between
         self.use_flux_plan = True
         self.use_iso_plan = True  # the same for isothermal layers (helios_fband_iso_plan_build)
+        # convective adjustment, convective marking + radiative-equilibrium test and the on-the-fly
+        # VMR / mean-molecular-mass interpolation as device kernels (csrc/convect.cu) instead of the host functions with
+        # their ~12 transfers per iteration.  Used when the host module is helios_b200.host; with the reference's
+        # unchanged host_functions.py (drop-in) its own host path runs, as the drop-in contract asks.
+        self.device_convection = hsfunc is None
+        self.device_vmr = hsfunc is None
         self.stats = {"iterations": 0}
         backend.lib()  # fail loudly right here if the CUDA library is missing
 
@@ -307,8 +313,11 @@ class Compute(object):
             self.interpolate_opacities_and_scattering_cross_sections(quant)
             self.interpolate_meanmolmass(quant)
         elif quant.opacity_mixing == "on-the-fly":
-            hs.calculate_vmr_for_all_species(quant)
-            hs.calculate_meanmolecularmass(quant)
+            if self.device_vmr:
+                self.calculate_vmr_and_meanmolmass_on_device(quant)
+            else:
+                hs.calculate_vmr_for_all_species(quant)
+                hs.calculate_meanmolecularmass(quant)
             hs.nullify_opac_scat_arrays(quant)
             self.calculate_total_opacity_and_scat_cross_sections_from_species(quant)
         if quant.clouds == 1:
@@ -442,6 +451,12 @@ class Compute(object):
         if quant.iso == 0:
             quant.kappa_int = quant.dev_kappa_int.get()
 
+    def _pull_convection_state(self, quant):
+        """host copies of what the output writers and the feedback prints read after / during the device-side loop"""
+        q = quant
+        for name in ("T_lay", "F_net", "F_down_tot", "F_up_tot", "F_net_diff", "F_smooth_sum", "conv_layer", "marked_red"):
+            setattr(q, name, getattr(q, "dev_" + name).get())
+
     def convection_loop(self, quant, write, read, rt_plot):
         """loops interchangeably through the radiative and convection schemes"""
         if not (quant.singlewalk == 0 and quant.convection == 1):
@@ -473,7 +488,26 @@ class Compute(object):
         quant.F_up_tot = quant.dev_F_up_tot.get()
         quant.F_down_tot = quant.dev_F_down_tot.get()
 
+        if self.device_convection and quant.iso == 0:
+            self._convection_buffers(quant)
+            quant.dev_conv_layer.set(np.asarray(quant.conv_layer, np.int32))
         running = unstable
+        try:
+            self._convection_iterations(quant, write, read, rt_plot, running, ev_loop)
+        finally:
+            if self.device_convection and quant.iso == 0 and unstable:
+                self._pull_convection_state(quant)  # also when the iteration guard ends the run (C:1157-1164)
+        ev_total[1].record()
+        ev_total[1].synchronize()
+        self.stats["convection_loop_ms"] = ev_total[0].time_till(ev_total[1])
+        self.stats["convection_iterations"] = int(quant.iter_value)
+        self._say("\nTime for rad.-conv. iteration [s]: {:.2f}".format(self.stats["convection_loop_ms"] * 1e-3))
+        self._say("Total number of iterative steps: " + str(quant.iter_value))
+
+    def _convection_iterations(self, quant, write, read, rt_plot, running, ev_loop):
+        """the body of the radiative-convective loop (C:1030-1164)"""
+        hs = self.hsfunc
+        time_loop = 0.0
         while running:
             it = int(quant.iter_value)
             if it % 100 == 0:
@@ -482,21 +516,30 @@ class Compute(object):
                 if it > 99:
                     self._say("Time for the last 100 steps [s]: {:.2f}".format(time_loop * 1e-3))
 
-            # 1. convective adjustment on the host
+            on_device = self.device_convection and quant.iso == 0
+            # 1. convective adjustment
             self.interpolate_temperatures(quant)
             if it % 10 == 0:
                 if quant.opacity_mixing == "premixed":
                     self.interpolate_meanmolmass(quant)
                 elif quant.opacity_mixing == "on-the-fly":
-                    hs.calculate_vmr_for_all_species(quant)
-                    hs.calculate_meanmolecularmass(quant)
-            self._fetch_kappa(quant)
-            quant.c_p_lay = quant.dev_c_p_lay.get()
-            quant.meanmolmass_lay = quant.dev_meanmolmass_lay.get()
-            quant.T_lay = quant.dev_T_lay.get()
-            quant.F_smooth_sum = quant.dev_F_smooth_sum.get()
-            hs.convective_adjustment(quant)
-            quant.dev_T_lay.set(quant.T_lay)
+                    if self.device_vmr:
+                        self.calculate_vmr_and_meanmolmass_on_device(quant)
+                    else:
+                        hs.calculate_vmr_for_all_species(quant)
+                        hs.calculate_meanmolecularmass(quant)
+            if on_device:
+                # one launch on resident arrays instead of six transfers and the host loops of H:337-538
+                self.interpolate_kappa_and_cp(quant)
+                self.convective_adjustment_on_device(quant)
+            else:
+                self._fetch_kappa(quant)
+                quant.c_p_lay = quant.dev_c_p_lay.get()
+                quant.meanmolmass_lay = quant.dev_meanmolmass_lay.get()
+                quant.T_lay = quant.dev_T_lay.get()
+                quant.F_smooth_sum = quant.dev_F_smooth_sum.get()
+                hs.convective_adjustment(quant)
+                quant.dev_T_lay.set(quant.T_lay)
 
             # 2. radiative fluxes for the adjusted profile
             self.interpolate_temperatures(quant)
@@ -504,21 +547,35 @@ class Compute(object):
             if it % 10 == 0:
                 self._refresh_atmosphere(quant)
             self._flux_solve(quant)
-            quant.F_net = quant.dev_F_net.get()
-            quant.F_down_tot = quant.dev_F_down_tot.get()
-            quant.F_up_tot = quant.dev_F_up_tot.get()
-            quant.F_net_diff = quant.dev_F_net_diff.get()
 
             # 3. mark the convective zones for the convergence test
-            self._fetch_kappa(quant)
-            quant.T_lay = quant.dev_T_lay.get()
-            hs.mark_convective_layers(quant, stitching=1)
-            if quant.physical_tstep != 0:
-                break
-            quant.F_smooth_sum = quant.dev_F_smooth_sum.get()
-            running = (not hs.check_for_radiative_eq(quant)) or (it < 400) or (sum(quant.conv_layer) == 0)
-            if it % 100 == 1 and self.verbose:
-                hs.give_feedback_on_convergence(quant)
+            if on_device:
+                self.interpolate_kappa_and_cp(quant)
+                n_conv_ok, n_rad, n_conv, zero_T = self.convection_marks_on_device(quant)
+                if zero_T:
+                    print("WARNING WARNING WARNING: Found zero temperature in", zero_T, "layer(s)")
+                if quant.physical_tstep != 0:
+                    break
+                if it % 100 == 1:
+                    self._say("Number of radiative layers converged: {:d} out of {:d}.".format(n_conv_ok, n_rad))
+                running = (n_conv_ok != n_rad) or (it < 400) or (n_conv == 0)
+                if it % 100 == 1 and self.verbose:
+                    self._pull_convection_state(quant)
+                    hs.give_feedback_on_convergence(quant)
+            else:
+                quant.F_net = quant.dev_F_net.get()
+                quant.F_down_tot = quant.dev_F_down_tot.get()
+                quant.F_up_tot = quant.dev_F_up_tot.get()
+                quant.F_net_diff = quant.dev_F_net_diff.get()
+                self._fetch_kappa(quant)
+                quant.T_lay = quant.dev_T_lay.get()
+                hs.mark_convective_layers(quant, stitching=1)
+                if quant.physical_tstep != 0:
+                    break
+                quant.F_smooth_sum = quant.dev_F_smooth_sum.get()
+                running = (not hs.check_for_radiative_eq(quant)) or (it < 400) or (sum(quant.conv_layer) == 0)
+                if it % 100 == 1 and self.verbose:
+                    hs.give_feedback_on_convergence(quant)
 
             # 4. radiative forward step where the local criterion is not met
             if running:
@@ -528,10 +585,12 @@ class Compute(object):
                     hs.calc_add_heating_flux(quant)
                     self._upload(quant, "F_add_heat_lay", quant.F_add_heat_lay)
                     self._upload(quant, "F_add_heat_sum", quant.F_add_heat_sum)
-                self._upload(quant, "conv_layer", np.asarray(quant.conv_layer, np.int32))
-                self._upload(quant, "marked_red", np.asarray(quant.marked_red, np.int32))
+                if not on_device:
+                    self._upload(quant, "conv_layer", np.asarray(quant.conv_layer, np.int32))
+                    self._upload(quant, "marked_red", np.asarray(quant.marked_red, np.int32))
                 self.conv_temp_iteration(quant)
-                quant.T_lay = quant.dev_T_lay.get()
+                if not on_device:
+                    quant.T_lay = quant.dev_T_lay.get()
                 if it % 100 == 99:
                     ev_loop[1].record()
                     ev_loop[1].synchronize()
@@ -550,12 +609,6 @@ class Compute(object):
                 print("\nRun exceeds allowed maximum allowed number of iteration steps. Aborting...")
                 raise SystemExit()
 
-        ev_total[1].record()
-        ev_total[1].synchronize()
-        self.stats["convection_loop_ms"] = ev_total[0].time_till(ev_total[1])
-        self.stats["convection_iterations"] = int(quant.iter_value)
-        self._say("\nTime for rad.-conv. iteration [s]: {:.2f}".format(self.stats["convection_loop_ms"] * 1e-3))
-        self._say("Total number of iterative steps: " + str(quant.iter_value))
 
     # ------------------------------------------------------------------ post-processing (C:1176-1296)
     def integrate_optdepth_transmission(self, quant):
@@ -642,10 +695,16 @@ class Compute(object):
 
     def calculate_total_opacity_and_scat_cross_sections_from_species(self, quant):
         q = quant
+        on_dev = getattr(q, "_vmr_on_device", None)
         for s, sp in enumerate(q.species_list):
-            self._upload(q, "vmr_spec_lay", np.asarray(sp.vmr_layer, np.float64))
-            if q.iso == 0:
-                self._upload(q, "vmr_spec_int", np.asarray(sp.vmr_interface, np.float64))
+            if on_dev is not None:
+                q.dev_vmr_spec_lay = on_dev[s][0]  # interpolated on the device: nothing to upload (C:1461-1463)
+                if q.iso == 0:
+                    q.dev_vmr_spec_int = on_dev[s][1]
+            else:
+                self._upload(q, "vmr_spec_lay", np.asarray(sp.vmr_layer, np.float64))
+                if q.iso == 0:
+                    self._upload(q, "vmr_spec_int", np.asarray(sp.vmr_interface, np.float64))
             if sp.absorbing == "yes":
                 q.dev_opacity_spec_pretab = self._resident(("k", s), sp.opacity_pretab)
                 self.interpolate_species_opac(q)
@@ -668,6 +727,69 @@ class Compute(object):
                     if q.iso == 0:
                         q.dev_scat_cross_spec_int = self._resident(("si", s), sp.scat_cross_sect_interface)
                 self.add_to_mixed_scat_cross_sect(q)
+
+
+    # ------------------------------------------------------------------ device-side host functions (csrc/convect.cu)
+    def calculate_vmr_and_meanmolmass_on_device(self, quant):
+        """H:874-924 without leaving the device: per species the VMR profile (bilinear in (T, log10 P) for FastChem-tabulated
+        species, the given constant profile otherwise) and the VMR-weighted mean molecular mass.  The per-species
+        profiles stay resident; the species loop (C:1454-1501) then takes them from there."""
+        q = quant
+        nl, ni = int(q.nlayer), int(q.ninterface)
+        levels = [("lay", q.dev_T_lay, q.dev_p_lay, nl)] + ([("int", q.dev_T_int, q.dev_p_int, ni)] if q.iso == 0 else [])
+        cache = getattr(q, "_vmr_on_device", None)
+        if cache is None or len(cache) != len(q.species_list):
+            cache = [[None, None] for _ in q.species_list]
+        scratch = getattr(q, "_mmm_scratch", None)
+        if scratch is None:
+            scratch = q._mmm_scratch = [self.ctx.zeros(ni), self.ctx.zeros(ni)]
+        for k, (tag, dT, dP, n) in enumerate(levels):
+            scratch[0].fill_zero()
+            scratch[1].fill_zero()
+            for s, sp in enumerate(q.species_list):
+                if getattr(sp, "source_for_vmr", None) == "FastChem":
+                    if cache[s][k] is None or cache[s][k].size != n:
+                        cache[s][k] = self.ctx.zeros(n)
+                    table = self._resident(("vmr", s), sp.vmr_pretab)
+                    self.ctx.call("vmr_interpol", dT, dP, q.dev_ktemp, q.dev_kpress, table, cache[s][k], q.npress, q.ntemp, n)
+                else:
+                    host = sp.vmr_layer if tag == "lay" else sp.vmr_interface
+                    cache[s][k] = self._resident(("vmr_" + tag, s), host)
+                if "CIA" in sp.name or sp.name in ("H-_ff", "He-"):
+                    continue  # not part of the mean molecular mass (H:941-943)
+                self.ctx.call("meanmolmass_accumulate", cache[s][k], float(sp.weight), scratch[0], scratch[1], n)
+            out = q.dev_meanmolmass_lay if tag == "lay" else q.dev_meanmolmass_int
+            self.ctx.call("meanmolmass_finish", scratch[0], scratch[1], out, n)
+        q._vmr_on_device = cache
+
+    def _convection_buffers(self, quant):
+        q = quant
+        n1 = int(q.nlayer) + 1
+        for name in ("conv_layer", "conv_unstable", "marked_red"):
+            dev = getattr(q, "dev_" + name, None)
+            if not isinstance(dev, backend.DeviceArray) or dev.size != n1 or dev.dtype != np.int32:
+                setattr(q, "dev_" + name, self.ctx.zeros(n1, np.int32))
+        if getattr(q, "_conv_status", None) is None:
+            q._conv_status = self.ctx.zeros(8, np.int32)
+
+    def convective_adjustment_on_device(self, quant):
+        """H:509-538 in one launch; returns nothing (the status words stay on the device until asked for)"""
+        q = quant
+        dampara = -1.0 if q.input_dampara == "automatic" else float(q.input_dampara)
+        self.ctx.call("convective_adjustment", q.dev_T_lay, q.dev_p_lay, q.dev_p_int, q.dev_kappa_lay, q.dev_kappa_int,
+                      q.dev_c_p_lay, q.dev_meanmolmass_lay, q.dev_F_add_heat_sum, q.dev_F_smooth_sum, q.dev_F_down_tot,
+                      q.dev_F_up_tot, q.dev_conv_layer, q.dev_conv_unstable, q._conv_status, q.F_intern, q.T_star, dampara,
+                      q.iter_value, q.nlayer)
+
+    def convection_marks_on_device(self, quant):
+        """H:545-582 (stitching = 1) + H:251-286; returns (converged radiative layers, radiative layers, convective layers)"""
+        q = quant
+        self.ctx.call("convection_marks", q.dev_T_lay, q.dev_p_lay, q.dev_p_int, q.dev_kappa_lay, q.dev_kappa_int,
+                      q.dev_F_net, q.dev_F_down_tot, q.dev_F_add_heat_sum, q.dev_F_smooth_sum, q.dev_conv_layer,
+                      q.dev_marked_red, q._conv_status.view(4, 4), q.F_intern, q.rad_convergence_limit, q.iter_value,
+                      q.nlayer)
+        st = q._conv_status.get()
+        return int(st[4]), int(st[5]), int(st[6]), int(st[7])
 
 
 def _amu(hsfunc):

@@ -334,8 +334,9 @@ def interpolate_grid_to_lay_or_int(log_press, temp, vmr_2D, log_press_profile, t
     kx = ky = 1 is exactly piecewise-bilinear interpolation, clamped at the grid edges)"""
     temp = np.asarray(temp, np.float64)
     log_press = np.asarray(log_press, np.float64)
-    t = np.clip(np.asarray(temp_profile, np.float64), temp[0], temp[-1])
     p = np.clip(np.asarray(log_press_profile, np.float64), log_press[0], log_press[-1])
+    # the reference walks range(len(log_press_profile)) (H:908): T_lay carries the surface as an extra last entry
+    t = np.clip(np.asarray(temp_profile, np.float64)[:p.size], temp[0], temp[-1])
     it = np.clip(np.searchsorted(temp, t, side="right") - 1, 0, temp.size - 2)
     ip = np.clip(np.searchsorted(log_press, p, side="right") - 1, 0, log_press.size - 2)
     ft = (t - temp[it]) / (temp[it + 1] - temp[it])

@@ -405,6 +405,40 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
  * device into *sum_dev (device int).  B200-side addition, no reference kernel. */
 int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev);
 
+/* ------------------------------------------------------------------ device-side host functions */
+
+/* host_functions.py:509-538 convective_adjustment (conv_check / mark_convective_layers / conv_correct to stability, then
+ * the damped correction), one launch instead of the reference's host round trips (C:1053-1062).  T_lay (nlayer + 1,
+ * index nlayer = surface) and conv_layer are updated in place; conv_unstable and status_dev[4] = {adjustment cycles,
+ * convective zones, instability found at entry, 1 if the cycle limit was hit} are outputs.  dampara <= 0: "automatic"
+ * (H:441-449).  B200-side addition: the reference has no kernel for this. */
+int helios_convective_adjustment(helios_ctx* ctx, double* T_lay, const double* p_lay, const double* p_int,
+                                 const double* kappa_lay, const double* kappa_int, const double* c_p_lay,
+                                 const double* meanmolmass_lay, const double* F_add_heat_sum, const double* F_smooth_sum,
+                                 const double* F_down_tot, const double* F_up_tot, int* conv_layer, int* conv_unstable,
+                                 int* status_dev, double F_intern, double T_star, double dampara, int iter_value,
+                                 int nlayer);
+
+/* host_functions.py:545-582 mark_convective_layers(stitching = 1) followed by H:251-286 check_for_radiative_eq, after the
+ * flux solve of a radiative-convective iteration (C:1093-1115).  status_dev[4] = {radiative layers converged, radiative
+ * layers, convective layers, layers with T == 0}. */
+int helios_convection_marks(helios_ctx* ctx, const double* T_lay, const double* p_lay, const double* p_int,
+                            const double* kappa_lay, const double* kappa_int, const double* F_net,
+                            const double* F_down_tot, const double* F_add_heat_sum, const double* F_smooth_sum,
+                            int* conv_layer, int* marked_red, int* status_dev, double F_intern,
+                            double rad_convergence_limit, int iter_value, int nlayer);
+
+/* host_functions.py:874-910: a species' pre-tabulated VMR [ntemp][npress] interpolated bilinearly in (T, log10 P), clamped
+ * at the grid edges, along a profile of n points (the reference: scipy RectBivariateSpline(kx = ky = 1) per layer). */
+int helios_vmr_interpol(helios_ctx* ctx, const double* temp, const double* press, const double* ktemp,
+                        const double* kpress, const double* vmr_pretab, double* vmr_out, int npress, int ntemp, int n);
+
+/* host_functions.py:927-959 calc_meanmolmass on the device: sum_weighted += vmr * weight, sum_vmr += vmr per species, then
+ * meanmolmass = sum_weighted / sum_vmr * AMU */
+int helios_meanmolmass_accumulate(helios_ctx* ctx, const double* vmr, double weight, double* sum_weighted, double* sum_vmr,
+                                  int n);
+int helios_meanmolmass_finish(helios_ctx* ctx, const double* sum_weighted, const double* sum_vmr, double* meanmolmass, int n);
+
 /* ------------------------------------------------------------------ post-processing ---------- */
 
 /* K:2888 / K:2916, C:1180-1212 */

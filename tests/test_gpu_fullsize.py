@@ -240,4 +240,5 @@ def test_full_size_batch_of_128(ctx):
             assert np.array_equal(qb.atmosphere(name, b), getattr(q, "dev_" + name).get()), (b, name)
     # ... and a single of the batch against the reference's kernel
     q = singles[1]
+    q._flux_plan_valid = False  # (stage_vs_ref rewrites every buffer, which drops the plan record: the unplanned sweep)
     stage_vs_ref(q, comp, ref, "populate_spectral_flux_iteratively", ["F_down_wg", "F_up_wg"])
