@@ -588,6 +588,41 @@ def rce_leg(ctx, workload, seed_offset=0):
     return out
 
 
+def convection_leg(ctx, n_iter=400):
+    """The radiative-convective loop (C:992-1174) actually iterating: the C2 atmosphere from a super-adiabatic start
+    profile, first `n_iter` iterations (the synthetic opacities give no C2 variant whose convective loop converges --
+    with T_intern >= 200 K it runs into the iteration limit with the product's and with the reference's kernels alike --
+    so the loop BODY is timed).  host path: convective adjustment, marking and equilibrium test as host functions with
+    their ~12 transfers per iteration (the reference's structure); device path: csrc/convect.cu, 16 bytes per iteration."""
+    from helios_b200 import synthetic
+    from helios_b200.computation import Compute
+    out = {}
+    for mode in ("host_functions", "device_kernels"):
+        q = synthetic.make_store("C2", ctx=ctx)
+        p = np.asarray(q.p_lay)
+        T = np.maximum(3200.0 * (p / p[0]) ** 0.45, 900.0)  # steeper than the dry adiabat (kappa = 2/7) at depth
+        q.T_lay = np.append(T, T[0] * 1.05)
+        q.max_nr_iterations = n_iter
+        synthetic.upload(q)
+        comp = Compute(ctx, verbose=False)
+        comp.device_convection = mode == "device_kernels"
+        comp.construct_planck_table(q)
+        comp.correct_incident_energy(q)
+        _quiesce(ctx)
+        t0 = time.perf_counter()
+        try:
+            comp.convection_loop(q, None, None, None)
+        except SystemExit:
+            pass
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        gc.enable()
+        out[mode] = {"iterations": int(q.iter_value), "seconds": dt, "ms_per_iteration": 1e3 * dt / max(1, int(q.iter_value)),
+                     "convective_layers": int(np.sum(q.conv_layer))}
+    out["what"] = convection_leg.__doc__.split("\n")[0].strip()
+    return out
+
+
 def rce_batch(ctx, nbatch=32):
     """the same for a grid of C1 atmospheres advanced together (one launch per kernel for the whole batch)"""
     from helios_b200 import synthetic, sharding
@@ -864,6 +899,11 @@ def _run_single(args, ctx, flush, base, l2, world, rank, barrier, reduce_max):
                         "(rad_convergence_limit 1e-8): radiation loop on the device (CUDA-graph blocks of 10 iterations) + "
                         "convection loop, wall clock incl. host logic; host_loop = the reference's loop structure; each the "
                         "faster of two runs" % args.workload)
+        if rank == 0 and world == 1:
+            try:
+                rce["convection_loop"] = convection_leg(ctx)
+            except Exception as e:  # noqa: BLE001
+                rce["convection_loop"] = {"error": repr(e)}
     t_solve, t_fband, t_e2e = reduce_max([t_solve, t_fband, t_e2e])
     line = dict(base, value=world * points * args.steps / (t_solve * 1e-3), ms_per_step=t_solve / args.steps,
                 scaling="weak",

@@ -1,6 +1,11 @@
 // Planck table, stellar energy correction, temperature / Planck / opacity interpolation.
 // From-scratch sm_100a kernels for K:362-1011 and K:3209-3259 of the reference.
 #include "common.cuh"
+#include <cstdlib>
+
+#ifndef PT_GATHER_TMA_DEFAULT
+#define PT_GATHER_TMA_DEFAULT 0  // measured on B200: 35.8 us staged vs 31.7 us streamed for the C2 refresh
+#endif
 
 // ------------------------------------------------------------------------------------------
 // Planck table (K:362-416).  One thread per table entry (x, row); rows 0..dim-1 have
@@ -276,7 +281,7 @@ k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, dou
         const size_t a = blockIdx.z;
         const size_t which = table_index ? (size_t)table_index[a] : 0;
         box += a * (size_t)n;
-        table += which * tstride;
+        if (table != nullptr) table += which * tstride;
         out += a * ostride;
         if (table2 != nullptr) {
             table2 += which * tstride2;
@@ -288,7 +293,7 @@ k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, dou
     const size_t r_ud = (size_t)b.pup + (size_t)npress * b.tdown;
     const size_t r_du = (size_t)b.pdown + (size_t)npress * b.tup;
     const size_t r_uu = (size_t)b.pup + (size_t)npress * b.tup;
-    {
+    if (table != nullptr) {
         const double* __restrict__ t_dd = table + r_dd * rowlen;
         const double* __restrict__ t_ud = table + r_ud * rowlen;
         const double* __restrict__ t_du = table + r_du * rowlen;
@@ -306,6 +311,62 @@ k_pt_gather(const PTBox* __restrict__ box, const double* __restrict__ table, dou
         for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < rowlen2; c += gridDim.x * blockDim.x)
             o[c] = bilin4(__ldg(t_dd + c), __ldg(t_ud + c), __ldg(t_du + c), __ldg(t_uu + c), b);
     }
+}
+
+// The same gather with the table rows staged through shared memory by TMA (north_star: "tables staged through
+// TMA/shared memory for the interpolation gathers").  A CTA owns one chunk of GT_CHUNK columns of one layer: one thread
+// requests the chunk of each of the four rows of the layer's (P, T) box as a cp.async.bulk copy (SASS UBLKCP) that
+// completes on an mbarrier; the block then combines them from shared memory and stores the output row coalesced.
+// Rows start at r * rowlen doubles: the 16-byte alignment TMA needs holds for even rowlen (else the LDG form above).
+constexpr int GT_CHUNK = 1024;
+
+__global__ void __launch_bounds__(128)
+k_pt_gather_tma(const PTBox* __restrict__ box, const double* __restrict__ table, double* __restrict__ out, int rowlen,
+                int npress, int n, const int* __restrict__ table_index, size_t tstride, size_t ostride) {
+    __shared__ __align__(16) double rows[4][GT_CHUNK];
+    __shared__ __align__(8) unsigned long long bar;
+    const int i = blockIdx.y;
+    {
+        const size_t a = blockIdx.z;
+        box += a * (size_t)n;
+        table += (table_index ? (size_t)table_index[a] : 0) * tstride;
+        out += a * ostride;
+    }
+    const PTBox b = box[i];
+    const int c0 = blockIdx.x * GT_CHUNK;
+    const int len = min(GT_CHUNK, rowlen - c0);
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const size_t r[4] = {(size_t)b.pdown + (size_t)npress * b.tdown, (size_t)b.pup + (size_t)npress * b.tdown,
+                             (size_t)b.pdown + (size_t)npress * b.tup, (size_t)b.pup + (size_t)npress * b.tup};
+        const unsigned bytes = (unsigned)len * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&rows[k][0]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(table + r[k] * rowlen + c0), "r"(bytes), "r"(bar_s)
+                         : "memory");
+        }
+    }
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar_s),
+        "r"(0u)
+        : "memory");
+    double* __restrict__ o = out + (size_t)i * rowlen + c0;
+    for (int c = threadIdx.x; c < len; c += blockDim.x) o[c] = bilin4(rows[0][c], rows[1][c], rows[2][c], rows[3][c], b);
 }
 
 // scalar tables tab[p + npress*t] (K:649-919)
@@ -439,6 +500,14 @@ int helios_iteration_prepare(helios_ctx* ctx, const double* tlay, double* tint, 
     return HELIOS_OK;
 }
 
+static int g_pt_gather_tma = -1;  // -1: not decided yet (environment / default), 0: streamed, 1: TMA-staged
+
+extern "C" int helios_set_pt_gather_tma(int on) {
+    const int before = g_pt_gather_tma;
+    g_pt_gather_tma = on < 0 ? -1 : (on ? 1 : 0);
+    return before;
+}
+
 static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gtemp, const double* press,
                            const double* gpress, const double* table, double* out, int rowlen,
                            const double* table2, double* out2, int rowlen2, int npress, int ntemp, int n,
@@ -455,6 +524,21 @@ static int pt_table_interp(helios_ctx* ctx, const double* temp, const double* gt
     k_pt_prep<<<dim3(ceil_div(n, 128), nb), 128, 0, ctx->stream>>>(temp, press, gtemp, gpress, ntemp, npress, n,
                                                                    clamp_mode, 0, box, tstride);
     HLAUNCHED(ctx);
+    // HELIOS_PT_GATHER: "tma" = table rows staged by cp.async.bulk (k_pt_gather_tma), "ldg" = streamed with __ldg;
+    // default: see the measurement in DESIGN.md 6b
+    if (g_pt_gather_tma < 0) {
+        const char* e = getenv("HELIOS_PT_GATHER");
+        g_pt_gather_tma = e == nullptr ? PT_GATHER_TMA_DEFAULT : (e[0] == 't' ? 1 : 0);
+    }
+    if (g_pt_gather_tma == 1 && rowlen % 2 == 0) {
+        dim3 tgrid(ceil_div(rowlen, GT_CHUNK), n, nb);
+        k_pt_gather_tma<<<tgrid, 128, 0, ctx->stream>>>(box, table, out, rowlen, npress, n, bd.active ? bd.table_index : nullptr,
+                                                       bd.ktable_stride, bd.active ? bd.wg() : 0);
+        HLAUNCHED(ctx);
+        if (table2 == nullptr) return HELIOS_OK;
+        // the cross-section table (rowlen2 = nbin doubles per row) stays on the streaming form
+        table = nullptr;
+    }
     int bx = ceil_div(rowlen, 256);
     const int cap = (ctx->num_sms * 8 + n * nb - 1) / (n * nb);
     if (bx > cap) bx = cap > 0 ? cap : 1;

@@ -405,6 +405,11 @@ int helios_conv_temp_iter(helios_ctx* ctx, const double* F_down_tot, const doubl
  * device into *sum_dev (device int).  B200-side addition, no reference kernel. */
 int helios_abort_sum(helios_ctx* ctx, const int* abrt, int n, int* sum_dev);
 
+/* opac_interpol / opac_species_interpol: 1 = stage the four table rows of a layer's (P, T) box through shared memory with
+ * TMA bulk copies (k_pt_gather_tma), 0 = stream them with read-only loads (default: measured faster on B200), -1 = back
+ * to the default / HELIOS_PT_GATHER.  Process-wide; returns the previous setting.  Both forms give identical results. */
+int helios_set_pt_gather_tma(int on);
+
 /* ------------------------------------------------------------------ device-side host functions */
 
 /* host_functions.py:509-538 convective_adjustment (conv_check / mark_convective_layers / conv_correct to stability, then

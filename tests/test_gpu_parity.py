@@ -592,3 +592,26 @@ def test_temperature_step_with_smoothing(ctx, kernel):
             stage_vs_ref(q, comp, ref_gpu.RefCompute(ctx.device), kernel, outs)
         stage_vs_oracle(q, comp, oc, kernel, outs)
         assert np.any(q.dev_F_smooth.get() != 0.0), "the smoothing branch did not run"
+
+
+def test_tma_staged_table_gather_equals_the_streamed_one(ctx):
+    """opac_interpol with the table rows staged through shared memory by TMA bulk copies (k_pt_gather_tma) against the
+    streamed form: bitwise the same output (the staged form was measured slower on B200 and is not the default)"""
+    from helios_b200 import backend
+    q = _variant("C2", ctx)
+    comp = Compute(ctx, verbose=False)
+    comp.interpolate_temperatures(q)
+    lib = backend.lib()
+    out = {}
+    for mode in (0, 1):
+        before = lib.helios_set_pt_gather_tma(mode)
+        try:
+            for n in ("opac_wg_lay", "opac_wg_int", "scat_cross_lay", "scat_cross_int"):
+                getattr(q, "dev_" + n).fill_zero()
+            comp.interpolate_opacities_and_scattering_cross_sections(q)
+            out[mode] = {n: getattr(q, "dev_" + n).get() for n in ("opac_wg_lay", "opac_wg_int", "scat_cross_lay", "scat_cross_int")}
+        finally:
+            lib.helios_set_pt_gather_tma(before)
+    for n in out[0]:
+        assert np.array_equal(out[0][n], out[1][n]), n
+        assert np.any(out[0][n] != 0.0), n
