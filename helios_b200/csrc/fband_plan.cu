@@ -655,12 +655,22 @@ k_plan_build_iso(double* __restrict__ plan, const double* __restrict__ F_dir, co
         const int atm = blk / nblk;
         const int t0 = (blk - atm * nblk) * TPB;  // first warp tile of this CTA
         const int ntl = min(TPB, ntw - t0);
-        // identity steps everywhere first (cells outside the column, idle lanes): a = 1, everything else 0
-        for (int k = threadIdx.x; k < ntl * PB; k += 256) {
-            const int w = k % PB;
-            sm[k] = (w < CH * NR * rl && (w / rl) % NR == 0) ? 1.0 : 0.0;
+        // identity steps (a = 1, everything else 0) in the slots no layer maps to: chunk * CH + k >= nlay.  Every other slot
+        // is written below, and so are the surface constants of every column.
+        {
+            const int first = nlay;                 // slots are numbered chunk * CH + k
+            const int nfree = rs * CH - first;      // per column
+            for (int e = threadIdx.x; e < ntl * CPW * nfree; e += 256) {
+                const int cc = e / nfree, slot = first + e % nfree;
+                double* __restrict__ p = sm + (size_t)(cc / CPW) * PB + (size_t)((slot % CH) * NR) * rl + (cc % CPW) * rs + slot / CH;
+                p[0] = 1.0;
+                for (int j = 1; j < NR; j++) p[j * rl] = 0.0;
+            }
+            // (the trailing doubles behind the 2 * CPW surface constants are padding)
+            if constexpr (CPW == 1) {
+                for (int e = threadIdx.x; e < ntl * 2; e += 256) sm[(size_t)(e / 2) * PB + CH * NR * rl + 2 + e % 2] = 0.0;
+            }
         }
-        __syncthreads();
         const int col = min(t0 * CPW + c, ncol - 1);
         const int x = col / s.ny;
         const int tl = c / CPW, cw = c % CPW;  // tile within the CTA, column within the tile
@@ -757,12 +767,15 @@ k_plan_build_noniso(double* __restrict__ plan, const double* __restrict__ F_dir,
         const int atm = blk / nblk;
         const int t0 = (blk - atm * nblk) * TC;
         const int ntl = min(TC, ncol - t0);
-        for (int k = threadIdx.x; k < ntl * PB; k += 256) {
-            const int w = k % PB;
-            const int row = (w / rl) % NR;
-            sm[k] = (w < CH * NR * rl && (row == 0 || row == 4)) ? 1.0 : 0.0;
+        {   // identity steps (a_u = a_l = 1, everything else 0) in the slots no layer maps to; trailing doubles cleared
+            const int first = nlay, nfree = rl * CH - first;
+            for (int e = threadIdx.x; e < ntl * nfree; e += 256) {
+                const int cc = e / nfree, slot = first + e % nfree;
+                double* __restrict__ p = sm + (size_t)cc * PB + (size_t)((slot % CH) * NR) * rl + slot / CH;
+                for (int j = 0; j < NR; j++) p[j * rl] = (j == 0 || j == 4) ? 1.0 : 0.0;
+            }
+            for (int e = threadIdx.x; e < ntl * 2; e += 256) sm[(size_t)(e / 2) * PB + CH * NR * rl + 2 + e % 2] = 0.0;  // padding
         }
-        __syncthreads();
         const int col = min(t0 + c, ncol - 1);
         const int x = col / s.ny;
         if (c < ntl) {
