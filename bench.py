@@ -518,6 +518,47 @@ def _sweep_roofline(r, tag, nbatch=None):
                      nbatch, r["sbpc"])
 
 
+def bench_rebuild(ctx, flush, workload="C2", reps=7):
+    """the kernels of an opacity refresh (every 10th RT iteration, C:860-879) and the one-time Planck table, each timed
+    alone with CUDA events on a cold L2; fp64 rooflines for the compute-bound ones from their algorithmic operation counts
+    and the measured pipe rates (profiles/r2_measured_fp64_peaks.json)"""
+    q, comp = _prepare(workload, ctx)
+    cells = int(q.nlayer) * int(q.nbin) * int(q.ny)
+
+    def timed(fn):
+        ts = []
+        for k in range(reps + 2):
+            flush()
+            e0, e1 = ctx.event(), ctx.event()
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            if k >= 2:
+                ts.append(e0.time_till(e1))
+        return float(np.median(ts))
+
+    out = {"workload": "%s: refresh kernels, %d layers x %d bins x %d gauss points" % (workload, q.nlayer, q.nbin, q.ny)}
+    t = timed(lambda: comp.calculate_transmission(q))
+    halves = 1 if q.iso == 1 else 2
+    # per half-layer cell: 1 exp, 2 sqrt, ~8 divisions, ~50 multiply-adds (trans.cu: cell_coeffs)
+    out["calculate_transmission"] = {"ms": t, "roofline": _fp64_roofline(
+        "k_calc_trans_%s" % ("iso" if q.iso == 1 else "noniso"),
+        {"exp": 1.0 * halves * cells, "sqrt": 2.0 * halves * cells, "div": 8.0 * halves * cells, "fma": 50.0 * halves * cells}, t,
+        "1 exp + 2 sqrt + ~8 div + ~50 FMA per half-layer cell; the kernel also stores 8 / 16 arrays (%.0f MB)"
+        % (cells * 8 * 8 * halves / 1e6))}
+    out["calculate_direct_beamflux"] = {"ms": timed(lambda: comp.calculate_direct_beamflux(q))}
+    out["interpolate_opacities"] = {"ms": timed(lambda: comp.interpolate_opacities_and_scattering_cross_sections(q))}
+    out["build_flux_plan"] = {"ms": timed(lambda: comp.build_flux_plan(q))}
+    t = timed(lambda: comp.construct_planck_table(q))
+    entries = (int(q.plancktable_dim) + 1) * int(q.nbin)
+    # K:362-416: 199-term series at both bin edges: 398 exp and ~8 multiply-adds per term
+    out["construct_planck_table"] = {"ms": t, "roofline": _fp64_roofline(
+        "k_plancktable", {"exp": 398.0 * entries, "fma": 398.0 * 8 * entries}, t,
+        "one-time: %d table entries x 398 exp (199-term series at both bin edges)" % entries)}
+    return out
+
+
 def _quiesce(ctx):
     """before a wall-clock leg: release what earlier legs left behind now (every DeviceArray that dies frees its
     buffer with a device-synchronising cudaFree) and keep the collector out of the timed region"""
@@ -838,6 +879,10 @@ def run_ours(args):
                 extra["C3_on_the_fly_mixing"] = bench_mixing(ctx, flush)
             except Exception as e:  # noqa: BLE001
                 extra["C3_on_the_fly_mixing"] = {"error": repr(e)}
+            try:
+                extra["C2_refresh_kernels"] = bench_rebuild(ctx, flush)
+            except Exception as e:  # noqa: BLE001
+                extra["C2_refresh_kernels"] = {"error": repr(e)}
             line["workloads"] = extra
         elif world > 1 and not args.only_main:
             # every N: the wavelength-sharded spectrum (strong scaling, with the NVLink exchange) and the batched grid
