@@ -14,7 +14,8 @@
 __global__ void __launch_bounds__(256)
 k_peer_allreduce(CommPeers peers, double* __restrict__ vec_a, double* __restrict__ vec_b,
                  double* __restrict__ net, int n, int rank, int world, int slot, size_t data_bytes,
-                 unsigned long long seq) {
+                 unsigned long long* __restrict__ seq_dev) {
+    const unsigned long long seq = *seq_dev + 1ull;  // this round (one block: everybody reads before thread 0 advances it)
     const int bank = (int)(seq & 1ull);
     const int nn = vec_b ? 2 * n : n;
     // 1. scatter my partials into slot `rank` of every mailbox (my own included)
@@ -53,6 +54,8 @@ k_peer_allreduce(CommPeers peers, double* __restrict__ vec_a, double* __restrict
             if (net) net[t] = a - b;
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) *seq_dev = seq;
 }
 
 static int comm_launch(helios_ctx* ctx, const char* who, double* a, double* b, double* net, int n) {
@@ -73,8 +76,7 @@ static int comm_launch(helios_ctx* ctx, const char* who, double* a, double* b, d
     }
     CommPeers p;
     for (int r = 0; r < COMM_MAX_WORLD; r++) p.p[r] = c->peers[r];
-    c->seq++;
-    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(p, a, b, net, n, c->rank, c->world, c->slot, c->data_bytes, c->seq);
+    k_peer_allreduce<<<1, 256, 0, ctx->stream>>>(p, a, b, net, n, c->rank, c->world, c->slot, c->data_bytes, c->seq_dev);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
@@ -104,7 +106,7 @@ int helios_comm_fused_next(helios_ctx* ctx, int n, FusedComm* fc) {
     fc->world = c->world;
     fc->slot = c->slot;
     fc->data_bytes = c->data_bytes;
-    fc->seq = ++c->seq;
+    fc->seq_dev = c->seq_dev;
     fc->ticket = c->fused_ticket;
     return HELIOS_OK;
 }
@@ -143,6 +145,8 @@ int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles, u
         return helios_fail_cuda(e, "cudaMalloc(mailbox)", __FILE__, __LINE__);
     }
     e = cudaMemset(c->own, 0, total);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&c->seq_dev, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->seq_dev, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->own);
@@ -196,6 +200,7 @@ int helios_comm_destroy(helios_ctx* ctx) {
         if (c->opened[r] && c->peers[r]) cudaIpcCloseMemHandle(c->peers[r]);
     if (c->own) cudaFree(c->own);
     if (c->fused_ticket) cudaFree(c->fused_ticket);
+    if (c->seq_dev) cudaFree(c->seq_dev);
     delete c;
     ctx->comm = nullptr;
     return HELIOS_OK;

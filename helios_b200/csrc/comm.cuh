@@ -7,7 +7,10 @@
 
 struct helios_comm_state {
     int rank = 0, world = 1, slot = 0;
-    unsigned long long seq = 0;
+    // exchange sequence number, ON THE DEVICE: every exchanging kernel reads it at its start (round = *seq_dev + 1) and its
+    // last block advances it, so that a recorded launch (CUDA graph) can be replayed -- a by-value sequence number would
+    // be frozen into the graph.  All ranks make the same sequence of exchanges, so their counters stay in step.
+    unsigned long long* seq_dev = nullptr;
     // own mailbox: [2 banks][world][slot] doubles, then [world] flags (u64), flags padded to 128 B
     void* own = nullptr;
     void* peers[COMM_MAX_WORLD] = {nullptr};
@@ -27,7 +30,7 @@ struct FusedComm {
     CommPeers peers;
     int rank = 0, world = 0, slot = 0;
     size_t data_bytes = 0;
-    unsigned long long seq = 0;
+    unsigned long long* seq_dev = nullptr;
     unsigned* ticket = nullptr;
 };
 
@@ -40,5 +43,5 @@ __device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long lon
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// fills `fc` for the next exchange (advances the sequence number); HELIOS_OK or an error status
+// fills `fc` for an exchange inside k_band_integrate; HELIOS_OK or an error status
 int helios_comm_fused_next(helios_ctx* ctx, int n, FusedComm* fc);

@@ -140,10 +140,12 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     // totals.  One launch instead of integration + exchange kernel.
     if (fc.world > 0) {
         __shared__ bool all_done;
+        __shared__ unsigned long long round;
         if (threadIdx.x == 0) {
             all_done = false;
+            round = *fc.seq_dev + 1ull;  // read before this block's ticket: the counter only advances after the last ticket
             if (last) {
-                const int bank = (int)(fc.seq & 1ull);
+                const int bank = (int)(round & 1ull);
                 const double up = F_up_tot[i], dn = F_down_tot[i];
                 for (int r = 0; r < fc.world; r++) {
                     double* data = reinterpret_cast<double*>(fc.peers.p[r]) + ((size_t)bank * fc.world + fc.rank) * fc.slot;
@@ -156,17 +158,18 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         }
         __syncthreads();
         if (all_done) {
+            const unsigned long long seq = round;
             if ((int)threadIdx.x < fc.world) {
                 unsigned long long* flags = reinterpret_cast<unsigned long long*>(
                     reinterpret_cast<char*>(fc.peers.p[threadIdx.x]) + fc.data_bytes);
-                st_flag(flags + 16 * fc.rank, fc.seq);
+                st_flag(flags + 16 * fc.rank, seq);
                 const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
                     reinterpret_cast<char*>(fc.peers.p[fc.rank]) + fc.data_bytes);
-                while (ld_flag(mine + 16 * threadIdx.x) < fc.seq) __nanosleep(64);
+                while (ld_flag(mine + 16 * threadIdx.x) < seq) __nanosleep(64);
             }
             __syncthreads();
             __threadfence_system();
-            const int bank = (int)(fc.seq & 1ull);
+            const int bank = (int)(seq & 1ull);
             const volatile double* box = reinterpret_cast<const volatile double*>(fc.peers.p[fc.rank]);
             for (int t = threadIdx.x; t < nint; t += blockDim.x) {
                 double a = 0.0, b = 0.0;
@@ -178,7 +181,11 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                 F_down_tot[t] = b;
                 F_net[t] = a - b;
             }
-            if (threadIdx.x == 0) *fc.ticket = 0u;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                *fc.ticket = 0u;
+                *fc.seq_dev = seq;  // the next exchanging launch (stream order) sees the advanced counter
+            }
         }
     }
 }
