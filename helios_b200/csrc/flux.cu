@@ -6,13 +6,11 @@
 // ------------------------------------------------------------------------------------------------
 // integrate_flux (K:2428-2513).  The reference runs ONE 1024-thread block that funnels every cell
 // through fp64 CAS-loop atomics.  Here:
-//   grid (bin groups, interfaces, atmospheres).  With Gauss points (ny > 1) a WARP owns a bin: lanes along y read the
-//   bin's ny contiguous values of each of the three wg arrays as one coalesced piece, weight them and add them with a
-//   fixed shuffle tree -> F_*_band[i][x]; without (opacity sampling) a thread owns a bin.  A block walks its share of
-//   the interface's bins, keeps its part of the wavelength integral in registers, tree-sums it, and the last block
-//   of an interface to finish adds the per-block partial sums in block order -> F_up_tot, F_down_tot, F_net.
-// One launch; the summation order is fixed (and independent of the batch size), so results are bitwise
-// reproducible run to run.  Under wavelength sharding the exchange of the totals runs in the same launch (below).
+//   grid (x-tiles, interfaces, atmospheres): a block stages XB*ny contiguous doubles of each of the three wg arrays
+//   through shared memory (coalesced), one thread per bin adds its ny Gauss points in y order -> F_*_band[i][x];
+//   the block then tree-sums its bins' contributions to the wavelength integral, and the last block of an
+//   interface to finish adds the per-block partial sums in block order -> F_up_tot, F_down_tot, F_net.
+// One launch; the summation order is fixed, so results are bitwise reproducible run to run.
 // ------------------------------------------------------------------------------------------------
 #define IF_THREADS 256
 
@@ -36,58 +34,59 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                  const double* __restrict__ deltalambda, double* __restrict__ partial, unsigned* __restrict__ ticket,
                  double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net, FusedComm fc) {
     extern __shared__ double sm[];
+    const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
+    double* s_dn = sm;
+    double* s_up = sm + (size_t)xb * pitch;
+    double* s_dr = sm + (size_t)2 * xb * pitch;
     const int i = blockIdx.y;
     {   // batch (blockIdx.z = atmosphere): [i][x][y] and [i][x] arrays both hold gridDim.y = ninterface rows
         const size_t wg = (size_t)blockIdx.z * gridDim.y * nbin * ny, bd = (size_t)blockIdx.z * gridDim.y * nbin;
         F_down_wg += wg; F_up_wg += wg; F_dir_wg += wg;
         F_down_band += bd; F_up_band += bd; F_dir_band += bd;
     }
-    // Gauss sums.  ny > 1: one WARP per bin, lanes along the Gauss points -- the ny values of a bin are contiguous, so a
-    // warp reads them as one coalesced piece per array, weights them and adds them with a fixed shuffle tree; a block
-    // walks the groups of 8 bins blockIdx.x, blockIdx.x + gridDim.x, ... of its interface and keeps its share of the
-    // wavelength integral in registers (lane 0 of every warp).  ny == 1 (opacity sampling): one thread per bin, a block
-    // walks tiles of blockDim.x bins (1e5 bins: 11 blocks per interface instead of ~400).
+    // A block walks the x-tiles blockIdx.x, blockIdx.x + gridDim.x, ... of its interface (wide spectra: 1e5 bins are
+    // ~400 tiles; a block per tile would be ~40,000 blocks of two barriers-and-a-ticket each) and keeps its share of the
+    // wavelength integral in registers across them.
     double t_up = 0.0, t_dn = 0.0;  // this thread's bins in the sum over wavelength
-    (void)xb;
-    (void)sm;
-    if (ny > 1) {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        constexpr int WPB = IF_THREADS / 32;
-        for (int x = blockIdx.x * WPB + warp; x < nbin; x += gridDim.x * WPB) {
-            const size_t base = ((size_t)i * nbin + x) * ny;
-            double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
-            for (int y = lane; y < ny; y += 32) {
-                const double hw = 0.5 * gauss_weight[y];
-                a_dr += hw * F_dir_wg[base + y];
-                a_up += hw * F_up_wg[base + y];
-                a_dn += hw * F_down_wg[base + y];
+    const int ntiles = (nbin + xb - 1) / xb;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int x0 = tile * xb;
+        const int nx = min(xb, nbin - x0);
+        const size_t base = ((size_t)i * nbin + x0) * ny;
+        if (ny > 1) {
+            const int n = nx * ny;
+            for (int k = threadIdx.x; k < n; k += blockDim.x) {
+                const int xl = k / ny, y = k - xl * ny;
+                const int d = xl * pitch + y;
+                s_dn[d] = F_down_wg[base + k];
+                s_up[d] = F_up_wg[base + k];
+                s_dr[d] = F_dir_wg[base + k];
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                a_dr += __shfl_xor_sync(0xffffffffu, a_dr, d);
-                a_up += __shfl_xor_sync(0xffffffffu, a_up, d);
-                a_dn += __shfl_xor_sync(0xffffffffu, a_dn, d);
-            }
-            if (lane == 0) {
-                const size_t o = (size_t)i * nbin + x;
-                F_dir_band[o] = a_dr;
-                F_up_band[o] = a_up;
-                F_down_band[o] = a_dn;
-                t_up += a_up * deltalambda[x];
-                t_dn += (a_dr + a_dn) * deltalambda[x];
-            }
+            __syncthreads();
         }
-    } else {
-        const double hw = 0.5 * gauss_weight[0];
-        for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < nbin; x += gridDim.x * blockDim.x) {
-            const size_t o = (size_t)i * nbin + x;
-            const double a_dr = hw * F_dir_wg[o], a_up = hw * F_up_wg[o], a_dn = hw * F_down_wg[o];
+        for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
+            double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
+            if (ny > 1) {
+                for (int y = 0; y < ny; y++) {
+                    const double hw = 0.5 * gauss_weight[y];
+                    a_dr += hw * s_dr[xl * pitch + y];
+                    a_up += hw * s_up[xl * pitch + y];
+                    a_dn += hw * s_dn[xl * pitch + y];
+                }
+            } else {  // opacity sampling: one point per bin, consecutive threads read consecutive bins
+                const double hw = 0.5 * gauss_weight[0];
+                a_dr += hw * F_dir_wg[base + xl];
+                a_up += hw * F_up_wg[base + xl];
+                a_dn += hw * F_down_wg[base + xl];
+            }
+            const size_t o = (size_t)i * nbin + x0 + xl;
             F_dir_band[o] = a_dr;
             F_up_band[o] = a_up;
             F_down_band[o] = a_dn;
-            t_up += a_up * deltalambda[x];
-            t_dn += (a_dr + a_dn) * deltalambda[x];
+            t_up += a_up * deltalambda[x0 + xl];
+            t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
         }
+        if (ny > 1) __syncthreads();  // the next tile overwrites the staging area
     }
     // Sum over wavelength in the same launch (K:2484-2509): fixed tree over this block's bins, then the LAST block
     // of the interface to finish adds the per-block partial sums in block order -- a fixed summation order, bitwise
@@ -520,9 +519,14 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
     HARG(deltalambda && F_down_tot && F_up_tot && F_net && F_down_wg && F_up_wg && F_dir_wg &&
          F_down_band && F_up_band && F_dir_band && gauss_weight);
     HARG(nbin > 0 && numinterfaces > 0 && ny > 0);
-    // bins per block and step: 8 (one warp per bin) with Gauss points, 256 (one thread per bin) without
-    const int xb = ny > 1 ? IF_THREADS / 32 : IF_THREADS;
-    const size_t smem = 0;
+    // bins per block: as many as fit in ~36 kB of shared memory, at most 256
+    int xb = (int)(36 * 1024 / (3 * sizeof(double) * (ny + 1)));
+    if (xb > 256) xb = 256;
+    if (xb < 1) {
+        helios_set_error("helios_integrate_flux_double: ny = %d too large", ny);
+        return HELIOS_ERR_ARG;
+    }
+    const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
     const int nb = ctx->batch.nbatch;
     // blocks per (atmosphere, interface): one per x-tile while that keeps a single atmosphere's grid within ~8 blocks per
