@@ -606,6 +606,7 @@ def rce_leg(ctx, workload, seed_offset=0):
         q = synthetic.make_store(workload, ctx=ctx, seed=synthetic.SEED + seed_offset)
         status = "converged"
         conv_iters = 0
+        loop_wall = None
         if mode == "host_loop":
             synthetic.upload(q)
             comp = Compute(ctx, verbose=False)
@@ -634,6 +635,7 @@ def rce_leg(ctx, workload, seed_offset=0):
             try:
                 bcomp.radiation_loop(qb)
                 rad_iters = int(qb.converged_at[0])
+                loop_wall = dict(bcomp.stats.get("radiation_loop_wall", {}), gpu_ms=bcomp.stats.get("radiation_loop_ms"))
                 if q.convection == 1:
                     # hand the converged state over to the host-driven convection loop (C:992-1174)
                     for name in ("T_lay", "F_net", "F_up_tot", "F_down_tot", "abort", "T_store", "delta_t_prefactor"):
@@ -650,6 +652,8 @@ def rce_leg(ctx, workload, seed_offset=0):
         if mode not in out or dt < out[mode]["seconds"]:
             out[mode] = {"seconds": dt, "radiation_iterations": rad_iters, "convection_iterations": conv_iters,
                          "status": status, "ms_per_iteration": 1e3 * dt / max(1, rad_iters + conv_iters)}
+            if mode == "device_loop":
+                out[mode]["wall_breakdown"] = loop_wall
     return out
 
 

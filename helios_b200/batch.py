@@ -258,19 +258,26 @@ class BatchCompute(Compute):
         ev[0].record()
         block = 10
         graphs = {}
+        import time as _time
+        wall = {"first_block_s": 0.0, "capture_s": 0.0, "replay_s": 0.0}
+        t_mark = _time.perf_counter()
         try:
             # the first block runs eagerly: it sizes the library's scratch buffers, which must not grow while capturing
             for k in range(block):
                 self._iteration(q, refresh=(k == 0), heights=False, fused=fused)
             done, at, it = q.state()
+            wall["first_block_s"] = _time.perf_counter() - t_mark
+            t_mark = _time.perf_counter()
             while not done.all():
                 limit = float(q.rad_convergence_limit)
                 if graph:
                     if limit not in graphs:
+                        t_cap = _time.perf_counter()
                         with self.ctx.capture() as g:
                             for k in range(block):
                                 self._iteration(q, refresh=(k == 0), heights=False, fused=fused)
                         graphs[limit] = g
+                        wall["capture_s"] += _time.perf_counter() - t_cap
                     graphs[limit].launch()
                 else:
                     for k in range(block):
@@ -284,9 +291,11 @@ class BatchCompute(Compute):
                 if it > q.max_nr_iterations:
                     print("\nRun exceeds allowed maximum allowed number of iteration steps. Aborting...")
                     raise SystemExit()
+            wall["replay_s"] = _time.perf_counter() - t_mark - wall["capture_s"]
             q.converged_at = at.astype(np.int64)
             q.iter_value = np.int32(it)
             self._heights(q)
+            self.stats["radiation_loop_wall"] = wall
         finally:
             ev[1].record()
             ev[1].synchronize()
