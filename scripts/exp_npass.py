@@ -11,7 +11,7 @@ ctx = runtime.set_default_context(backend.Context(0))
 for wl in sys.argv[1:] or ["C2", "C1"]:
     q, comp = bench._prepare(wl, ctx)
     assert q._flux_plan_valid
-    for n in (1, 4, 16):
+    for n in [int(v) for v in os.environ.get('NPASS', '1,4,16').split(',')]:
         def run():
             if q.iso == 1:
                 ctx.call("fband_iso_planned", q.dev_F_down_wg, q.dev_F_up_wg, q.dev_fband_plan, q.dev_planckband_lay,
