@@ -41,8 +41,12 @@ struct PlanScalars {
     double Rstar, a, f_factor;
     int nint, nbin, ny, dir_beam, npass, nch, rs, nbatch;
     const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
+    int cp;             // column pitch of the staged flux rows (CtaShape::cpitch), formed by the launcher
+    unsigned ny_magic;  // floor(2^32 / ny) + 1: column -> bin by one multiply-high (exact below 2^32 / ny columns)
 #ifdef HELIOS_ABLATE
     int ablate;  // experiment builds only (scripts/exp_ablate.sh): bit mask of parts of the sweep to leave out
+    int skew_ns;  // experiment: co-resident CTA r (blockIdx.x / SMs) starts r * skew_ns late
+    int nsm;
 #endif
 };
 #ifdef HELIOS_ABLATE
@@ -50,6 +54,10 @@ struct PlanScalars {
 #else
 #define ABL(bit) false
 #endif
+
+__device__ __forceinline__ int bin_of(int col, const PlanScalars& s) {
+    return s.ny == 1 ? col : (int)__umulhi((unsigned)col, s.ny_magic);
+}
 
 // ---------------------------------------------------------------- async-copy plumbing (PTX) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -217,11 +225,13 @@ __device__ __forceinline__ void flux_block(const FluxMap<CH, NC, THREADS>& m, do
     }
 }
 
-// The previous fluxes come in by 16-byte cp.async.cg when the column count is even: an 8-byte cp.async has to go through
-// L1 (.ca), and a tile touches one 32-byte piece of 100+ different 128-byte lines per array -- more lines than the L1
-// that is left beside the shared-memory carve-out holds, so the LSU stalled on line allocation (the flux loads cost 7 of
-// 44 us, profiles/r2_sweep_ablation.txt).  Two adjacent columns of one interface are one 16-byte piece; they are staged
-// side by side, [k][column pair][lane][2]: thread (kh, lane l, pair pc) moves the rows l * CH + k, k = kh, kh + 2, ...
+// With an even column count the fluxes move as 16-byte pieces (two adjacent columns of one interface), staged side by
+// side, [k][column pair][lane][2]; thread (kh, lane l, pair pc) moves the rows l * CH + k, k = kh, kh + 2, ...
+//   in : cp.async.cg -- an 8-byte cp.async has to go through L1 (.ca), and a tile touches one 32-byte piece of 100+
+//        different 128-byte lines per array, more lines than the L1 left beside the shared-memory carve-out holds: the
+//        LSU stalled on line allocation (the flux loads cost 7 of 44 us, profiles/r2_sweep_ablation.txt);
+//   out: LDS.128 + STG.128, half the instructions of the dependent load-store pairs of the 8-byte form.
+// The owners' 8-byte accesses to this layout stride 16 bytes (2 wavefronts more per access).
 template <int CH, int NC, int THREADS>
 struct PairMap {
     int o0, r0, pc, kh;
@@ -239,16 +249,19 @@ struct PairMap {
     __device__ static __forceinline__ int owner(int c, int sl, int cp) { return (c >> 1) * 2 * cp + 2 * sl + (c & 1); }
 };
 
-template <int CH, int NC, int THREADS>
-__device__ __forceinline__ void flux_pairs_load(const PairMap<CH, NC, THREADS>& m, const double* __restrict__ g,
-                                                unsigned stage_s, int nlay, int ncol, int col0, int frow) {
+template <int CH, int NC, int THREADS, bool LOAD>
+__device__ __forceinline__ void flux_pairs(const PairMap<CH, NC, THREADS>& m, double* __restrict__ g, unsigned stage_s,
+                                           const double* stage, int nlay, int ncol, int col0, int frow) {
     const int col = col0 + 2 * m.pc;
     if (col >= ncol) return;
-    const double* __restrict__ p = g + col + (size_t)m.r0 * ncol;
+    double* __restrict__ p = g + col + (size_t)m.r0 * ncol;
 #pragma unroll
     for (int k2 = 0; k2 < (CH + 1) / 2; k2++) {
         const int k = 2 * k2 + m.kh;
-        if (k < CH && m.r0 + k < nlay) cp_async16(stage_s + (unsigned)(m.o0 + k * frow) * 8u, p + (size_t)k * ncol);
+        if (k < CH && m.r0 + k < nlay) {
+            if (LOAD) cp_async16(stage_s + (unsigned)(m.o0 + k * frow) * 8u, p + (size_t)k * ncol);
+            else *reinterpret_cast<double2*>(p + (size_t)k * ncol) = *reinterpret_cast<const double2*>(stage + m.o0 + k * frow);
+        }
     }
 }
 
@@ -267,7 +280,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     using CS = CtaShape<CH, NR, 1, CH, NST, CPW, WARPS>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rs = s.rs, rl = rs * CPW, cp = CS::cpitch(rs), frow = CS::frow(rs);
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rs = s.rs, rl = rs * CPW, cp = s.cp, frow = NC * cp;
     const int ncol = s.nbin * s.ny;
     const unsigned ntw = (unsigned)(ncol + CPW - 1) / CPW;  // warp tiles per atmosphere (plan blocks)
     const unsigned nct = (unsigned)(ncol + NC - 1) / NC;    // CTA tiles per atmosphere
@@ -288,12 +301,12 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     const bool act = sl < nch;
     const int lo = sl * CH;
     const int me = cw * rs + sl;                        // my element of a staged row of my warp
-    const int fme = (warp * CPW + cw) * cp + (act ? sl : 0);  // ... and of a staged flux row of the CTA
     // slots never written by the copies (layers beyond the column) must read as zeros
     for (int k = lane; k < CH * rl + 8; k += 32) bbuf[k] = 0.0;
     for (int k = threadIdx.x; k < CS::flux_doubles(rs); k += THREADS) fin[k] = 0.0;
-    // PAIRS (the host checks: even column count, 16-byte aligned arrays): previous fluxes arrive as 16-byte pieces
-    const int fme_in = PAIRS ? PairMap<CH, NC, THREADS>::owner(warp * CPW + cw, act ? sl : 0, cp) : fme;
+    // PAIRS (the host checks: even column count, 16-byte aligned arrays): the fluxes move as 16-byte pieces
+    const int fme = PAIRS ? PairMap<CH, NC, THREADS>::owner(warp * CPW + cw, act ? sl : 0, cp)
+                          : (warp * CPW + cw) * cp + (act ? sl : 0);  // my element of a staged flux row of the CTA
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -306,7 +319,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         const int ctile = (int)(ct - atm * nct);
         const unsigned tile = min((unsigned)ctile * WARPS + warp, ntw - 1u);  // warps beyond the last column mirror it
         const int colc = min((int)tile * CPW + cw, ncol - 1);
-        const int x = colc / s.ny;
+        const int x = bin_of(colc, s);
         if (lane == 0) {
             fence_proxy_async();  // the generic-proxy reads of the previous tile are ordered before the bulk write
             mbar_expect_tx(bar, (unsigned)PB * 8u);
@@ -322,7 +335,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         if (PAIRS) {
             PairMap<CH, NC, THREADS> pmap;
             pmap.init(cp);
-            flux_pairs_load<CH, NC, THREADS>(pmap, F_up + (size_t)atm * ncol * nint, fin_s, nlay, ncol, ctile * NC, frow);
+            flux_pairs<CH, NC, THREADS, true>(pmap, F_up + (size_t)atm * ncol * nint, fin_s, nullptr, nlay, ncol, ctile * NC, frow);
         } else {
             FluxMap<CH, NC, THREADS> fmap;
             fmap.init(nlay, cp);
@@ -353,7 +366,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
             a[k] = pbuf[(k * NR + 0) * rl + mec];
             b[k] = pbuf[(k * NR + 1) * rl + mec];
             const double k1 = pbuf[(k * NR + 2) * rl + mec];
-            Fu_reg[k] = fin[k * frow + fme_in];
+            Fu_reg[k] = fin[k * frow + fme];
             Fd_reg[k] = 0.0;
             if (NOBEAM) {
                 sd[k] = __dmul_rn(k1, B);
@@ -453,10 +466,17 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         if (!skip) {
             double* __restrict__ gd = F_down + (size_t)atm * ncol * nint;
             double* __restrict__ gu = F_up + (size_t)atm * ncol * nint;
-            FluxMap<CH, NC, THREADS> fmap;
-            fmap.init(nlay, cp);
-            flux_block<CH, NC, THREADS, false>(fmap, gd, 0u, fout_dn, ncol, ctile * NC, frow);
-            flux_block<CH, NC, THREADS, false>(fmap, gu, 0u, fout_up, ncol, ctile * NC, frow);
+            if (PAIRS) {
+                PairMap<CH, NC, THREADS> pmap;
+                pmap.init(cp);
+                flux_pairs<CH, NC, THREADS, false>(pmap, gd, 0u, fout_dn, nlay, ncol, ctile * NC, frow);
+                flux_pairs<CH, NC, THREADS, false>(pmap, gu, 0u, fout_up, nlay, ncol, ctile * NC, frow);
+            } else {
+                FluxMap<CH, NC, THREADS> fmap;
+                fmap.init(nlay, cp);
+                flux_block<CH, NC, THREADS, false>(fmap, gd, 0u, fout_dn, ncol, ctile * NC, frow);
+                flux_block<CH, NC, THREADS, false>(fmap, gu, 0u, fout_up, ncol, ctile * NC, frow);
+            }
             if (live && sl == nch - 1) {  // interface nlayer (TOA)
                 gd[(size_t)ncol * nlay + colc] = toa;
                 gu[(size_t)ncol * nlay + colc] = F_out;
@@ -483,7 +503,7 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     using CS = CtaShape<CH, NR, 2, NBV, 5, 1, WARPS>;
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rl = s.rs, cp = CS::cpitch(rl), frow = CS::frow(rl);
+    const int nint = s.nint, nlay = nint - 1, nch = s.nch, rl = s.rs, cp = s.cp, frow = NC * cp;
     const int ncol = s.nbin * s.ny;
     const unsigned nct = (unsigned)(ncol + NC - 1) / NC;  // CTA tiles per atmosphere
     const unsigned total = nct * (unsigned)s.nbatch;
@@ -503,11 +523,11 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     const int sl = lane;
     const bool act = sl < nch;
     const int lo = sl * CH;
-    const int fme = warp * cp + (act ? sl : 0);  // my element of a staged flux row of the CTA
     for (int k = lane; k < NBV * rl + 8; k += 32) bbuf[k] = 0.0;
     for (int k = threadIdx.x; k < CS::flux_doubles(rl); k += THREADS) fin[k] = 0.0;
-    // PAIRS (the host checks: even column count, 16-byte aligned arrays): previous fluxes arrive as 16-byte pieces
-    const int fme_in = PAIRS ? PairMap<CH, NC, THREADS>::owner(warp, act ? sl : 0, cp) : fme;
+    // PAIRS (the host checks: even column count, 16-byte aligned arrays): the fluxes move as 16-byte pieces
+    const int fme = PAIRS ? PairMap<CH, NC, THREADS>::owner(warp, act ? sl : 0, cp)
+                          : warp * cp + (act ? sl : 0);  // my element of a staged flux row of the CTA
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -515,26 +535,35 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     }
     __syncthreads();
 
+    const double* bbuf0 = smem + 2 + PB;  // warp 0's Planck block
+    const unsigned bbuf0_s = smem_u32(bbuf0);
+    auto one_bin = [&](int ctile) { return bin_of(ctile * NC, s) == bin_of(min(ctile * NC + NC - 1, ncol - 1), s); };
+
     auto issue = [&](unsigned ct) {
         const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
         const int ctile = (int)(ct - atm * nct);
         const int col = min(ctile * NC + warp, ncol - 1);  // warps beyond the last column mirror it
-        const int x = col / s.ny;
+        const int x = bin_of(col, s);
         if (lane == 0 && !ABL(8)) {
             fence_proxy_async();
             mbar_expect_tx(bar, (unsigned)PB * 8u);
-            bulk_g2s(pbuf_s, plan + ((size_t)atm * ncol + col) * PB, (unsigned)PB * 8u, bar);
+            bulk_g2s(pbuf_s, plan + ((size_t)atm * ncol + (ABL(256) ? (col & 255) : col)) * PB, (unsigned)PB * 8u, bar);
         }
         const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
         const double* __restrict__ BI = planck_int + (size_t)atm * s.nbin * nint + (size_t)x * nint;
+        // The Planck values belong to the bin: when the CTA's columns all lie in one bin (always, if the tile width
+        // divides ny) they are staged ONCE, in warp 0's block, each warp fetching every WARPS-th row -- a quarter of the
+        // requests (each touches a sector per lane) and of the L1 lines of the per-warp form.
+        const bool shx = one_bin(ctile);
+        const unsigned bdst = shx ? bbuf0_s : bbuf_s;
         if (act && !ABL(16)) {
 #pragma unroll
             for (int k = 0; k < CH; k++) {
                 const int i = lo + k;
-                if (i < nlay) {
-                    cp_async8(bbuf_s + (unsigned)(k * rl + sl) * 8u, BL + i);
-                    cp_async8(bbuf_s + (unsigned)((CH + k) * rl + sl) * 8u, BI + i);
-                    if (k == CH - 1 || i == nlay - 1) cp_async8(bbuf_s + (unsigned)((CH + k + 1) * rl + sl) * 8u, BI + i + 1);
+                if (i < nlay && (!shx || k % WARPS == warp)) {
+                    cp_async8(bdst + (unsigned)(k * rl + sl) * 8u, BL + i);
+                    cp_async8(bdst + (unsigned)((CH + k) * rl + sl) * 8u, BI + i);
+                    if (k == CH - 1 || i == nlay - 1) cp_async8(bdst + (unsigned)((CH + k + 1) * rl + sl) * 8u, BI + i + 1);
                 }
             }
         }
@@ -544,8 +573,8 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         } else if (PAIRS) {
             PairMap<CH, NC, THREADS> pmap;
             pmap.init(cp);
-            flux_pairs_load<CH, NC, THREADS>(pmap, F_up + ao, fin_s, nlay, ncol, ctile * NC, frow);
-            flux_pairs_load<CH, NC, THREADS>(pmap, Fc_up + ao, fin_s + (unsigned)fone * 8u, nlay, ncol, ctile * NC, frow);
+            flux_pairs<CH, NC, THREADS, true>(pmap, F_up + ao, fin_s, nullptr, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
+            flux_pairs<CH, NC, THREADS, true>(pmap, Fc_up + ao, fin_s + (unsigned)fone * 8u, nullptr, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
         } else {
             FluxMap<CH, NC, THREADS> fmap;
             fmap.init(nlay, cp);
@@ -556,6 +585,17 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     };
 
     if (blockIdx.x < total) issue(blockIdx.x);
+#ifdef HELIOS_ABLATE
+    if (s.skew_ns > 0) {
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        const unsigned long long wait = (unsigned long long)(blockIdx.x / s.nsm) * s.skew_ns;
+        do {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (t1 - t0 < wait);
+    }
+#endif
     unsigned phase = 0;
     const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
     for (unsigned ct = blockIdx.x; ct < total; ct += gridDim.x) {
@@ -571,10 +611,11 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         // step constants: [0] = upper half, [1] = lower half of the lane's k-th layer
         double a[2][CH], b[2][CH], sd[2][CH], su[2][CH], Fu_reg[CH], Fcu_reg[CH], Fd_reg[CH], Fcd_reg[CH], cc[2][CH];
         const int mec = act ? sl : 0;
+        const double* __restrict__ bb = one_bin(ctile) ? bbuf0 : bbuf;
 #pragma unroll
         for (int k = 0; k < CH; k++) {
-            const double Blay = bbuf[k * rl + mec], Bint_lo = bbuf[(CH + k) * rl + mec];
-            const double Bint_hi = bbuf[(CH + k + 1) * rl + mec];  // the interface above my k-th layer
+            const double Blay = bb[k * rl + mec], Bint_lo = bb[(CH + k) * rl + mec];
+            const double Bint_hi = bb[(CH + k + 1) * rl + mec];  // the interface above my k-th layer
             const double* __restrict__ p = pbuf + (size_t)(k * NR) * rl + mec;
 #ifdef HELIOS_ABLATE
             if (ABL(128)) {  // no shared-memory reads of the constants
@@ -601,8 +642,8 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
             su[0][k] = __fma_rn(k2u, Blay, __fma_rn(k1u, Bint_hi, k0u_u));
             sd[1][k] = __fma_rn(k1l, Blay, __fma_rn(k2l, Bint_lo, k0d_l));
             su[1][k] = __fma_rn(k2l, Blay, __fma_rn(k1l, Bint_lo, k0u_l));
-            Fu_reg[k] = fin[k * frow + fme_in];
-            Fcu_reg[k] = fin[fone + k * frow + fme_in];
+            Fu_reg[k] = fin[k * frow + fme];
+            Fcu_reg[k] = fin[fone + k * frow + fme];
             Fd_reg[k] = Fcd_reg[k] = 0.0;
         }
         const double emis = __dmul_rn(pbuf[CH * NR * rl], cbuf[1]);
@@ -715,12 +756,21 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         }
         if (!skip && !ABL(2) && !ABL(32)) {
             const size_t ao = (size_t)atm * ncol * nint;
-            FluxMap<CH, NC, THREADS> fmap;
-            fmap.init(nlay, cp);
-            flux_block<CH, NC, THREADS, false>(fmap, F_down + ao, 0u, fout_dn, ncol, ctile * NC, frow);
-            flux_block<CH, NC, THREADS, false>(fmap, Fc_down + ao, 0u, fout_dn + fone, ncol, ctile * NC, frow);
-            flux_block<CH, NC, THREADS, false>(fmap, F_up + ao, 0u, fout_up, ncol, ctile * NC, frow);
-            flux_block<CH, NC, THREADS, false>(fmap, Fc_up + ao, 0u, fout_up + fone, ncol, ctile * NC, frow);
+            if (PAIRS) {
+                PairMap<CH, NC, THREADS> pmap;
+                pmap.init(cp);
+                flux_pairs<CH, NC, THREADS, false>(pmap, F_down + ao, 0u, fout_dn, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
+                flux_pairs<CH, NC, THREADS, false>(pmap, Fc_down + ao, 0u, fout_dn + fone, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
+                flux_pairs<CH, NC, THREADS, false>(pmap, F_up + ao, 0u, fout_up, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
+                flux_pairs<CH, NC, THREADS, false>(pmap, Fc_up + ao, 0u, fout_up + fone, nlay, ncol, (ABL(512) ? (ctile & 63) : ctile) * NC, frow);
+            } else {
+                FluxMap<CH, NC, THREADS> fmap;
+                fmap.init(nlay, cp);
+                flux_block<CH, NC, THREADS, false>(fmap, F_down + ao, 0u, fout_dn, ncol, ctile * NC, frow);
+                flux_block<CH, NC, THREADS, false>(fmap, Fc_down + ao, 0u, fout_dn + fone, ncol, ctile * NC, frow);
+                flux_block<CH, NC, THREADS, false>(fmap, F_up + ao, 0u, fout_up, ncol, ctile * NC, frow);
+                flux_block<CH, NC, THREADS, false>(fmap, Fc_up + ao, 0u, fout_up + fone, ncol, ctile * NC, frow);
+            }
             if (live && sl == nch - 1) {  // interface nlayer (TOA)
                 F_down[ao + (size_t)ncol * nlay + colc] = toa;
                 F_up[ao + (size_t)ncol * nlay + colc] = F_out;
@@ -1041,13 +1091,19 @@ int launch_sweep_iso(helios_ctx* ctx, double* F_down, double* F_up, const double
     constexpr int MINB = 4;
     constexpr int NC = WARPS * (32 / LPC);
     // 16-byte pieces of the flux rows (two columns of one interface) need an even column count and aligned arrays
-    const bool pairs = ((s.nbin * s.ny) & 1) == 0 && (reinterpret_cast<size_t>(F_up) & 15) == 0;
+    const bool pairs = ((s.nbin * s.ny) & 1) == 0 && ((reinterpret_cast<size_t>(F_up) | reinterpret_cast<size_t>(F_down)) & 15) == 0;
     auto kern = pairs ? k_sweep_iso<CH, LPC, NOBEAM, WARPS, MINB, true> : k_sweep_iso<CH, LPC, NOBEAM, WARPS, MINB, false>;
     using CS = CtaShape<CH, NOBEAM ? 3 : 5, 1, CH, Log2<LPC>::v, 32 / LPC, WARPS>;
     const size_t smem = (size_t)CS::cta_doubles(g.rs) * sizeof(double);
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (long long)((s.nbin * s.ny + NC - 1) / NC) * s.nbatch;
     const int grid = resident_grid(ctx, kern, WARPS * 32, smem, total);
+    s.cp = CS::cpitch(g.rs);
+    if ((unsigned long long)s.nbin * s.ny * s.ny >= (1ull << 32)) {
+        helios_set_error("planned sweep: %d x %d columns exceed the range of the column -> bin multiply", s.nbin, s.ny);
+        return HELIOS_ERR_ARG;
+    }
+    s.ny_magic = (unsigned)((1ull << 32) / (unsigned)s.ny + 1ull);
     kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, planck_lay, plan, albedo, s);
     HLAUNCHED(ctx);
     return HELIOS_OK;
@@ -1062,15 +1118,24 @@ int launch_sweep_noniso(helios_ctx* ctx, double* F_down, double* F_up, double* F
     // spills inside the passes and was measured slower.  CTAs of 4 warps (4 columns = one 32-byte sector per flux row).
     constexpr int WARPS = 4;
     constexpr int MINB = (CH >= 4) ? 3 : 4;
-    const bool pairs = (ncol & 1) == 0 && ((reinterpret_cast<size_t>(F_up) | reinterpret_cast<size_t>(Fc_up)) & 15) == 0;
+    const bool pairs = (ncol & 1) == 0 && ((reinterpret_cast<size_t>(F_up) | reinterpret_cast<size_t>(Fc_up) |
+                                            reinterpret_cast<size_t>(F_down) | reinterpret_cast<size_t>(Fc_down)) & 15) == 0;
     auto kern = pairs ? k_sweep_noniso<CH, NOBEAM, WARPS, MINB, true> : k_sweep_noniso<CH, NOBEAM, WARPS, MINB, false>;
     using CS = CtaShape<CH, NOBEAM ? 8 : 12, 2, 2 * CH + 1, 5, 1, WARPS>;
     const size_t smem = (size_t)CS::cta_doubles(g.rs) * sizeof(double);
     HCUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total = (long long)((ncol + WARPS - 1) / WARPS) * s.nbatch;
     int grid = resident_grid(ctx, kern, WARPS * 32, smem, total);
+    s.cp = CS::cpitch(g.rs);
+    if ((unsigned long long)s.nbin * s.ny * s.ny >= (1ull << 32)) {
+        helios_set_error("planned sweep: %d x %d columns exceed the range of the column -> bin multiply", s.nbin, s.ny);
+        return HELIOS_ERR_ARG;
+    }
+    s.ny_magic = (unsigned)((1ull << 32) / (unsigned)s.ny + 1ull);
 #ifdef HELIOS_ABLATE
     if (const char* e = getenv("HELIOS_SWEEP_ABLATE")) s.ablate = atoi(e);
+    if (const char* e = getenv("HELIOS_SWEEP_SKEW_NS")) s.skew_ns = atoi(e);
+    s.nsm = ctx->num_sms;
     if (const char* e = getenv("HELIOS_SWEEP_CTAS_PER_SM")) grid = std::min(grid, ctx->num_sms * atoi(e));
 #endif
     kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, Fc_down, Fc_up, planck_lay, planck_int, plan, albedo, s);

@@ -73,7 +73,7 @@ def rayleigh_table(ktemp, kpress, lam_c):
 
 def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=28, plancktable_dim=8000,
                plancktable_step=2, kcoeff_mixing="RO", n_species=10, table_scale=1.0, T_star=6117.0, g=930.0,
-               T_lay=None, seed=SEED, tables=None):
+               T_lay=None, seed=SEED, tables=None, ngauss=20):
     """`tables`: optional dict scale -> (opac_k, opac_scat_cross, opac_meanmass) shared between the stores of a
     grid, filled on first use (the stores then reference ONE host copy per scaling)"""
     rng = np.random.default_rng(seed)
@@ -149,7 +149,7 @@ def make_store(config="C1", ctx=None, nbin=None, nlayer=100, ntemp=120, npress=2
     if config == "C4":
         q.gauss_y = np.array([0.0])
     else:
-        q.gauss_y = 0.5 * leggauss(20)[0] + 0.5
+        q.gauss_y = 0.5 * leggauss(int(ngauss))[0] + 0.5
     q.ny = np.int32(q.gauss_y.size)
     host.set_up_numerical_parameters(q)  # gauss_weight and the numerical limits
     shared = tables.get(table_scale) if tables is not None else None

@@ -480,6 +480,19 @@ FLIPPED = [("C1", 31), ("C1", 100), ("C1", 128), ("C1", 203), ("C2", 33), ("C2",
 
 @pytest.mark.parametrize("config,nlayer,flip", [(c, n, False) for c, n in SHAPES] + [(c, n, True) for c, n in FLIPPED])
 def test_sweep_tile_shapes(ctx, config, nlayer, flip):
+    _sweep_tile_shape(ctx, config, nlayer, flip)
+
+
+@pytest.mark.parametrize("config,nlayer,ngauss", [("C1", 100, 7), ("C1", 33, 7), ("C1", 100, 6), ("C2", 100, 7),
+                                                  ("C2", 33, 7), ("C2", 100, 6), ("C2", 98, 3)])
+def test_sweep_column_counts(ctx, config, nlayer, ngauss):
+    """the same checks with other numbers of Gauss points per bin: 5 x 7 = 35 and 5 x 3 = 15 columns are odd (the fluxes
+    then move as 8-byte pieces instead of 16-byte column pairs), and with 7, 6 or 3 points per bin the column tiles of a
+    CTA straddle bins (the Planck values are then staged per warp instead of once per CTA)"""
+    _sweep_tile_shape(ctx, config, nlayer, False, ngauss=ngauss)
+
+
+def _sweep_tile_shape(ctx, config, nlayer, flip, **store_args):
     """every instantiation of the layer-parallel sweeps (layers per lane 1..8, 16 / 32 lanes per column), with and
     without a partial top chunk and with every lane of a column in use (128 / 256 layers): two consecutive flux solves
     against the reference's kernel (1e-10); where a sweep plan exists (isothermal <= 256 layers, non-isothermal <= 128)
@@ -488,7 +501,7 @@ def test_sweep_tile_shapes(ctx, config, nlayer, flip):
     solves.  5 bins x 20 Gauss points = 100 columns: the last column tile of the builders is partial."""
     from util import HostMirror, restore
     q = synthetic.make_store(config, ctx=ctx, nbin=5, nlayer=nlayer, ntemp=12, npress=8, plancktable_dim=700,
-                             plancktable_step=10)
+                             plancktable_step=10, **store_args)
     q.mu_star = np.float64(np.cos((180 - 50.0) * np.pi / 180.0))
     if flip:
         q.dir_beam = np.int32(1 - int(q.dir_beam))

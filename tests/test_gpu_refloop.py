@@ -83,7 +83,10 @@ def test_loops_against_the_references_own_computation_py(ctx, tmp_path, config):
           "the nearest reference run %.2e K (reference run-to-run %.2e K), TOA spectrum %.2e (run-to-run %.2e)" %
           (config, ours["rad"], rad_ref, ours["conv"], conv_ref, dT, spread_T, ds, spread_s))
     assert all(str(r["status"]) == "converged" for r in refs)
-    assert min(rad_ref) * 0.7 <= ours["rad"] <= max(rad_ref) * 1.3, (ours["rad"], rad_ref)
+    # the reference's own count is not reproducible (fp64 atomics in its band integration, K:2484-2509: three runs of
+    # this case have given 8492, 9372 and 18022 iterations), so the count is a sanity bound; the converged profile and
+    # spectrum below are the parity check
+    assert min(rad_ref) * 0.5 <= ours["rad"] <= max(rad_ref) * 2.0, (ours["rad"], rad_ref)
     assert (ours["conv"] > 0) == (max(conv_ref) > 0), (ours["conv"], conv_ref)
     assert dT <= max(0.01, 2 * spread_T), (dT, spread_T)
     assert ds <= max(1e-8, 2 * spread_s), (ds, spread_s)
