@@ -314,6 +314,10 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     }
     __syncthreads();
 
+    const double* bbuf0 = smem + 2 + PB;  // warp 0's Planck block
+    const unsigned bbuf0_s = smem_u32(bbuf0);
+    auto one_bin = [&](int ctile) { return bin_of(ctile * NC, s) == bin_of(min(ctile * NC + NC - 1, ncol - 1), s); };
+
     auto issue = [&](unsigned ct) {
         const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
         const int ctile = (int)(ct - atm * nct);
@@ -325,11 +329,15 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
             mbar_expect_tx(bar, (unsigned)PB * 8u);
             bulk_g2s(pbuf_s, plan + ((size_t)atm * ntw + tile) * PB, (unsigned)PB * 8u, bar);
         }
+        // The Planck values belong to the bin: when the CTA's columns all lie in one bin they are staged ONCE, in column
+        // slot 0 of warp 0's block, each warp fetching every WARPS-th row (as in the non-isothermal sweep)
         const double* __restrict__ BL = planck_lay + (size_t)atm * (nlay + 2) * s.nbin + (size_t)x * (nlay + 2);
-        if (act) {
+        const bool shx = one_bin(ctile);
+        if (act && (!shx || cw == 0)) {
+            const unsigned bdst = shx ? bbuf0_s + (unsigned)sl * 8u : bbuf_s + (unsigned)me * 8u;
 #pragma unroll
             for (int k = 0; k < CH; k++)
-                if (lo + k < nlay) cp_async8(bbuf_s + (unsigned)(k * rl + me) * 8u, BL + lo + k);
+                if (lo + k < nlay && (!shx || k % WARPS == warp)) cp_async8(bdst + (unsigned)(k * rl) * 8u, BL + lo + k);
         }
         if (sl < 3) cp_async8(cbuf_s + (unsigned)(cw * 4 + sl) * 8u, sl == 0 ? BL + nlay : (sl == 1 ? BL + nlay + 1 : albedo + x));
         if (PAIRS) {
@@ -360,9 +368,10 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         __syncthreads();  // everybody's flux copies have landed; the previous tile's cooperative stores are done
         double a[CH], b[CH], sd[CH], su[NOBEAM ? 1 : CH], Fu_reg[CH], Fd_reg[CH], cc[CH];
         const int mec = act ? me : cw * rs;  // idle lanes mirror chunk 0 of their column; nothing of theirs is consumed
+        const double* __restrict__ bb = one_bin(ctile) ? bbuf0 + (act ? sl : 0) : bbuf + mec;
 #pragma unroll
         for (int k = 0; k < CH; k++) {
-            const double B = bbuf[k * rl + mec];
+            const double B = bb[k * rl];
             a[k] = pbuf[(k * NR + 0) * rl + mec];
             b[k] = pbuf[(k * NR + 1) * rl + mec];
             const double k1 = pbuf[(k * NR + 2) * rl + mec];
