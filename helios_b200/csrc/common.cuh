@@ -6,6 +6,7 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 #include "../../include/helios_b200.h"
 
 // physical constants: the literals of the reference device code (K:36-41), so that both sides
@@ -69,6 +70,7 @@ struct helios_ctx {
     helios_comm_state* comm = nullptr;
     BatchDesc batch;
     bool capturing = false;  // helios_graph_begin .. helios_graph_end
+    std::vector<void*> deferred_free;  // buffers released while capturing (a free synchronises: illegal inside a capture)
     unsigned long long capture_launches0 = 0;
     // Direct-beam arrays known to hold only (signed) zeros: written by fdir_* with dir_beam == 0 and not
     // touched since (every write to device memory goes through this library).  fband_* then skips loading

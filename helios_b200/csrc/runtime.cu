@@ -201,6 +201,29 @@ struct helios_graph {
     unsigned long long launches = 0;  // kernel launches recorded (bench bookkeeping)
 };
 
+static void graph_release(helios_graph* g) {
+    cudaSetDevice(g->device);
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    delete g;
+}
+
+// Graph objects released while some context of the process is capturing (a host garbage collector picks its own moment)
+// are destroyed when that capture ends: destroying a graph inside a capture invalidates it.
+static std::mutex g_graph_mu;
+static int g_capturing = 0;
+static std::vector<helios_graph*> g_graph_late;
+
+static void graph_capture_mark(int delta) {
+    std::vector<helios_graph*> late;
+    {
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        g_capturing += delta;
+        if (g_capturing == 0) late.swap(g_graph_late);
+    }
+    for (helios_graph* g : late) graph_release(g);
+}
+
 int helios_graph_begin(helios_ctx* ctx) {
     HCTX(ctx);
     if (ctx->capturing) {
@@ -209,6 +232,7 @@ int helios_graph_begin(helios_ctx* ctx) {
     }
     HCUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
+    graph_capture_mark(+1);
     ctx->capture_launches0 = ctx->launches;
     return HELIOS_OK;
 }
@@ -226,6 +250,18 @@ int helios_graph_end(helios_ctx* ctx, helios_graph** out) {
     g->launches = ctx->launches - ctx->capture_launches0;
     ctx->launches = ctx->capture_launches0;  // recorded, not executed
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+    graph_capture_mark(-1);
+    {
+        std::vector<void*> late;
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            late.swap(ctx->deferred_free);
+        }
+        if (!late.empty()) {
+            cudaStreamSynchronize(ctx->stream);
+            for (void* p : late) cudaFree(p);
+        }
+    }
     if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
     if (e != cudaSuccess) {
         if (g->graph) cudaGraphDestroy(g->graph);
@@ -246,10 +282,14 @@ int helios_graph_launch(helios_ctx* ctx, helios_graph* g) {
 
 int helios_graph_destroy(helios_graph* g) {
     if (g == nullptr) return HELIOS_OK;
-    cudaSetDevice(g->device);
-    if (g->exec) cudaGraphExecDestroy(g->exec);
-    if (g->graph) cudaGraphDestroy(g->graph);
-    delete g;
+    {
+        std::lock_guard<std::mutex> lk(g_graph_mu);
+        if (g_capturing > 0) {
+            g_graph_late.push_back(g);
+            return HELIOS_OK;
+        }
+    }
+    graph_release(g);
     return HELIOS_OK;
 }
 
@@ -314,6 +354,13 @@ int helios_buf_free(helios_ctx* ctx, void* dptr) {
         }
         ctx->bytes_allocated -= it->second;
         ctx->allocs.erase(it);
+    }
+    if (ctx->capturing) {
+        // (a host-side garbage collector may release an array at any time) synchronising or freeing would invalidate the
+        // capture: the buffer is released when the capture ends
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->deferred_free.push_back(dptr);
+        return HELIOS_OK;
     }
     // kernels still in flight on the stream may use the buffer
     HCUDA(cudaStreamSynchronize(ctx->stream));

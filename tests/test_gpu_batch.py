@@ -147,3 +147,23 @@ def test_unbatched_entry_points_refuse_batch_mode(ctx):
             ctx.call("temp_inter", qb.dev_T_lay, qb.dev_T_int, int(qb.ninterface) + 1)
     finally:
         qb.leave()
+
+
+def test_array_released_during_a_capture(ctx):
+    """a host garbage collector may release a device array or a graph while launches are being recorded: the free
+    (which synchronises) and the graph destruction are deferred to the end of the capture instead of invalidating it"""
+    a = ctx.to_device(np.arange(1000.0))
+    victim = ctx.to_device(np.zeros(1 << 16))
+    b = ctx.zeros(1000)
+    with ctx.capture() as g:
+        del victim  # -> helios_buf_free inside the capture
+        b.copy_from(a)
+    g.launch()
+    ctx.synchronize()
+    assert np.array_equal(b.get(), np.arange(1000.0))
+    b.fill_zero()
+    with ctx.capture() as g:  # rebinding `g` releases the first graph inside the second capture
+        b.copy_from(a)
+    g.launch()
+    ctx.synchronize()
+    assert np.array_equal(b.get(), np.arange(1000.0))
