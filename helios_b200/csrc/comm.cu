@@ -106,6 +106,7 @@ int helios_comm_fused_next(helios_ctx* ctx, int n, FusedComm* fc) {
     fc->world = c->world;
     fc->slot = c->slot;
     fc->data_bytes = c->data_bytes;
+    fc->ll_off = c->ll_off;
     fc->seq_dev = c->seq_dev;
     fc->ticket = c->fused_ticket;
     return HELIOS_OK;
@@ -138,7 +139,8 @@ int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles, u
     c->slot = slot_doubles;
     c->data_bytes = (size_t)2 * world * slot_doubles * sizeof(double);
     c->data_bytes = (c->data_bytes + 127) / 128 * 128;
-    const size_t total = c->data_bytes + (size_t)world * 128;
+    c->ll_off = c->data_bytes + (size_t)world * 128;
+    const size_t total = c->ll_off + (size_t)2 * world * slot_doubles * 16;
     cudaError_t e = cudaMalloc(&c->own, total);
     if (e != cudaSuccess) {
         delete c;

@@ -11,8 +11,10 @@ struct helios_comm_state {
     // last block advances it, so that a recorded launch (CUDA graph) can be replayed -- a by-value sequence number would
     // be frozen into the graph.  All ranks make the same sequence of exchanges, so their counters stay in step.
     unsigned long long* seq_dev = nullptr;
-    // own mailbox: [2 banks][world][slot] doubles, then [world] flags (u64), flags padded to 128 B
+    // own mailbox: [2 banks][world][slot] doubles, then [world] flags (u64), flags padded to 128 B (the stand-alone
+    // kernel); then, at ll_off, [2 banks][world][slot] 16-byte packet pairs (the fused form, no flags)
     void* own = nullptr;
+    size_t ll_off = 0;
     void* peers[COMM_MAX_WORLD] = {nullptr};
     bool opened[COMM_MAX_WORLD] = {false};
     void** peers_dev = nullptr;
@@ -29,10 +31,27 @@ struct CommPeers {
 struct FusedComm {
     CommPeers peers;
     int rank = 0, world = 0, slot = 0;
-    size_t data_bytes = 0;
+    size_t data_bytes = 0, ll_off = 0;
     unsigned long long* seq_dev = nullptr;
     unsigned* ticket = nullptr;
 };
+
+// One double as two self-validating 8-byte packets {32 data bits, round}: the receiver needs no flag and the sender no
+// fence -- a packet that carries the current round number has arrived whole (8-byte stores are not torn), whatever the
+// order in which NVLink delivers the stores.  A slot is reused every second round (two banks) and starts out zero, so a
+// stale packet never carries the round that is being waited for (rounds count from 1).
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned round) {
+    const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(round), "r"(hi), "r"(round)
+                 : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned round) {
+    unsigned lo, f0, hi, f1;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(p) : "memory");
+    } while (f0 != round || f1 != round);
+    return __hiloint2double((int)hi, (int)lo);
+}
 
 __device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
     unsigned long long v;

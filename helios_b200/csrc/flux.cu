@@ -55,12 +55,31 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         const size_t base = ((size_t)i * nbin + x0) * ny;
         if (ny > 1) {
             const int n = nx * ny;
-            for (int k = threadIdx.x; k < n; k += blockDim.x) {
-                const int xl = k / ny, y = k - xl * ny;
-                const int d = xl * pitch + y;
-                s_dn[d] = F_down_wg[base + k];
-                s_up[d] = F_up_wg[base + k];
-                s_dr[d] = F_dir_wg[base + k];
+            // four rounds of loads in flight per thread before the first is consumed: the staging is a handful of
+            // round trips to HBM, and a loop that stores each value as it arrives pays every one of them in full
+            constexpr int U = 4;
+            for (int k0 = threadIdx.x; k0 < n; k0 += blockDim.x * U) {
+                double v_dn[U], v_up[U], v_dr[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k = k0 + u * blockDim.x;
+                    if (k < n) {
+                        v_dn[u] = F_down_wg[base + k];
+                        v_up[u] = F_up_wg[base + k];
+                        v_dr[u] = F_dir_wg[base + k];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int k = k0 + u * blockDim.x;
+                    if (k < n) {
+                        const int xl = k / ny, y = k - xl * ny;
+                        const int d = xl * pitch + y;
+                        s_dn[d] = v_dn[u];
+                        s_up[d] = v_up[u];
+                        s_dr[d] = v_dr[u];
+                    }
+                }
             }
             __syncthreads();
         }
@@ -133,48 +152,50 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         ticket[slot] = 0u;
     }
     // Wavelength sharding, fused form (helios_comm_set_fused): the sum over ranks of the per-interface totals runs in THIS
-    // launch.  The block that finishes an interface stores this rank's two partial totals straight into slot `rank` of
-    // every peer's mailbox over NVLink; the block that finishes the LAST interface raises this rank's flag in every
-    // mailbox, waits for the peers' flags and adds the world's slots in rank order -- every rank obtains bitwise the same
-    // totals.  One launch instead of integration + exchange kernel.
+    // launch, with no fence and no flag.  Every double travels as two 8-byte packets {32 data bits, round number}
+    // (comm.cuh: ll_store / ll_load): the block that finishes an interface stores this rank's two totals straight into
+    // slot `rank` of every mailbox over NVLink (thread r -> peer r); the block that finishes the LAST interface of this
+    // rank polls its own mailbox until every packet of the round has arrived -- a packet is valid when it carries the
+    // round number -- and adds the world's slots in rank order: every rank obtains bitwise the same totals, one NVLink
+    // latency after the slowest rank's integration.
     if (fc.world > 0) {
         __shared__ bool all_done;
-        __shared__ unsigned long long round;
+        __shared__ unsigned round_s;
+        __shared__ double tot_s[2];
         if (threadIdx.x == 0) {
             all_done = false;
-            round = *fc.seq_dev + 1ull;  // read before this block's ticket: the counter only advances after the last ticket
+            // read before this block's ticket: the counter only advances after the last ticket of the launch
+            round_s = (unsigned)(*fc.seq_dev + 1ull);
             if (last) {
-                const int bank = (int)(round & 1ull);
-                const double up = F_up_tot[i], dn = F_down_tot[i];
-                for (int r = 0; r < fc.world; r++) {
-                    double* data = reinterpret_cast<double*>(fc.peers.p[r]) + ((size_t)bank * fc.world + fc.rank) * fc.slot;
-                    data[i] = up;
-                    data[nint + i] = dn;
-                }
-                __threadfence_system();
+                tot_s[0] = F_up_tot[i];
+                tot_s[1] = F_down_tot[i];
+            }
+        }
+        __syncthreads();
+        const unsigned round = round_s;
+        const int bank = (int)(round & 1u);
+        if (last) {
+            if ((int)threadIdx.x < fc.world) {
+                uint4* box = reinterpret_cast<uint4*>(reinterpret_cast<char*>(fc.peers.p[threadIdx.x]) + fc.ll_off) +
+                             ((size_t)bank * fc.world + fc.rank) * fc.slot;
+                ll_store(box + i, tot_s[0], round);
+                ll_store(box + nint + i, tot_s[1], round);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();  // this block's F_*_tot[i] before the final block's sums (same device)
                 all_done = atomicAdd(fc.ticket, 1u) == (unsigned)nint - 1;
             }
         }
         __syncthreads();
         if (all_done) {
-            const unsigned long long seq = round;
-            if ((int)threadIdx.x < fc.world) {
-                unsigned long long* flags = reinterpret_cast<unsigned long long*>(
-                    reinterpret_cast<char*>(fc.peers.p[threadIdx.x]) + fc.data_bytes);
-                st_flag(flags + 16 * fc.rank, seq);
-                const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(
-                    reinterpret_cast<char*>(fc.peers.p[fc.rank]) + fc.data_bytes);
-                while (ld_flag(mine + 16 * threadIdx.x) < seq) __nanosleep(64);
-            }
-            __syncthreads();
-            __threadfence_system();
-            const int bank = (int)(seq & 1ull);
-            const volatile double* box = reinterpret_cast<const volatile double*>(fc.peers.p[fc.rank]);
+            const uint4* box = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(fc.peers.p[fc.rank]) + fc.ll_off) +
+                               (size_t)bank * fc.world * fc.slot;
             for (int t = threadIdx.x; t < nint; t += blockDim.x) {
                 double a = 0.0, b = 0.0;
                 for (int r = 0; r < fc.world; r++) {
-                    a += box[((size_t)bank * fc.world + r) * fc.slot + t];
-                    b += box[((size_t)bank * fc.world + r) * fc.slot + nint + t];
+                    a += ll_load(box + (size_t)r * fc.slot + t, round);
+                    b += ll_load(box + (size_t)r * fc.slot + nint + t, round);
                 }
                 F_up_tot[t] = a;
                 F_down_tot[t] = b;
@@ -183,7 +204,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
             __syncthreads();
             if (threadIdx.x == 0) {
                 *fc.ticket = 0u;
-                *fc.seq_dev = seq;  // the next exchanging launch (stream order) sees the advanced counter
+                *fc.seq_dev += 1ull;  // the next exchanging launch (stream order) sees the advanced counter
             }
         }
     }
