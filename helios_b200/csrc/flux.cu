@@ -255,6 +255,7 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
         if (c_p_lay) c_p_lay += v0;
         if (mmm_lay) mmm_lay += v0;
     }
+    int my_flags = 0;  // convergence flags this thread has just written (the fused tail sums them without re-reading)
     if (!skip) {
     // phase 1: flux divergence and smoothing force, from the OLD temperatures
     for (int i = threadIdx.x; i < nl; i += blockDim.x) {
@@ -328,6 +329,7 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
             else
                 ok = fabs(s.F_intern - F_net[0]) / (F_down_tot[nl] + s.F_intern) < s.local_limit;
             abrt[i] = ok ? 1 : 0;
+            my_flags += ok ? 1 : 0;
         } else {
             if (s.itervalue == 0) prefactor[i] = 1e-2;
             if (s.itervalue == 6000) prefactor[i] = 1e-3;
@@ -348,8 +350,11 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
         // fused tail: what k_abort_sum + k_iter_advance do, without two more launches per iteration
         __shared__ int red_i[256];
         __syncthreads();
-        int a = 0;
-        for (int i = threadIdx.x; i < nl + 1; i += blockDim.x) a += abrt[i];
+        int a = my_flags;
+        if (skip || s.conv != 0) {  // flags not rewritten by this launch: read them
+            a = 0;
+            for (int i = threadIdx.x; i < nl + 1; i += blockDim.x) a += abrt[i];
+        }
         red_i[threadIdx.x] = a;
         __syncthreads();
         for (int w = blockDim.x / 2; w > 0; w >>= 1) {
@@ -364,10 +369,14 @@ k_temp_iter(const double* __restrict__ F_down_tot, const double* __restrict__ F_
                 s.converged_at[b] = s.itervalue + 1;  // iterations completed
             }
             // the LAST block to finish advances the iteration counter: by then every block has read it
-            __threadfence();
-            if (atomicAdd(s.ticket, 1u) == gridDim.x - 1) {
-                *s.ticket = 0u;
+            if (gridDim.x == 1) {
                 *s.iter_w = s.itervalue + 1;
+            } else {
+                __threadfence();
+                if (atomicAdd(s.ticket, 1u) == gridDim.x - 1) {
+                    *s.ticket = 0u;
+                    *s.iter_w = s.itervalue + 1;
+                }
             }
         }
     }
