@@ -34,6 +34,9 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                  const double* __restrict__ deltalambda, double* __restrict__ partial, unsigned* __restrict__ ticket,
                  double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net, FusedComm fc) {
     extern __shared__ double sm[];
+    // launched with programmatic stream serialisation: the blocks may be resident before the preceding grid (the flux
+    // sweep) has finished; nothing it wrote is read before this point (a no-op for an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
     double* s_dn = sm;
     double* s_up = sm + (size_t)xb * pitch;
@@ -590,10 +593,22 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
         helios_set_error("helios_integrate_flux_double: the fused flux all-reduce is not available in batch mode");
         return HELIOS_ERR_STATE;
     }
-    k_band_integrate<<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band,
-                                                              F_up_band, F_dir_band, gauss_weight, nbin,
-                                                              ny, xb, deltalambda, scratch + 8, ctx->integ_ticket,
-                                                              F_down_tot, F_up_tot, F_net, fc);
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(IF_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        double* part = scratch + 8;
+        HCUDA(cudaLaunchKernelEx(&cfg, k_band_integrate, F_down_wg, F_up_wg, F_dir_wg, F_down_band, F_up_band, F_dir_band,
+                                 gauss_weight, nbin, ny, xb, deltalambda, part, ctx->integ_ticket, F_down_tot, F_up_tot,
+                                 F_net, fc));
+    }
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
