@@ -366,6 +366,8 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
         const int colc = live ? col : ncol - 1;
         // ---- lift the staged tile into registers
+        // (batch) the atmosphere's converged flag, requested before the waits so that its latency hides behind them
+        const int done_flag = s.done != nullptr ? __ldg(s.done + atm) : 0;
         cp_async_wait_all();
         mbar_wait(bar, phase);
         phase ^= 1u;
@@ -395,7 +397,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
         if (ct + gridDim.x < total) issue(ct + gridDim.x);
         else pdl_launch_dependents();  // last tile of this CTA: a dependent launch (the band integration) may move in
-        const bool skip = s.done != nullptr && s.done[atm] != 0;  // uniform per CTA
+        const bool skip = done_flag != 0;  // uniform per CTA
 
         double F_out = 0.0;
         if (!skip) {
@@ -618,6 +620,8 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         const int col = ctile * NC + warp;
         const bool live = col < ncol;  // uniform per warp
         const int colc = live ? col : ncol - 1;
+        // (batch) the atmosphere's converged flag, requested before the waits so that its latency hides behind them
+        const int done_flag = s.done != nullptr ? __ldg(s.done + atm) : 0;
         cp_async_wait_all();
         if (!ABL(8)) mbar_wait(bar, phase);
         phase ^= 1u;
@@ -667,7 +671,7 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
         if (ct + gridDim.x < total) issue(ct + gridDim.x);
         else pdl_launch_dependents();  // last tile of this CTA: a dependent launch (the band integration) may move in
-        const bool skip = s.done != nullptr && s.done[atm] != 0;  // uniform per CTA
+        const bool skip = done_flag != 0;  // uniform per CTA
 
         double F_out = 0.0;
         if (!skip) {
