@@ -43,6 +43,7 @@ struct PlanScalars {
     const int* done;  // batch: converged atmospheres are skipped (their fluxes stay as they are)
     int cp;             // column pitch of the staged flux rows (CtaShape::cpitch), formed by the launcher
     unsigned ny_magic;  // floor(2^32 / ny) + 1: column -> bin by one multiply-high (exact below 2^32 / ny columns)
+    unsigned nct_magic;  // the same for CTA tile -> atmosphere (0: divide)
 #ifdef HELIOS_ABLATE
     int ablate;  // experiment builds only (scripts/exp_ablate.sh): bit mask of parts of the sweep to leave out
     int skew_ns;  // experiment: co-resident CTA r (blockIdx.x / SMs) starts r * skew_ns late
@@ -55,6 +56,11 @@ struct PlanScalars {
 #define ABL(bit) false
 #endif
 
+// CTA tile -> atmosphere of a batch: nothing for one atmosphere, one multiply-high when the launcher found it exact
+__device__ __forceinline__ unsigned atm_of(unsigned ct, unsigned nct, const PlanScalars& s) {
+    if (s.nbatch == 1) return 0u;
+    return s.nct_magic != 0u ? __umulhi(ct, s.nct_magic) : ct / nct;
+}
 __device__ __forceinline__ int bin_of(int col, const PlanScalars& s) {
     return s.ny == 1 ? col : (int)__umulhi((unsigned)col, s.ny_magic);
 }
@@ -323,7 +329,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     auto one_bin = [&](int ctile) { return bin_of(ctile * NC, s) == bin_of(min(ctile * NC + NC - 1, ncol - 1), s); };
 
     auto issue = [&](unsigned ct) {
-        const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
+        const unsigned atm = atm_of(ct, nct, s);
         const int ctile = (int)(ct - atm * nct);
         const unsigned tile = min((unsigned)ctile * WARPS + warp, ntw - 1u);  // warps beyond the last column mirror it
         const int colc = min((int)tile * CPW + cw, ncol - 1);
@@ -360,7 +366,7 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
     unsigned phase = 0;
     const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
     for (unsigned ct = blockIdx.x; ct < total; ct += gridDim.x) {
-        const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
+        const unsigned atm = atm_of(ct, nct, s);
         const int ctile = (int)(ct - atm * nct);
         const int col = (ctile * WARPS + warp) * CPW + cw;
         const bool live = col < ncol;  // uniform per segment; dead segments still shuffle
@@ -556,7 +562,7 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     auto one_bin = [&](int ctile) { return bin_of(ctile * NC, s) == bin_of(min(ctile * NC + NC - 1, ncol - 1), s); };
 
     auto issue = [&](unsigned ct) {
-        const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
+        const unsigned atm = atm_of(ct, nct, s);
         const int ctile = (int)(ct - atm * nct);
         const int col = min(ctile * NC + warp, ncol - 1);  // warps beyond the last column mirror it
         const int x = bin_of(col, s);
@@ -615,7 +621,7 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
     unsigned phase = 0;
     const double toa_scale = (1.0 - s.dir_beam) * s.f_factor * ((s.Rstar / s.a) * (s.Rstar / s.a)) * hc::PI;
     for (unsigned ct = blockIdx.x; ct < total; ct += gridDim.x) {
-        const unsigned atm = s.nbatch == 1 ? 0u : ct / nct;  // (no division for a single atmosphere)
+        const unsigned atm = atm_of(ct, nct, s);
         const int ctile = (int)(ct - atm * nct);
         const int col = ctile * NC + warp;
         const bool live = col < ncol;  // uniform per warp
@@ -1081,6 +1087,12 @@ bool noniso_geom(int nlay, bool nobeam, NonisoGeom& g) {
     return true;
 }
 
+// floor(2^32 / d) + 1 if n -> n / d by multiply-high is exact for every n < total (n * d < 2^32 suffices), else 0
+static unsigned tile_magic(unsigned long long total, unsigned d) {
+    if (d <= 1u || total * d >= (1ull << 32)) return 0u;
+    return (unsigned)((1ull << 32) / d + 1ull);
+}
+
 // persistent grid: as many CTAs as fit per SM (registers, shared memory), capped by the work.  The occupancy query is
 // cached per (kernel, shared-memory size): launches may sit inside a CUDA-graph capture.
 template <typename K>
@@ -1123,6 +1135,7 @@ int launch_sweep_iso(helios_ctx* ctx, double* F_down, double* F_up, const double
         return HELIOS_ERR_ARG;
     }
     s.ny_magic = (unsigned)((1ull << 32) / (unsigned)s.ny + 1ull);
+    s.nct_magic = tile_magic((unsigned long long)total, (unsigned)((s.nbin * s.ny + NC - 1) / NC));
     kern<<<grid, WARPS * 32, smem, ctx->stream>>>(F_down, F_up, planck_lay, plan, albedo, s);
     HLAUNCHED(ctx);
     return HELIOS_OK;
@@ -1151,6 +1164,7 @@ int launch_sweep_noniso(helios_ctx* ctx, double* F_down, double* F_up, double* F
         return HELIOS_ERR_ARG;
     }
     s.ny_magic = (unsigned)((1ull << 32) / (unsigned)s.ny + 1ull);
+    s.nct_magic = tile_magic((unsigned long long)total, (unsigned)((ncol + WARPS - 1) / WARPS));
 #ifdef HELIOS_ABLATE
     if (const char* e = getenv("HELIOS_SWEEP_ABLATE")) s.ablate = atoi(e);
     if (const char* e = getenv("HELIOS_SWEEP_SKEW_NS")) s.skew_ns = atoi(e);
