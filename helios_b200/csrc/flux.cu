@@ -14,6 +14,16 @@
 // ------------------------------------------------------------------------------------------------
 #define IF_THREADS 256
 
+#ifdef HELIOS_INTEG_TIMING  // experiment builds only (scripts/exp_integ_timing.py): phase stamps of one block, SM cycles
+__device__ long long g_integ_t[8];
+#define ISTAMP(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 50 && blockIdx.z == 0) g_integ_t[k] = clock64(); } while (0)
+extern "C" int helios_debug_integ_timing(long long* out8) {
+    return cudaMemcpyFromSymbol(out8, g_integ_t, sizeof(g_integ_t)) == cudaSuccess ? 0 : 1;
+}
+#else
+#define ISTAMP(k) do { } while (0)
+#endif
+
 __device__ __forceinline__ double block_sum(double v, double* red) {
     red[threadIdx.x] = v;
     __syncthreads();
@@ -36,7 +46,9 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     extern __shared__ double sm[];
     // launched with programmatic stream serialisation: the blocks may be resident before the preceding grid (the flux
     // sweep) has finished; nothing it wrote is read before this point (a no-op for an ordinary launch)
+    ISTAMP(0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    ISTAMP(1);
     const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
     double* s_dn = sm;
     double* s_up = sm + (size_t)xb * pitch;
@@ -85,6 +97,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                 }
             }
             __syncthreads();
+            ISTAMP(2);
         }
         for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
             double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
@@ -109,6 +122,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
             t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
         }
         if (ny > 1) __syncthreads();  // the next tile overwrites the staging area
+        ISTAMP(3);
     }
     // Sum over wavelength in the same launch (K:2484-2509): fixed tree over this block's bins, then the LAST block
     // of the interface to finish adds the per-block partial sums in block order -- a fixed summation order, bitwise
@@ -137,8 +151,10 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         }
         partial[(slot * ntile + blockIdx.x) * 2] = t_up;
         partial[(slot * ntile + blockIdx.x) * 2 + 1] = t_dn;
+        ISTAMP(4);
         __threadfence();
         last = atomicAdd(ticket + slot, 1u) == (unsigned)ntile - 1;
+        ISTAMP(5);
     }
     __syncthreads();
     if (last && threadIdx.x == 0) {
@@ -154,6 +170,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         F_net[slot] = up - dn;
         ticket[slot] = 0u;
     }
+    ISTAMP(6);
     // Wavelength sharding, fused form (helios_comm_set_fused): the sum over ranks of the per-interface totals runs in THIS
     // launch, with no fence and no flag.  Every double travels as two 8-byte packets {32 data bits, round number}
     // (comm.cuh: ll_store / ll_load): the block that finishes an interface stores this rank's two totals straight into
