@@ -13,6 +13,7 @@
 // One launch; the summation order is fixed, so results are bitwise reproducible run to run.
 // ------------------------------------------------------------------------------------------------
 #define IF_THREADS 256
+#define IF_MAXW 64  // Gauss points per bin whose half weights are kept in shared memory
 
 #ifdef HELIOS_INTEG_TIMING  // experiment builds only (scripts/exp_integ_timing.py): phase stamps of one block, SM cycles
 __device__ long long g_integ_t[8];
@@ -49,6 +50,8 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     ISTAMP(0);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     ISTAMP(1);
+    __shared__ double s_hw[IF_MAXW];  // 0.5 * gauss_weight[y]
+    if ((int)threadIdx.x < ny && ny <= IF_MAXW) s_hw[threadIdx.x] = 0.5 * gauss_weight[threadIdx.x];  // (barrier: after staging)
     const int pitch = ny + 1;  // odd pitch keeps the per-bin reads off one bank
     double* s_dn = sm;
     double* s_up = sm + (size_t)xb * pitch;
@@ -70,9 +73,9 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         const size_t base = ((size_t)i * nbin + x0) * ny;
         if (ny > 1) {
             const int n = nx * ny;
-            // four rounds of loads in flight per thread before the first is consumed: the staging is a handful of
+            // six rounds of loads in flight per thread before the first is consumed: the staging is a handful of
             // round trips to HBM, and a loop that stores each value as it arrives pays every one of them in full
-            constexpr int U = 4;
+            constexpr int U = 6;
             for (int k0 = threadIdx.x; k0 < n; k0 += blockDim.x * U) {
                 double v_dn[U], v_up[U], v_dr[U];
 #pragma unroll
@@ -102,11 +105,35 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
             double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
             if (ny > 1) {
-                for (int y = 0; y < ny; y++) {
-                    const double hw = 0.5 * gauss_weight[y];
-                    a_dr += hw * s_dr[xl * pitch + y];
-                    a_up += hw * s_up[xl * pitch + y];
-                    a_dn += hw * s_dn[xl * pitch + y];
+                // half weights from shared memory (a global load per Gauss point sat in the dependent chain: 135 cycles
+                // per point, phase stamps of scripts/exp_integ_timing.py), four points in flight; same operations, same order
+                const double* __restrict__ r_dr = s_dr + xl * pitch;
+                const double* __restrict__ r_up = s_up + xl * pitch;
+                const double* __restrict__ r_dn = s_dn + xl * pitch;
+                int y = 0;
+                if (ny <= IF_MAXW) {
+                    for (; y + 4 <= ny; y += 4) {  // all sixteen loads first, then the adds in y order
+                        double w[4], v_dr[4], v_up[4], v_dn[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            w[u] = s_hw[y + u];
+                            v_dr[u] = r_dr[y + u];
+                            v_up[u] = r_up[y + u];
+                            v_dn[u] = r_dn[y + u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            a_dr += w[u] * v_dr[u];
+                            a_up += w[u] * v_up[u];
+                            a_dn += w[u] * v_dn[u];
+                        }
+                    }
+                }
+                for (; y < ny; y++) {
+                    const double hw = ny <= IF_MAXW ? s_hw[y] : 0.5 * gauss_weight[y];
+                    a_dr += hw * r_dr[y];
+                    a_up += hw * r_up[y];
+                    a_dn += hw * r_dn[y];
                 }
             } else {  // opacity sampling: one point per bin, consecutive threads read consecutive bins
                 const double hw = 0.5 * gauss_weight[0];
