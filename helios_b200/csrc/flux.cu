@@ -13,6 +13,10 @@
 // One launch; the summation order is fixed, so results are bitwise reproducible run to run.
 // ------------------------------------------------------------------------------------------------
 #define IF_THREADS 256
+#ifndef IF_YB
+#define IF_YB 4  // Gauss points whose loads are in flight together
+#endif
+#define IF_BLOCKS_PER_SM 5
 #define IF_MAXW 64  // Gauss points per bin whose half weights are kept in shared memory
 
 #ifdef HELIOS_INTEG_TIMING  // experiment builds only (scripts/exp_integ_timing.py): phase stamps of one block, SM cycles
@@ -37,7 +41,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return r;
 }
 
-__global__ void __launch_bounds__(IF_THREADS)
+// 5 blocks per SM (<= 51 registers): the C2 grid of 6 x 101 blocks is then ONE wave (740 slots); at 58 registers it was
+// 592 slots and a second wave of 14 blocks doubled the kernel's duration
+__global__ void __launch_bounds__(IF_THREADS, IF_BLOCKS_PER_SM)
 k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict__ F_up_wg,
                  const double* __restrict__ F_dir_wg, double* __restrict__ F_down_band,
                  double* __restrict__ F_up_band, double* __restrict__ F_dir_band,
@@ -73,9 +79,10 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         const size_t base = ((size_t)i * nbin + x0) * ny;
         if (ny > 1) {
             const int n = nx * ny;
-            // six rounds of loads in flight per thread before the first is consumed: the staging is a handful of
+            // two rounds of loads in flight per thread before the first is consumed (more would spill at the register budget
+            // of IF_BLOCKS_PER_SM): the staging is a handful of
             // round trips to HBM, and a loop that stores each value as it arrives pays every one of them in full
-            constexpr int U = 6;
+            constexpr int U = 2;
             for (int k0 = threadIdx.x; k0 < n; k0 += blockDim.x * U) {
                 double v_dn[U], v_up[U], v_dr[U];
 #pragma unroll
@@ -112,17 +119,17 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                 const double* __restrict__ r_dn = s_dn + xl * pitch;
                 int y = 0;
                 if (ny <= IF_MAXW) {
-                    for (; y + 4 <= ny; y += 4) {  // all sixteen loads first, then the adds in y order
-                        double w[4], v_dr[4], v_up[4], v_dn[4];
+                    for (; y + IF_YB <= ny; y += IF_YB) {  // the loads of IF_YB points first, then the adds in y order
+                        double w[IF_YB], v_dr[IF_YB], v_up[IF_YB], v_dn[IF_YB];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
+                        for (int u = 0; u < IF_YB; u++) {
                             w[u] = s_hw[y + u];
                             v_dr[u] = r_dr[y + u];
                             v_up[u] = r_up[y + u];
                             v_dn[u] = r_dn[y + u];
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
+                        for (int u = 0; u < IF_YB; u++) {
                             a_dr += w[u] * v_dr[u];
                             a_up += w[u] * v_up[u];
                             a_dn += w[u] * v_dn[u];
@@ -606,11 +613,11 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
     const size_t smem = (size_t)3 * xb * (ny + 1) * sizeof(double);
     HBATCHDIMS(ctx, numinterfaces == ctx->batch.nint() && nbin == ctx->batch.nbin && ny == ctx->batch.ny);
     const int nb = ctx->batch.nbatch;
-    // blocks per (atmosphere, interface): one per x-tile while that keeps a single atmosphere's grid within ~8 blocks per
+    // blocks per (atmosphere, interface): one per x-tile while that keeps a single atmosphere's grid within IF_BLOCKS_PER_SM blocks per
     // SM, else a block walks several tiles.  Independent of the batch size: the summation order of an atmosphere is the
     // same alone and in a batch (bit-for-bit equality of the two paths, tests/test_gpu_batch.py).
     int ntile = ceil_div(nbin, xb);
-    const int cap = ctx->num_sms * 8 / numinterfaces;
+    const int cap = ctx->num_sms * IF_BLOCKS_PER_SM / numinterfaces;  // one wave
     if (ntile > cap) ntile = cap < 1 ? 1 : cap;
     dim3 grid(ntile, numinterfaces, nb);
     // per-block partial sums (transient, scratch) and one ticket per (atmosphere, interface) (persistent, zeroed)
