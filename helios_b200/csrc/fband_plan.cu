@@ -99,10 +99,6 @@ __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {  // 
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// Programmatic dependent launch: once every CTA of this grid has passed here (or exited), a following launch that allows
-// it (helios_integrate_flux_double) is scheduled into the SMs' free slots and waits, at its griddepcontrol.wait, for
-// this grid to complete -- its launch latency overlaps the last tiles instead of following them.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- the passes -------------------
@@ -402,7 +398,6 @@ k_sweep_iso(double* __restrict__ F_down, double* __restrict__ F_up, const double
         const double A_s = cbuf[cw * 4 + 2];
         __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
         if (ct + gridDim.x < total) issue(ct + gridDim.x);
-        else pdl_launch_dependents();  // last tile of this CTA: a dependent launch (the band integration) may move in
         const bool skip = done_flag != 0;  // uniform per CTA
 
         double F_out = 0.0;
@@ -676,7 +671,6 @@ k_sweep_noniso(double* __restrict__ F_down, double* __restrict__ F_up, double* _
         const double A_s = cbuf[2];
         __syncthreads();  // every thread has read the staging areas: the next tile's copies may overwrite them
         if (ct + gridDim.x < total) issue(ct + gridDim.x);
-        else pdl_launch_dependents();  // last tile of this CTA: a dependent launch (the band integration) may move in
         const bool skip = done_flag != 0;  // uniform per CTA
 
         double F_out = 0.0;

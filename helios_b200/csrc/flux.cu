@@ -43,6 +43,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 
 // 5 blocks per SM (<= 51 registers): the C2 grid of 6 x 101 blocks is then ONE wave (740 slots); at 58 registers it was
 // 592 slots and a second wave of 14 blocks doubled the kernel's duration
+template <bool NY1>  // NY1: one point per bin (opacity sampling), no staging, next tile prefetched
 __global__ void __launch_bounds__(IF_THREADS, IF_BLOCKS_PER_SM)
 k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict__ F_up_wg,
                  const double* __restrict__ F_dir_wg, double* __restrict__ F_down_band,
@@ -51,10 +52,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                  const double* __restrict__ deltalambda, double* __restrict__ partial, unsigned* __restrict__ ticket,
                  double* __restrict__ F_down_tot, double* __restrict__ F_up_tot, double* __restrict__ F_net, FusedComm fc) {
     extern __shared__ double sm[];
-    // launched with programmatic stream serialisation: the blocks may be resident before the preceding grid (the flux
-    // sweep) has finished; nothing it wrote is read before this point (a no-op for an ordinary launch)
     ISTAMP(0);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     ISTAMP(1);
     __shared__ double s_hw[IF_MAXW];  // 0.5 * gauss_weight[y]
     if ((int)threadIdx.x < ny && ny <= IF_MAXW) s_hw[threadIdx.x] = 0.5 * gauss_weight[threadIdx.x];  // (barrier: after staging)
@@ -73,11 +71,27 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
     // wavelength integral in registers across them.
     double t_up = 0.0, t_dn = 0.0;  // this thread's bins in the sum over wavelength
     const int ntiles = (nbin + xb - 1) / xb;
+    // ny == 1 (opacity sampling, one thread per bin, no staging): the values of the block's NEXT tile are requested before
+    // the current one is consumed -- a block walks up to ~60 tiles, and each used to wait for its own loads
+    double p_dr = 0.0, p_up = 0.0, p_dn = 0.0, p_dl = 0.0;
+    auto fetch1 = [&](int tile) {
+        const int x = tile * xb + (int)threadIdx.x;
+        if (tile < ntiles && (int)threadIdx.x < xb && x < nbin) {
+            const size_t k = (size_t)i * nbin + x;
+            p_dr = F_dir_wg[k];
+            p_up = F_up_wg[k];
+            p_dn = F_down_wg[k];
+            p_dl = deltalambda[x];
+        }
+    };
+    if (NY1) fetch1(blockIdx.x);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int x0 = tile * xb;
         const int nx = min(xb, nbin - x0);
         const size_t base = ((size_t)i * nbin + x0) * ny;
-        if (ny > 1) {
+        const double c_dr = p_dr, c_up = p_up, c_dn = p_dn, c_dl = p_dl;
+        if (NY1) fetch1(tile + gridDim.x);
+        if (!NY1) {
             const int n = nx * ny;
             // two rounds of loads in flight per thread before the first is consumed (more would spill at the register budget
             // of IF_BLOCKS_PER_SM): the staging is a handful of
@@ -111,7 +125,7 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
         }
         for (int xl = threadIdx.x; xl < nx; xl += blockDim.x) {
             double a_dn = 0.0, a_up = 0.0, a_dr = 0.0;
-            if (ny > 1) {
+            if (!NY1) {
                 // half weights from shared memory (a global load per Gauss point sat in the dependent chain: 135 cycles
                 // per point, phase stamps of scripts/exp_integ_timing.py), four points in flight; same operations, same order
                 const double* __restrict__ r_dr = s_dr + xl * pitch;
@@ -142,20 +156,21 @@ k_band_integrate(const double* __restrict__ F_down_wg, const double* __restrict_
                     a_up += hw * r_up[y];
                     a_dn += hw * r_dn[y];
                 }
-            } else {  // opacity sampling: one point per bin, consecutive threads read consecutive bins
+            } else {  // opacity sampling: one point per bin, consecutive threads read consecutive bins (xl == threadIdx.x)
                 const double hw = 0.5 * gauss_weight[0];
-                a_dr += hw * F_dir_wg[base + xl];
-                a_up += hw * F_up_wg[base + xl];
-                a_dn += hw * F_down_wg[base + xl];
+                a_dr += hw * c_dr;
+                a_up += hw * c_up;
+                a_dn += hw * c_dn;
             }
             const size_t o = (size_t)i * nbin + x0 + xl;
             F_dir_band[o] = a_dr;
             F_up_band[o] = a_up;
             F_down_band[o] = a_dn;
-            t_up += a_up * deltalambda[x0 + xl];
-            t_dn += (a_dr + a_dn) * deltalambda[x0 + xl];
+            const double dl = NY1 ? c_dl : deltalambda[x0 + xl];
+            t_up += a_up * dl;
+            t_dn += (a_dr + a_dn) * dl;
         }
-        if (ny > 1) __syncthreads();  // the next tile overwrites the staging area
+        if (!NY1) __syncthreads();  // the next tile overwrites the staging area
         ISTAMP(3);
     }
     // Sum over wavelength in the same launch (K:2484-2509): fixed tree over this block's bins, then the LAST block
@@ -644,22 +659,16 @@ int helios_integrate_flux_double(helios_ctx* ctx, const double* deltalambda, dou
         helios_set_error("helios_integrate_flux_double: the fused flux all-reduce is not available in batch mode");
         return HELIOS_ERR_STATE;
     }
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(IF_THREADS);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        double* part = scratch + 8;
-        HCUDA(cudaLaunchKernelEx(&cfg, k_band_integrate, F_down_wg, F_up_wg, F_dir_wg, F_down_band, F_up_band, F_dir_band,
-                                 gauss_weight, nbin, ny, xb, deltalambda, part, ctx->integ_ticket, F_down_tot, F_up_tot,
-                                 F_net, fc));
-    }
+    if (ny == 1)
+        k_band_integrate<true><<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band, F_up_band,
+                                                                        F_dir_band, gauss_weight, nbin, ny, xb, deltalambda,
+                                                                        scratch + 8, ctx->integ_ticket, F_down_tot,
+                                                                        F_up_tot, F_net, fc);
+    else
+        k_band_integrate<false><<<grid, IF_THREADS, smem, ctx->stream>>>(F_down_wg, F_up_wg, F_dir_wg, F_down_band, F_up_band,
+                                                                         F_dir_band, gauss_weight, nbin, ny, xb, deltalambda,
+                                                                         scratch + 8, ctx->integ_ticket, F_down_tot,
+                                                                         F_up_tot, F_net, fc);
     HLAUNCHED(ctx);
     return HELIOS_OK;
 }
