@@ -162,3 +162,38 @@ def test_upward_weights_are_the_downward_ones_swapped_bit_for_bit():
     for upper in (True, False):
         _, _, _, k1d, k2d, _, k1u, k2u = plan_half(w0, M, N, P, dt, g0, E, Dd, Du, upper, 0.5, 1e-4)
         assert np.array_equal(k1u, k2d) and np.array_equal(k2u, k1d)
+
+
+def test_multiply_high_division_of_the_sweep_launchers():
+    """the sweeps map column -> bin (divide by ny) and CTA tile -> atmosphere (divide by the tiles per atmosphere) with
+    one multiply-high by floor(2^32 / d) + 1 (fband_plan.cu: bin_of, atm_of, tile_magic); the launchers only allow it
+    while n * d < 2^32 for every n that occurs, where it is exact -- checked here at the range ends and on a sweep"""
+    for d in (2, 3, 5, 7, 16, 20, 21, 32, 45, 100, 963, 1925, 12500):
+        magic = (1 << 32) // d + 1
+        limit = ((1 << 32) - 1) // d  # the launchers' bound: n * d < 2^32
+        for n in np.unique(np.concatenate([np.arange(0, 4096), np.arange(limit - 4096, limit + 1),
+                                           np.random.default_rng(d).integers(0, limit + 1, 20000)])).astype(np.uint64):
+            if int(n) * d >= (1 << 32) or n < 0:
+                continue
+            assert (int(n) * magic) >> 32 == int(n) // d, (d, int(n))
+
+
+def test_staging_pitch_rule():
+    """column pitch of the staged flux rows (CtaShape::cpitch): the smallest pitch >= rs that is (16 / columns) * odd,
+    which puts the column starts of a cooperative 8-byte access 16 / columns bank pairs apart (conflict-free for the
+    copiers, lanes along the columns, and for the owners, lanes along one column)"""
+    def cpitch(rs, ncol):
+        st = 1 if ncol >= 16 else 16 // ncol
+        v = rs
+        while v % (2 * st) != st:
+            v += 1
+        return v
+
+    for ncol, lanes_per_col in ((4, 8), (8, 4)):  # a warp request: ncol columns x 32 / ncol slots
+        for rs in range(2, 34, 2):
+            cp = cpitch(rs, ncol)
+            assert rs <= cp < rs + 2 * (16 // ncol) and (cp // (16 // ncol)) % 2 == 1
+            for l0 in range(0, 32, lanes_per_col):
+                offs = [c * cp + l0 + l for l in range(lanes_per_col) for c in range(ncol)]
+                for half in (offs[:16], offs[16:]):  # 8-byte accesses are served per half-warp over 16 bank pairs
+                    assert len({o % 16 for o in half}) == 16, (ncol, rs, cp)
