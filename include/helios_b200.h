@@ -491,7 +491,8 @@ int helios_integrate_beamflux(helios_ctx* ctx, double* F_dir_tot, const double* 
  * (cudaIpc-mapped), then sums the slots in rank order, so all ranks get bitwise-identical totals.
  * No reference counterpart (the reference is single-GPU). */
 #define HELIOS_IPC_HANDLE_BYTES 64
-/* allocate this rank's mailbox (world*slot_doubles doubles + flags) and export its IPC handle */
+/* allocate this rank's mailbox (two banks of world*slot_doubles doubles + flags for the stand-alone kernel, the same
+ * again as 16-byte packet pairs for the fused form) and export its IPC handle */
 int helios_comm_create(helios_ctx* ctx, int rank, int world, int slot_doubles,
                        unsigned char* handle_out /* HELIOS_IPC_HANDLE_BYTES */);
 /* map the peers' mailboxes; handles = world consecutive handles (own entry ignored) */
@@ -504,8 +505,9 @@ int helios_comm_allreduce_sum(helios_ctx* ctx, double* vec, int n);
  * slot_doubles must be >= 2*numinterfaces. */
 int helios_comm_allreduce_flux_totals(helios_ctx* ctx, double* F_up_tot, double* F_down_tot, double* F_net,
                                       int numinterfaces);
-/* on != 0: helios_integrate_flux_double performs the flux-total exchange in its own launch (the block that finishes the
- * last interface pushes / waits / sums over the peer mailboxes); helios_comm_allreduce_flux_totals must then NOT be
+/* on != 0: helios_integrate_flux_double performs the flux-total exchange in its own launch (the block that finishes an
+ * interface pushes this rank's two totals to every mailbox as self-validating {data, round} packets -- no fence, no flag;
+ * the block that finishes the last interface polls its own mailbox and sums the slots in rank order); helios_comm_allreduce_flux_totals must then NOT be
  * called for that step.  Every rank has to make the same sequence of exchanging calls. */
 int helios_comm_set_fused(helios_ctx* ctx, int on);
 int helios_comm_destroy(helios_ctx* ctx);
