@@ -28,7 +28,10 @@
 // scans are pass-invariant and hoisted (scan_setup); the reference's tiny-value clean-up is replaced by a sign-bit vote
 // per tile with an exact redo (clean<>).  Measured on B200: the first build of this file, one warp per
 // column with per-lane 8-byte copies, spent 16 of its 46 us per C2 solve in the flux stores and 8 us in the flux loads
-// (25 wavefronts per LSU instruction); the cooperative staging brought the solve to 44 us.
+// (25 wavefronts per LSU instruction); the cooperative staging brought the solve to 44 us.  The global side of the staging
+// then took it to 38 us: 16-byte cp.async.cg column pairs instead of 8-byte copies through L1 (flux_pairs), Planck values
+// staged once per CTA when its columns share a bin (one_bin), tile-invariant index arithmetic formed at its use instead
+// of living in registers across the passes (FluxMap / PairMap), the batch's converged flag requested before the waits.
 #include "common.cuh"
 #include "sweep_math.cuh"
 #include "fband_plan.cuh"
