@@ -3,7 +3,11 @@ import ctypes
 import os
 import subprocess
 
+import pytest
+
 from helios_b200 import backend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_header_declares_the_hot_path():
@@ -52,3 +56,33 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_product_fails_loudly_without_the_library_or_a_gpu(tmp_path, monkeypatch):
+    """no CPU fallback anywhere on the product path: a missing libhelios_b200.so raises BackendMissing on first use, and
+    with the library present but no GPU the first entry point that needs the device (context creation) raises -- it does
+    not silently compute on the host"""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from helios_b200 import backend\n"
+        "backend.LIB_PATH = %r\n"
+        "try:\n"
+        "    backend.lib()\n"
+        "except backend.BackendMissing as e:\n"
+        "    print('MISSING-OK', 'no CPU fallback' in str(e))\n"
+        "else:\n"
+        "    print('LOADED-WITHOUT-LIBRARY')\n"
+    ) % (ROOT, str(tmp_path / "absent" / "libhelios_b200.so"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120).stdout
+    assert "MISSING-OK True" in out, out
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        from helios_b200 import backend
+        with pytest.raises(backend.HeliosError):
+            backend.Context(0)
